@@ -1,0 +1,266 @@
+// C-ABI compute entries: graph convolution forward/backward (Chebyshev / Monomial),
+// bias+activation, pseudo-convolutions.  Each entry is a short sequence of launches of the
+// kernels in ds_spmm.cu / ds_gemm.cu / ds_umma.cu on the caller's stream.
+#include "ds_common.cuh"
+
+namespace ds {
+
+// tensor-core contraction (ds_umma.cu).  Returns -1 when the shape is not supported by
+// the tcgen05 path (caller then reports an error; there is no silent fallback).
+int umma_supported(int64_t Kc, int nseg, int64_t N);
+int launch_umma_gemm_nn(int64_t R, int64_t N, int64_t Kc, int nseg, const float* A0, const float* Arest,
+                        int64_t a_seg_stride, const float* Bm, int64_t b_kc_stride, int64_t b_seg_stride,
+                        const float* bias, int act, float* C, int mode, cudaStream_t st);
+
+namespace {
+
+int check_common(const ds_plan_t* plan, int32_t recursion, int32_t K, int64_t B, int64_t Fin, int64_t Fout,
+                 int32_t act, int32_t mode, const char* who) {
+  DS_CHECK(plan != nullptr, "%s: NULL plan", who);
+  DS_CHECK(recursion == DS_RECURSION_CHEBYSHEV || recursion == DS_RECURSION_MONOMIAL, "%s: bad recursion %d", who,
+           recursion);
+  DS_CHECK(K >= 1, "%s: K must be >= 1 (got %d)", who, K);
+  DS_CHECK(B >= 1 && Fin >= 1 && Fout >= 1, "%s: empty shape B=%lld Fin=%lld Fout=%lld", who, (long long)B,
+           (long long)Fin, (long long)Fout);
+  DS_CHECK(act >= DS_ACT_LINEAR && act <= DS_ACT_SOFTPLUS, "%s: unknown activation id %d", who, act);
+  DS_CHECK(mode >= DS_MODE_FP32 && mode <= DS_MODE_TF32X3, "%s: unknown mode %d", who, mode);
+  return 0;
+}
+
+// T_1..T_{K-1} into basis ([K-1, B, M, Fin]); T_0 = x
+int compute_basis(const SparseDev& S, int32_t recursion, int32_t K, int64_t B, int64_t Fin, const float* x,
+                  float* basis, cudaStream_t st) {
+  const int64_t A = B * S.M * Fin;
+  auto T = [&](int k) -> const float* { return k == 0 ? x : basis + (int64_t)(k - 1) * A; };
+  for (int k = 1; k < K; ++k) {
+    float* out = basis + (int64_t)(k - 1) * A;
+    if (recursion == DS_RECURSION_CHEBYSHEV && k >= 2) {
+      DS_TRY(launch_spmm(S, B, Fin, T(k - 1), 2.f, T(k - 2), -1.f, nullptr, 0.f, out, st));  // gnn_layers.py:141
+    } else {
+      DS_TRY(launch_spmm(S, B, Fin, T(k - 1), 1.f, nullptr, 0.f, nullptr, 0.f, out, st));  // :138 / :288
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace ds
+
+extern "C" {
+
+int64_t ds_graph_conv_basis_elems(int64_t M, int64_t B, int64_t Fin, int32_t K) {
+  return K > 1 ? (int64_t)(K - 1) * B * M * Fin : 0;
+}
+
+int ds_graph_conv_forward(const ds_plan_t* plan, int32_t recursion, int32_t K, int64_t B, int64_t Fin, int64_t Fout,
+                          const float* x, const float* kernel, const float* bias, int32_t act, float* y, float* basis,
+                          int32_t mode, void* stream) {
+  using namespace ds;
+  DS_TRY(check_common(plan, recursion, K, B, Fin, Fout, act, mode, "ds_graph_conv_forward"));
+  DS_CHECK(x && kernel && y, "ds_graph_conv_forward: NULL tensor");
+  DS_CHECK(K == 1 || basis != nullptr, "ds_graph_conv_forward: basis workspace required for K > 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t M = plan->M, R = B * M, A = R * Fin;
+  DS_TRY(compute_basis(plan->fwd, recursion, K, B, Fin, x, basis, st));
+  if (mode == DS_MODE_FP32) {
+    return launch_gemm_nn(R, Fout, Fin, K, x, basis, A, Fin, kernel, Fout, K, 1, bias, Fout, act, y, Fout, st);
+  }
+  DS_CHECK(umma_supported(Fin, K, Fout) == 0,
+           "ds_graph_conv_forward: tensor-core mode needs Fin %% 8 == 0 and Fout %% 16 == 0, 16 <= Fout <= 256 "
+           "(got Fin=%lld Fout=%lld); use DS_MODE_FP32",
+           (long long)Fin, (long long)Fout);
+  return launch_umma_gemm_nn(R, Fout, Fin, K, x, basis, A, kernel, K, 1, bias, act, y, mode, st);
+}
+
+int64_t ds_graph_conv_backward_workspace_elems(int64_t M, int64_t B, int64_t Fin, int64_t Fout, int32_t K,
+                                               int32_t have_basis, int32_t act) {
+  using namespace ds;
+  const int64_t R = B * M, A = R * Fin;
+  int64_t n = 0;
+  if (act != DS_ACT_LINEAR) n += R * Fout;                  // dz
+  if (!have_basis && K > 1) n += (int64_t)(K - 1) * A;      // recomputed basis
+  n += 4 * A;                                               // G_k + three Clenshaw buffers
+  n += gemm_tn_workspace_elems(R, Fin, K, Fout);            // dkernel split partials
+  n += colsum_workspace_elems(Fout);                        // dbias partials
+  return n + 64;
+}
+
+int ds_graph_conv_backward(const ds_plan_t* plan, int32_t recursion, int32_t K, int64_t B, int64_t Fin, int64_t Fout,
+                           const float* x, const float* kernel, const float* y, const float* dy, int32_t act,
+                           const float* basis, float* dx, float* dkernel, float* dbias, float* workspace, int32_t mode,
+                           void* stream) {
+  using namespace ds;
+  DS_TRY(check_common(plan, recursion, K, B, Fin, Fout, act, mode, "ds_graph_conv_backward"));
+  DS_CHECK(x && kernel && dy && dkernel && workspace, "ds_graph_conv_backward: NULL tensor");
+  DS_CHECK(act == DS_ACT_LINEAR || y != nullptr, "ds_graph_conv_backward: y required when act != LINEAR");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t M = plan->M, R = B * M, A = R * Fin;
+  float* ws = workspace;
+  auto take = [&](int64_t n) { float* p = ws; ws += (n + 3) / 4 * 4; return p; };
+
+  // 1. gradient w.r.t. the pre-activation
+  const float* dz = dy;
+  if (act != DS_ACT_LINEAR) {
+    float* dzb = take(R * Fout);
+    DS_TRY(launch_act_backward(R, Fout, Fout, y, dy, act, dzb, st));
+    dz = dzb;
+  }
+  // 2. basis (saved by the forward or recomputed)
+  const float* T = basis;
+  if (T == nullptr && K > 1) {
+    float* tb = take((int64_t)(K - 1) * A);
+    DS_TRY(compute_basis(plan->fwd, recursion, K, B, Fin, x, tb, st));
+    T = tb;
+  }
+  float* G = take(A);
+  float* buf[3] = {take(A), take(A), take(A)};
+  float* tn_partial = take(gemm_tn_workspace_elems(R, Fin, K, Fout));
+  float* cs_partial = take(colsum_workspace_elems(Fout));
+
+  // 3. dbias = sum_{b,m} dz
+  if (dbias != nullptr) DS_TRY(launch_colsum(R, Fout, Fout, dz, dbias, cs_partial, st));
+  // 4. dkernel[f*K + k, o] = sum_{b,m} T_k[b,m,f] dz[b,m,o]
+  DS_TRY(launch_gemm_tn(R, Fout, Fin, K, x, T, A, Fin, dz, Fout, dkernel, Fout, K, 1, tn_partial, st));
+  if (dx == nullptr) return 0;
+
+  // 5. dx = sum_k T_k(L~^T) G_k,  G_k[b,m,f] = sum_o dz[b,m,o] kernel[f*K + k, o]   (Clenshaw / Horner)
+  auto make_G = [&](int k, float* out) {
+    return launch_gemm_nt(R, Fin, Fout, 1, dz, Fout, kernel + (int64_t)k * Fout, Fout, K, 0, nullptr, 1,
+                          DS_ACT_LINEAR, out, Fin, 0, st);
+  };
+  const SparseDev& St = plan->bwd;
+  if (K == 1) return make_G(0, dx);
+  const bool cheb = recursion == DS_RECURSION_CHEBYSHEV;
+  int cur = 0, old = -1, nxt = 1;
+  DS_TRY(make_G(K - 1, buf[cur]));  // b_{K-1} = G_{K-1}
+  for (int k = K - 2; k >= 1; --k) {
+    DS_TRY(make_G(k, G));
+    // Chebyshev: b_k = G_k + 2 L^T b_{k+1} - b_{k+2};   Monomial: h_k = G_k + L^T h_{k+1}
+    DS_TRY(launch_spmm(St, B, Fin, buf[cur], cheb ? 2.f : 1.f, (cheb && old >= 0) ? buf[old] : nullptr, -1.f, G, 1.f,
+                       buf[nxt], st));
+    const int freed = old >= 0 ? old : 3 - cur - nxt;
+    old = cur;
+    cur = nxt;
+    nxt = freed;
+  }
+  DS_TRY(make_G(0, G));
+  // Chebyshev: dx = G_0 + L^T b_1 - b_2;   Monomial: dx = G_0 + L^T h_1
+  return launch_spmm(St, B, Fin, buf[cur], 1.f, (cheb && old >= 0) ? buf[old] : nullptr, -1.f, G, 1.f, dx, st);
+}
+
+int ds_bias_act_forward(int64_t R, int64_t F, const float* z, const float* bias, int32_t act, float* y, void* stream);
+int ds_bias_act_backward(int64_t R, int64_t F, const float* y, const float* dy, int32_t act, float* dz, float* dbias,
+                         float* workspace, void* stream) {
+  using namespace ds;
+  DS_CHECK(dy && dz && R > 0 && F > 0, "ds_bias_act_backward: bad argument");
+  DS_CHECK(act == DS_ACT_LINEAR || y != nullptr, "ds_bias_act_backward: y required");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (act != DS_ACT_LINEAR) DS_TRY(launch_act_backward(R, F, F, y, dy, act, dz, st));
+  else if (dz != dy) DS_CUDA(cudaMemcpyAsync(dz, dy, sizeof(float) * R * F, cudaMemcpyDeviceToDevice, st));
+  if (dbias != nullptr) {
+    DS_CHECK(workspace != nullptr, "ds_bias_act_backward: workspace required for dbias");
+    DS_TRY(launch_colsum(R, F, F, dz, dbias, workspace, st));
+  }
+  return 0;
+}
+
+// ---- pseudo convolutions (healpy_layers.py:87-216) as GEMMs over NESTED-contiguous children ----
+
+static int pconv_check(int64_t B, int64_t M, int64_t Fin, int64_t Fout, int32_t p, int32_t act, int32_t mode,
+                       bool reduce, const char* who) {
+  using namespace ds;
+  DS_CHECK(p >= 1 && p <= 12, "%s: p=%d out of range", who, p);
+  DS_CHECK(B >= 1 && M >= 1 && Fin >= 1 && Fout >= 1, "%s: empty shape", who);
+  DS_CHECK(!reduce || M % (1LL << (2 * p)) == 0, "%s: M=%lld not divisible by 4^p=%lld", who, (long long)M,
+           (long long)(1LL << (2 * p)));
+  DS_CHECK(act >= DS_ACT_LINEAR && act <= DS_ACT_SOFTPLUS, "%s: unknown activation id %d", who, act);
+  DS_CHECK(mode >= DS_MODE_FP32 && mode <= DS_MODE_TF32X3, "%s: unknown mode %d", who, mode);
+  return 0;
+}
+
+int ds_pconv_forward(int64_t B, int64_t M, int64_t Fin, int64_t Fout, int32_t p, const float* x, const float* w,
+                     const float* bias, int32_t act, float* y, int32_t mode, void* stream) {
+  using namespace ds;
+  DS_TRY(pconv_check(B, M, Fin, Fout, p, act, mode, true, "ds_pconv_forward"));
+  DS_CHECK(x && w && y, "ds_pconv_forward: NULL tensor");
+  const int64_t r = 1LL << (2 * p), Ro = B * (M / r), Kc = r * Fin;
+  return launch_gemm_nn(Ro, Fout, Kc, 1, x, nullptr, 0, Kc, w, Fout, 1, 0, bias, Fout, act, y, Fout,
+                        (cudaStream_t)stream);
+}
+
+int64_t ds_pconv_backward_workspace_elems(int64_t B, int64_t M, int64_t Fin, int64_t Fout, int32_t p, int32_t act) {
+  using namespace ds;
+  const int64_t r = 1LL << (2 * p), Ro = B * (M / r), Kc = r * Fin;
+  return (act != DS_ACT_LINEAR ? Ro * Fout : 0) + gemm_tn_workspace_elems(Ro, Kc, 1, Fout) +
+         colsum_workspace_elems(Fout) + 64;
+}
+
+int ds_pconv_backward(int64_t B, int64_t M, int64_t Fin, int64_t Fout, int32_t p, const float* x, const float* w,
+                      const float* y, const float* dy, int32_t act, float* dx, float* dw, float* dbias,
+                      float* workspace, int32_t mode, void* stream) {
+  using namespace ds;
+  DS_TRY(pconv_check(B, M, Fin, Fout, p, act, mode, true, "ds_pconv_backward"));
+  DS_CHECK(x && w && dy && dw && workspace, "ds_pconv_backward: NULL tensor");
+  DS_CHECK(act == DS_ACT_LINEAR || y != nullptr, "ds_pconv_backward: y required when act != LINEAR");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t r = 1LL << (2 * p), Ro = B * (M / r), Kc = r * Fin;
+  float* ws = workspace;
+  auto take = [&](int64_t n) { float* q = ws; ws += (n + 3) / 4 * 4; return q; };
+  const float* dz = dy;
+  if (act != DS_ACT_LINEAR) {
+    float* dzb = take(Ro * Fout);
+    DS_TRY(launch_act_backward(Ro, Fout, Fout, y, dy, act, dzb, st));
+    dz = dzb;
+  }
+  float* tn_partial = take(gemm_tn_workspace_elems(Ro, Kc, 1, Fout));
+  float* cs_partial = take(colsum_workspace_elems(Fout));
+  if (dbias) DS_TRY(launch_colsum(Ro, Fout, Fout, dz, dbias, cs_partial, st));
+  DS_TRY(launch_gemm_tn(Ro, Fout, Kc, 1, x, nullptr, 0, Kc, dz, Fout, dw, Fout, 1, 0, tn_partial, st));
+  if (dx) DS_TRY(launch_gemm_nt(Ro, Kc, Fout, 1, dz, Fout, w, Fout, 1, 0, nullptr, 1, DS_ACT_LINEAR, dx, Kc, 0, st));
+  return 0;
+}
+
+int ds_pconvT_forward(int64_t B, int64_t M, int64_t Fin, int64_t Fout, int32_t p, const float* x, const float* w,
+                      const float* bias, int32_t act, float* y, int32_t mode, void* stream) {
+  using namespace ds;
+  DS_TRY(pconv_check(B, M, Fin, Fout, p, act, mode, false, "ds_pconvT_forward"));
+  DS_CHECK(x && w && y, "ds_pconvT_forward: NULL tensor");
+  const int64_t r = 1LL << (2 * p), R = B * M, Nc = r * Fout;
+  return launch_gemm_nt(R, Nc, Fin, 1, x, Fin, w, Fin, 1, 0, bias, Fout, act, y, Nc, 0, (cudaStream_t)stream);
+}
+
+int64_t ds_pconvT_backward_workspace_elems(int64_t B, int64_t M, int64_t Fin, int64_t Fout, int32_t p, int32_t act) {
+  using namespace ds;
+  const int64_t r = 1LL << (2 * p), R = B * M, Nc = r * Fout;
+  return (act != DS_ACT_LINEAR ? R * Nc : 0) + gemm_tn_workspace_elems(R, Nc, 1, Fin) + colsum_workspace_elems(Nc) +
+         64;
+}
+
+int ds_pconvT_backward(int64_t B, int64_t M, int64_t Fin, int64_t Fout, int32_t p, const float* x, const float* w,
+                       const float* y, const float* dy, int32_t act, float* dx, float* dw, float* dbias,
+                       float* workspace, int32_t mode, void* stream) {
+  using namespace ds;
+  DS_TRY(pconv_check(B, M, Fin, Fout, p, act, mode, false, "ds_pconvT_backward"));
+  DS_CHECK(x && w && dy && dw && workspace, "ds_pconvT_backward: NULL tensor");
+  DS_CHECK(act == DS_ACT_LINEAR || y != nullptr, "ds_pconvT_backward: y required when act != LINEAR");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t r = 1LL << (2 * p), R = B * M, Nc = r * Fout;
+  float* ws = workspace;
+  auto take = [&](int64_t n) { float* q = ws; ws += (n + 3) / 4 * 4; return q; };
+  const float* dz = dy;
+  if (act != DS_ACT_LINEAR) {
+    float* dzb = take(R * Nc);
+    DS_TRY(launch_act_backward(R, Nc, Fout, y, dy, act, dzb, st));
+    dz = dzb;
+  }
+  float* tn_partial = take(gemm_tn_workspace_elems(R, Nc, 1, Fin));
+  float* cs_partial = take(colsum_workspace_elems(Nc));
+  if (dbias) DS_TRY(launch_colsum(R, Nc, Fout, dz, dbias, cs_partial, st));
+  // dw[c*Fout+o, f] = sum_r dz[r, c*Fout+o] x[r, f]
+  DS_TRY(launch_gemm_tn(R, Fin, Nc, 1, dz, nullptr, 0, Nc, x, Fin, dw, Fin, 1, 0, tn_partial, st));
+  // dx[r, f] = sum_{c,o} dz[r, c*Fout+o] w[c*Fout+o, f]
+  if (dx) DS_TRY(launch_gemm_nn(R, Fin, Nc, 1, dz, nullptr, 0, Nc, w, Fin, 1, 0, nullptr, 1, DS_ACT_LINEAR, dx, Fin, st));
+  return 0;
+}
+
+}  // extern "C"

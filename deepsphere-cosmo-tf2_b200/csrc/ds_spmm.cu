@@ -1,0 +1,163 @@
+// One hop of the graph recursion as a streaming ELL SpMM (+ CSR tail):
+//   out[b,m,:] = alpha * sum_n val[m,n] * in[b, col[m,n], :] + beta * prev[b,m,:] + gamma * add[b,m,:]
+// This is the generic (any L, any F) path that replaces tf.sparse.sparse_dense_matmul
+// (utils.py:76) and the `2*... - x0` elementwise pass (gnn_layers.py:141) in one kernel,
+// in the reference's native [B, M, F] layout (no transposes, gnn_layers.py:131-132).
+//
+// Mapping: a group of LPR lanes (power of two <= 32) owns one (b, m) row and strides over
+// the row's feature vector in float4 (F % 4 == 0) or scalar steps, so global loads of a
+// gathered row are contiguous.  Rows are walked in (b, m) order: consecutive groups gather
+// from neighbouring pixels (NESTED order keeps graph neighbours close in memory), so the
+// 9x re-use of each input row is served by L1/L2.  HBM-bound: algorithmic traffic is
+// read in + read prev + write out = 3 * B*M*F*4 bytes per hop (plan: M*W*8 bytes).
+#include "ds_common.cuh"
+
+namespace ds {
+namespace {
+
+template <int V>
+struct Vec;
+template <>
+struct Vec<1> {
+  float v[1];
+  __device__ __forceinline__ static Vec load(const float* p) { Vec r; r.v[0] = __ldg(p); return r; }
+  __device__ __forceinline__ void store(float* p) const { p[0] = v[0]; }
+};
+template <>
+struct Vec<4> {
+  float v[4];
+  __device__ __forceinline__ static Vec load(const float* p) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    Vec r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+template <int V>
+__global__ void __launch_bounds__(256) spmm_ell_kernel(const int32_t* __restrict__ ell_col,
+                                                       const float* __restrict__ ell_val, int W, int64_t M,
+                                                       int64_t B, int64_t F, const float* __restrict__ in, float alpha,
+                                                       const float* __restrict__ prev, float beta,
+                                                       const float* __restrict__ add, float gamma,
+                                                       float* __restrict__ out, int lpr_log2) {
+  const int lpr = 1 << lpr_log2;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) >> lpr_log2;
+  const int sub = (int)(tid & (lpr - 1));
+  const int64_t FV = F / V;
+  const int64_t R = B * M;
+  for (int64_t r = tid >> lpr_log2; r < R; r += n_groups) {
+    const int64_t b = r / M;
+    const int64_t m = r - b * M;
+    const float* inb = in + b * M * F;
+    const int32_t* cols = ell_col + m * W;
+    const float* vals = ell_val + m * W;
+    for (int64_t c = sub; c < FV; c += lpr) {
+      Vec<V> acc;
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc.v[i] = 0.f;
+#pragma unroll 3
+      for (int n = 0; n < W; ++n) {
+        const int32_t col = __ldg(cols + n);
+        const float w = __ldg(vals + n);
+        Vec<V> xv = Vec<V>::load(inb + (int64_t)col * F + c * V);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc.v[i] = fmaf(w, xv.v[i], acc.v[i]);
+      }
+      const int64_t off = r * F + c * V;
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc.v[i] *= alpha;
+      if (prev != nullptr) {
+        Vec<V> pv = Vec<V>::load(prev + off);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc.v[i] = fmaf(beta, pv.v[i], acc.v[i]);
+      }
+      if (add != nullptr) {
+        Vec<V> av = Vec<V>::load(add + off);
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc.v[i] = fmaf(gamma, av.v[i], acc.v[i]);
+      }
+      acc.store(out + off);
+    }
+  }
+}
+
+// rows longer than the ELL width: out[b,row,:] += alpha * sum_tail val * in[b,col,:]
+__global__ void __launch_bounds__(256) spmm_tail_kernel(const int32_t* __restrict__ tail_rows,
+                                                        const int64_t* __restrict__ tail_rowptr,
+                                                        const int32_t* __restrict__ tail_col,
+                                                        const float* __restrict__ tail_val, int64_t n_tail, int64_t M,
+                                                        int64_t B, int64_t F, const float* __restrict__ in, float alpha,
+                                                        float* __restrict__ out, int lpr_log2) {
+  const int lpr = 1 << lpr_log2;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) >> lpr_log2;
+  const int sub = (int)(tid & (lpr - 1));
+  const int64_t R = B * n_tail;
+  for (int64_t r = tid >> lpr_log2; r < R; r += n_groups) {
+    const int64_t b = r / n_tail;
+    const int64_t t = r - b * n_tail;
+    const int64_t m = tail_rows[t];
+    const int64_t p0 = tail_rowptr[t], p1 = tail_rowptr[t + 1];
+    const float* inb = in + b * M * F;
+    for (int64_t c = sub; c < F; c += lpr) {
+      float acc = 0.f;
+      for (int64_t p = p0; p < p1; ++p) acc = fmaf(__ldg(tail_val + p), __ldg(inb + (int64_t)tail_col[p] * F + c), acc);
+      out[(b * M + m) * F + c] += alpha * acc;
+    }
+  }
+}
+
+inline int ilog2_ceil(int64_t v) {
+  int l = 0;
+  while ((1LL << l) < v) ++l;
+  return l;
+}
+
+}  // namespace
+
+int launch_spmm(const SparseDev& S, int64_t B, int64_t F, const float* in, float alpha, const float* prev, float beta,
+                const float* add, float gamma, float* out, cudaStream_t st) {
+  DS_CHECK(B > 0 && F > 0, "spmm: empty batch or feature dimension");
+  DS_CHECK(in != out, "spmm: in-place hop is not supported (gather hazard)");
+  const int64_t R = B * S.M;
+  auto aligned = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec4 = (F % 4 == 0) && aligned(in) && aligned(prev) && aligned(add) && aligned(out);
+  const int V = vec4 ? 4 : 1;
+  const int lpr_log2 = std::min(5, ilog2_ceil(F / V));
+  const int threads = 256;
+  const int64_t groups_per_block = threads >> lpr_log2;
+  int64_t blocks = (R + groups_per_block - 1) / groups_per_block;
+  const int64_t max_blocks = (int64_t)num_sms() * 8 * 4;  // 8 resident CTAs/SM x 4 waves, grid-stride beyond
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (vec4) {
+    spmm_ell_kernel<4><<<(unsigned)blocks, threads, 0, st>>>(S.ell_col, S.ell_val, S.W, S.M, B, F, in, alpha, prev,
+                                                             prev ? beta : 0.f, add, add ? gamma : 0.f, out, lpr_log2);
+  } else {
+    spmm_ell_kernel<1><<<(unsigned)blocks, threads, 0, st>>>(S.ell_col, S.ell_val, S.W, S.M, B, F, in, alpha, prev,
+                                                             prev ? beta : 0.f, add, add ? gamma : 0.f, out, lpr_log2);
+  }
+  DS_LAUNCHED();
+  if (S.n_tail_rows > 0) {
+    const int tl = std::min(5, ilog2_ceil(F));
+    const int64_t gpb = threads >> tl;
+    int64_t tb = (B * S.n_tail_rows + gpb - 1) / gpb;
+    if (tb > max_blocks) tb = max_blocks;
+    spmm_tail_kernel<<<(unsigned)tb, threads, 0, st>>>(S.tail_rows, S.tail_rowptr, S.tail_col, S.tail_val,
+                                                       S.n_tail_rows, S.M, B, F, in, alpha, out, tl);
+    DS_LAUNCHED();
+  }
+  return 0;
+}
+
+}  // namespace ds
+
+extern "C" int ds_spmm(const ds_plan_t* plan, int32_t transpose, int64_t B, int64_t F, const float* in, float alpha,
+                       const float* prev, float beta, const float* add, float gamma, float* out, void* stream) {
+  using namespace ds;
+  DS_CHECK(plan && in && out, "ds_spmm: NULL argument");
+  return launch_spmm(transpose ? plan->bwd : plan->fwd, B, F, in, alpha, prev, beta, add, gamma, out,
+                     (cudaStream_t)stream);
+}

@@ -1,0 +1,177 @@
+"""ctypes binding of libdeepsphere_b200.so (include/deepsphere_b200.h).
+
+PyTorch is only the carrier of device memory and streams: every call hands raw device
+pointers (``tensor.data_ptr()``) and the current CUDA stream to the C-ABI.  There is no
+CPU fallback — if the library is missing, or no CUDA device is visible, the compute
+entry points raise.
+"""
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libdeepsphere_b200.so")
+
+MODE_FP32, MODE_TF32, MODE_TF32X3 = 0, 1, 2
+MODES = {"fp32": MODE_FP32, "tf32": MODE_TF32, "tf32x3": MODE_TF32X3}
+RECURSION_CHEBYSHEV, RECURSION_MONOMIAL = 0, 1
+ACT_LINEAR, ACT_RELU, ACT_ELU, ACT_SIGMOID, ACT_TANH, ACT_SOFTPLUS = range(6)
+POOL_MAX, POOL_AVG = 0, 1
+
+_i32, _i64, _f32, _ptr = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+# name -> (restype, argtypes); must list every symbol declared in include/deepsphere_b200.h
+SIGNATURES = {
+    "ds_abi_version": (ctypes.c_int, []),
+    "ds_last_error": (ctypes.c_char_p, []),
+    "ds_device_count": (ctypes.c_int, []),
+    "ds_launch_count": (_i64, []),
+    "ds_plan_create_coo": (ctypes.c_int, [_i64, _i64, _ptr, _ptr, _i32, ctypes.POINTER(_ptr)]),
+    "ds_plan_destroy": (ctypes.c_int, [_ptr]),
+    "ds_plan_info": (ctypes.c_int, [_ptr, _i32, ctypes.POINTER(_i64)]),
+    "ds_spmm": (ctypes.c_int, [_ptr, _i32, _i64, _i64, _ptr, _f32, _ptr, _f32, _ptr, _f32, _ptr, _ptr]),
+    "ds_graph_conv_basis_elems": (_i64, [_i64, _i64, _i64, _i32]),
+    "ds_graph_conv_forward": (
+        ctypes.c_int,
+        [_ptr, _i32, _i32, _i64, _i64, _i64, _ptr, _ptr, _ptr, _i32, _ptr, _ptr, _i32, _ptr],
+    ),
+    "ds_graph_conv_backward_workspace_elems": (_i64, [_i64, _i64, _i64, _i64, _i32, _i32, _i32]),
+    "ds_graph_conv_backward": (
+        ctypes.c_int,
+        [_ptr, _i32, _i32, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _ptr],
+    ),
+    "ds_bias_act_forward": (ctypes.c_int, [_i64, _i64, _ptr, _ptr, _i32, _ptr, _ptr]),
+    "ds_bias_act_backward": (ctypes.c_int, [_i64, _i64, _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr]),
+    "ds_pool_forward": (ctypes.c_int, [_i64, _i64, _i64, _i32, _i32, _ptr, _ptr, _ptr]),
+    "ds_pool_backward": (ctypes.c_int, [_i64, _i64, _i64, _i32, _i32, _ptr, _ptr, _ptr, _ptr]),
+    "ds_pconv_forward": (ctypes.c_int, [_i64, _i64, _i64, _i64, _i32, _ptr, _ptr, _ptr, _i32, _ptr, _i32, _ptr]),
+    "ds_pconv_backward_workspace_elems": (_i64, [_i64, _i64, _i64, _i64, _i32, _i32]),
+    "ds_pconv_backward": (
+        ctypes.c_int,
+        [_i64, _i64, _i64, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr, _i32, _ptr],
+    ),
+    "ds_pconvT_forward": (ctypes.c_int, [_i64, _i64, _i64, _i64, _i32, _ptr, _ptr, _ptr, _i32, _ptr, _i32, _ptr]),
+    "ds_pconvT_backward_workspace_elems": (_i64, [_i64, _i64, _i64, _i64, _i32, _i32]),
+    "ds_pconvT_backward": (
+        ctypes.c_int,
+        [_i64, _i64, _i64, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr, _i32, _ptr],
+    ),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class NativeError(RuntimeError):
+    """An entry point of libdeepsphere_b200.so reported a failure."""
+
+
+def lib():
+    """Load (once) and return the C-ABI library; fails loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise NativeError(
+                        f"{LIB_PATH} not found: build it with `python {os.path.join(_PKG_ROOT, 'build.py')}` "
+                        "(there is no CPU / PyTorch fallback for the hot path)"
+                    )
+                handle = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().ds_last_error().decode("utf-8", "replace")
+        raise NativeError(f"{what}: {msg}" if what else msg)
+
+
+def require_cuda():
+    if lib().ds_device_count() <= 0:
+        raise NativeError("no CUDA device visible: the deepsphere B200 hot path has no CPU fallback")
+
+
+def launch_count():
+    return int(lib().ds_launch_count())
+
+
+def ptr(t):
+    """Raw device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class GraphPlan:
+    """Device-resident ELL(+tail) form of a rescaled Laplacian and its transpose.
+
+    Built from the same triple the reference stores as tf.constants
+    (gnn_layers.py:68-72): COO ``indices`` int64 [nnz, 2], ``values`` float32 [nnz],
+    ``shape``.  One plan per device, created lazily on first use."""
+
+    def __init__(self, indices, values, shape, ell_width=0):
+        self.indices = np.ascontiguousarray(indices, dtype=np.int64)
+        self.values = np.ascontiguousarray(values, dtype=np.float32)
+        self.shape = (int(shape[0]), int(shape[1]))
+        if self.shape[0] != self.shape[1]:
+            raise ValueError(f"the graph Laplacian must be square, got {self.shape}")
+        self.ell_width = int(ell_width)
+        self._handles = {}
+
+    @property
+    def M(self):
+        return self.shape[0]
+
+    def handle(self, device_index):
+        h = self._handles.get(device_index)
+        if h is None:
+            import torch
+
+            require_cuda()
+            out = ctypes.c_void_p()
+            with torch.cuda.device(device_index):
+                check(
+                    lib().ds_plan_create_coo(
+                        self.shape[0],
+                        len(self.values),
+                        self.indices.ctypes.data_as(ctypes.c_void_p),
+                        self.values.ctypes.data_as(ctypes.c_void_p),
+                        self.ell_width,
+                        ctypes.byref(out),
+                    ),
+                    "ds_plan_create_coo",
+                )
+            h = self._handles[device_index] = out
+        return h
+
+    def info(self, device_index=0):
+        names = ["M", "nnz", "ell_width", "tail_rows", "tail_nnz", "ell_width_T", "tail_rows_T", "device_bytes",
+                 "symmetric"]
+        h = self.handle(device_index)
+        out = {}
+        for i, n in enumerate(names):
+            v = ctypes.c_int64()
+            check(lib().ds_plan_info(h, i, ctypes.byref(v)), "ds_plan_info")
+            out[n] = int(v.value)
+        return out
+
+    def __del__(self):
+        try:
+            for h in self._handles.values():
+                _lib.ds_plan_destroy(h)
+        except Exception:
+            pass

@@ -1,0 +1,158 @@
+"""HealpyGCNN — the reference's Sequential model shell (src/deepsphere/healpy_networks.py:14-188)
+over the B200 layers: same constructor, same validation and error types, same nside / index
+bookkeeping through pooling layers; the graph comes from the in-repo builder
+(deepsphere.graph.SphereHealpix) instead of PyGSP.
+"""
+
+import numpy as np
+
+from . import gnn_layers as gnn
+from . import healpix as hpx
+from . import healpy_layers as hp_nn
+from . import logger
+from .graph import SphereHealpix
+from .keras_compat import Sequential
+
+
+class HealpyGCNN(Sequential):
+    """A graph convolutional network using the Keras-style model API and the layers of this package."""
+
+    def __init__(self, nside, indices, layers, n_neighbors=8, max_batch_size=None, initial_Fin=None):
+        """
+        :param nside: integer, the nside of the input
+        :param indices: 1d array of pixel ids (NESTED) of the input of the network
+        :param layers: list of layers that make up the network
+        :param n_neighbors: neighbours per pixel in the graph: 8 (default), 20, 40 or 60
+        :param max_batch_size: kept for API compatibility: in the reference it sizes the column
+                               splits of tf.sparse.sparse_dense_matmul (healpy_networks.py:125-134);
+                               the splits are computed the same way and ignored by the kernels
+        :param initial_Fin: initial number of input features (same remark)
+        """
+        super().__init__(name="")
+        logger.info("WARNING: This network assumes that everything concerning healpy is in NEST ordering...")
+
+        if n_neighbors not in [8, 20, 40, 60]:
+            raise NotImplementedError(
+                f"The requested number of neighbors {n_neighbors} is nor supported. Choose either 8, 20, 40 or 60."
+            )
+
+        self.nside_in = nside
+        self.indices_in = np.asarray(indices)
+        self.layers_in = layers
+        self.n_neighbors = n_neighbors
+
+        # total reduction factor of the nside (healpy_networks.py:51-58)
+        self.reduction_fac = 1.0
+        for layer in self.layers_in:
+            if isinstance(layer, (hp_nn.HealpyPool, hp_nn.HealpyPseudoConv)):
+                self.reduction_fac *= 2 ** (layer.p)
+            if isinstance(layer, hp_nn.HealpyPseudoConv_Transpose):
+                self.reduction_fac /= 2 ** (layer.p)
+
+        self.nside_out = int(self.nside_in // self.reduction_fac)
+        if self.nside_out < 1:
+            raise ValueError(
+                "With the given input, the layers would reduce the nside below zero!"
+                "Use less layers that reduce the nside, e.g. HealpyPool or HealpyPseudoConv..."
+            )
+        if not hpx.isnsideok(self.nside_out, nest=True):
+            raise ValueError(f"The ouput of the network does not have a valid nside {self.nside_out}...")
+
+        logger.info(
+            f"Detected a reduction factor of {self.reduction_fac}, the input with nside {self.nside_in} will be "
+            f"transformed to {self.nside_out} during a forward pass. Checking for consistency with indices..."
+        )
+
+        # the index set must survive going down to nside_out and back (healpy_networks.py:73-88)
+        idx = self.indices_in.astype(np.int64)
+        npix_in = hpx.nside2npix(self.nside_in)
+        if idx.size == 0 or idx.min() < 0 or idx.max() >= npix_in:
+            raise ValueError(f"indices must be pixel ids of a nside {self.nside_in} map")
+        if self.nside_out <= self.nside_in:
+            p = hpx.nside2order(self.nside_in) - hpx.nside2order(self.nside_out)
+            transformed = hpx.refine_indices(hpx.coarsen_indices(idx, p), p)
+        else:
+            transformed = np.unique(idx)
+        if not (len(transformed) == len(idx) and np.all(np.sort(transformed) == np.sort(idx))):
+            raise ValueError(
+                "With the given indices it would not be possible to properly reduce the input maps "
+                "with the reduction factor determined by the layers. Use the function "
+                "<extend_indices> from utils with the determined minimal nside to make your set of "
+                "indices compatible..."
+            )
+        logger.info("indices seem consistent...")
+
+        # build the actual layers (healpy_networks.py:90-167)
+        self.layers_use = []
+        current_nside = self.nside_in
+        current_indices = idx
+        current_Fin = initial_Fin
+        graph_cache = {}
+
+        for layer in self.layers_in:
+            if isinstance(layer, (hp_nn.HealpyChebyshev, hp_nn.HealpyMonomial, hp_nn.Healpy_ResidualLayer)):
+                # the reference builds one SphereHealpix per graph layer even at equal nside
+                # (healpy_networks.py:110); the result only depends on (nside, indices, k), so cache it
+                key = (current_nside, len(current_indices), int(current_indices[0]), int(current_indices[-1]),
+                       int(np.sum(current_indices, dtype=np.int64)))
+                if key not in graph_cache:
+                    graph_cache[key] = SphereHealpix(
+                        subdivisions=current_nside, indexes=current_indices, nest=True, k=self.n_neighbors,
+                        lap_type="normalized",
+                    )
+                sphere = graph_cache[key]
+                current_L = sphere.L
+                if (max_batch_size is not None) and (current_Fin is not None):
+                    n_matmul_splits = 1
+                    while not (
+                        (max_batch_size * current_Fin % n_matmul_splits == 0)
+                        and (n_matmul_splits >= max_batch_size * current_Fin * len(current_L.indices) / 2**31)
+                    ):
+                        n_matmul_splits += 1
+                    actual_layer = layer._get_layer(current_L, n_matmul_splits)
+                else:
+                    actual_layer = layer._get_layer(current_L)
+                self.layers_use.append(actual_layer)
+            elif isinstance(layer, (hp_nn.HealpyPool, hp_nn.HealpyPseudoConv)):
+                new_nside = int(current_nside // 2**layer.p)
+                current_indices = self._transform_indices(current_nside, new_nside, current_indices)
+                current_nside = new_nside
+                self.layers_use.append(layer)
+            elif isinstance(layer, hp_nn.HealpyPseudoConv_Transpose):
+                new_nside = int(current_nside * 2**layer.p)
+                current_indices = self._transform_indices(current_nside, new_nside, current_indices)
+                current_nside = new_nside
+                self.layers_use.append(layer)
+            else:
+                self.layers_use.append(layer)
+
+            try:
+                current_Fin = layer.Fout
+            except AttributeError:
+                # e.g. residual or pooling layers, which have Fin = Fout
+                pass
+
+        for layer in self.layers_use:
+            self.add(layer)
+
+    def _transform_indices(self, nside_in, nside_out, indices):
+        """Index set at a new nside (healpy_networks.py:169-188; there via hp.ud_grade of a 0/1
+        mask and a > 1e-12 threshold, which in NESTED is integer parent/child arithmetic)."""
+        if nside_in == nside_out:
+            return indices
+        if nside_out < nside_in:
+            return hpx.coarsen_indices(indices, hpx.nside2order(nside_in) - hpx.nside2order(nside_out))
+        return hpx.refine_indices(indices, hpx.nside2order(nside_out) - hpx.nside2order(nside_in))
+
+    def _get_filter_coeffs(self, layer, ind_in=None, ind_out=None):
+        """Chebyshev filter coefficients of a layer as [Fin, Fout, K] (healpy_networks.py:190-217):
+        the kernel is read as Fin x K x Fout, which is what pins the f*K + k row order."""
+        K, Fout = layer.K, layer.kernel.shape[1]
+        weights = layer.kernel.detach().cpu().numpy()
+        Fin = weights.shape[0] // K
+        weights = weights.reshape((Fin, K, Fout)).transpose(0, 2, 1)
+        if ind_in is not None:
+            weights = weights[ind_in]
+        if ind_out is not None:
+            weights = weights[:, ind_out]
+        return weights

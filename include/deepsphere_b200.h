@@ -1,0 +1,157 @@
+/*
+ * deepsphere_b200.h — C-ABI of the B200-native DeepSphere graph-convolution hot path.
+ *
+ * Drop-in boundary for everything the reference executes between
+ * src/deepsphere/gnn_layers.py:113 and :159 (Chebyshev.call / Monomial.call), plus the
+ * nested-order pool / pseudo-convolution layers either side of it
+ * (src/deepsphere/healpy_layers.py:20-216).  The reference reaches this arithmetic
+ * through TensorFlow ops (tf.sparse.sparse_dense_matmul via
+ * utils.split_sparse_dense_matmul utils.py:49-78, tf.matmul gnn_layers.py:149, Keras
+ * MaxPool1D/AveragePooling1D/Conv1D/Conv2DTranspose); a TF custom op, a ctypes stub or
+ * any other FFI binds exactly the entry points below.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no C++/torch types.
+ *  - every entry returns 0 on success, non-zero on error; ds_last_error() gives the
+ *    message of the calling thread's last failure.
+ *  - tensors are caller-owned DEVICE pointers, dense row-major fp32, in the reference's
+ *    own layout [B, M, F] (batch, pixel, channel); `stream` is a cudaStream_t passed as
+ *    void*.  The library owns only opaque plan handles.
+ *  - there is no CPU fallback: without a CUDA device every compute entry fails.
+ *  - plans are immutable after creation; any number of host threads may call the
+ *    compute entries concurrently with distinct workspaces/streams.
+ */
+#ifndef DEEPSPHERE_B200_H
+#define DEEPSPHERE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DS_ABI_VERSION 1
+
+/* recursion type: gnn_layers.py:135-143 (Chebyshev) / :287-290 (Monomial) */
+#define DS_RECURSION_CHEBYSHEV 0 /* T_1 = L T_0 ; T_k = 2 L T_{k-1} - T_{k-2} */
+#define DS_RECURSION_MONOMIAL 1  /* T_k = L T_{k-1} */
+
+/* arithmetic of the K*Fin -> Fout contraction (gnn_layers.py:149) and its gradients */
+#define DS_MODE_FP32 0   /* CUDA-core fp32 FMA                        (parity rel <= 1e-5) */
+#define DS_MODE_TF32 1   /* tcgen05 tensor cores, single-pass TF32    (stated rel <= 1e-3) */
+#define DS_MODE_TF32X3 2 /* tcgen05, 3xTF32 error-compensated split   (rel <= 1e-5)        */
+
+/* fused epilogue activation (tf.keras.activations names, gnn_layers.py:55-60) */
+#define DS_ACT_LINEAR 0
+#define DS_ACT_RELU 1
+#define DS_ACT_ELU 2
+#define DS_ACT_SIGMOID 3
+#define DS_ACT_TANH 4
+#define DS_ACT_SOFTPLUS 5
+
+/* pooling type: healpy_layers.py:48-65 */
+#define DS_POOL_MAX 0
+#define DS_POOL_AVG 1
+
+typedef struct ds_plan ds_plan_t;
+
+int ds_abi_version(void);
+/* message of the calling thread's last error ("" if none) */
+const char* ds_last_error(void);
+/* number of visible CUDA devices (0 without a GPU); never fails */
+int ds_device_count(void);
+/* total number of kernel launches issued by this library in this process (bench.py's
+ * gpu_launches evidence) */
+int64_t ds_launch_count(void);
+
+/* ---- plan ---------------------------------------------------------------------------
+ * Replaces Chebyshev.__init__'s tf.constant triple (_L_indices int64 [nnz,2],
+ * _L_values floatx [nnz], _L_shape) — gnn_layers.py:68-72 — and the per-call
+ * tf.sparse.reorder (gnn_layers.py:115): the rescaled Laplacian L~ is given once, as
+ * HOST COO arrays in any order; the library sorts it row-major, builds a fixed-width
+ * ELL slab (width = ell_width, or chosen automatically when ell_width <= 0) plus a CSR
+ * tail for longer rows, does the same for L~^T (needed by the backward pass), and
+ * uploads both to the current device.
+ */
+int ds_plan_create_coo(int64_t M, int64_t nnz, const int64_t* indices /* [nnz,2] (row,col) */,
+                       const float* values /* [nnz] */, int32_t ell_width, ds_plan_t** plan_out);
+int ds_plan_destroy(ds_plan_t* plan);
+/* info: 0 M, 1 nnz, 2 ell_width, 3 tail_rows, 4 tail_nnz, 5 ell_width of L~^T,
+ *       6 tail_rows of L~^T, 7 device bytes held by the plan, 8 is L~ symmetric (0/1) */
+int ds_plan_info(const ds_plan_t* plan, int32_t what, int64_t* value_out);
+
+/* ---- utils.split_sparse_dense_matmul (utils.py:49-78) ---------------------------------
+ * out[b,m,f] = alpha * sum_j L~[m,j] in[b,j,f] + beta * prev[b,m,f] + gamma * add[b,m,f]
+ * (prev/add may be NULL when their factor is 0; transpose != 0 uses L~^T).  The
+ * reference's n_splits column split is a TF size workaround (utils.py:59) that this
+ * kernel does not need: 64-bit addressing throughout.
+ */
+int ds_spmm(const ds_plan_t* plan, int32_t transpose, int64_t B, int64_t F, const float* in, float alpha,
+            const float* prev, float beta, const float* add, float gamma, float* out, void* stream);
+
+/* ---- Chebyshev.call / Monomial.call (gnn_layers.py:106-161, :255-309) ------------------
+ * y[B,M,Fout] = act( sum_{f,k} T_k[b,m,f] * kernel[f*K + k, o] + bias[o] )
+ * with T_0 = x and the recursion above.  kernel is [K*Fin, Fout] with the reference's row
+ * order f*K + k (gnn_layers.py:145-147), bias is [Fout] (the reference's [1,1,Fout]) or
+ * NULL.  BatchNorm (gnn_layers.py:152-153) sits between the contraction and the bias, so
+ * a use_bn layer calls this with bias = NULL, act = LINEAR and finishes with
+ * ds_bias_act_forward.
+ *
+ * basis: workspace of (K-1)*B*M*Fin floats; on return it holds T_1..T_{K-1}
+ * ([K-1, B, M, Fin]) and may be handed to ds_graph_conv_backward to skip recomputation.
+ */
+int64_t ds_graph_conv_basis_elems(int64_t M, int64_t B, int64_t Fin, int32_t K);
+int ds_graph_conv_forward(const ds_plan_t* plan, int32_t recursion, int32_t K, int64_t B, int64_t Fin,
+                          int64_t Fout, const float* x, const float* kernel, const float* bias, int32_t act,
+                          float* y, float* basis, int32_t mode, void* stream);
+
+/* Gradients of the above w.r.t. x, kernel, bias for an upstream gradient dy [B,M,Fout]
+ * (what TF autodiff produces for gnn_layers.py:131-159).
+ *  y        : forward output, needed only when act != LINEAR (derivative from y)
+ *  basis    : T_1..T_{K-1} saved by the forward, or NULL to recompute them into
+ *             `workspace`
+ *  dx       : [B,M,Fin] or NULL;  dkernel: [K*Fin,Fout] (overwritten);  dbias: [Fout] or NULL
+ *  workspace: ds_graph_conv_backward_workspace_elems(...) floats
+ */
+int64_t ds_graph_conv_backward_workspace_elems(int64_t M, int64_t B, int64_t Fin, int64_t Fout, int32_t K,
+                                               int32_t have_basis, int32_t act);
+int ds_graph_conv_backward(const ds_plan_t* plan, int32_t recursion, int32_t K, int64_t B, int64_t Fin,
+                           int64_t Fout, const float* x, const float* kernel, const float* y, const float* dy,
+                           int32_t act, const float* basis, float* dx, float* dkernel, float* dbias,
+                           float* workspace, int32_t mode, void* stream);
+
+/* y = act(z + bias[o]) in place-capable elementwise form, and its backward
+ * (dz = dy * act'(y); dbias = sum dz).  Used when BatchNorm sits before the bias. */
+int ds_bias_act_forward(int64_t R, int64_t F, const float* z, const float* bias, int32_t act, float* y, void* stream);
+int ds_bias_act_backward(int64_t R, int64_t F, const float* y, const float* dy, int32_t act, float* dz,
+                         float* dbias /* nullable */, float* workspace /* 2*1024*F floats */, void* stream);
+
+/* ---- HealpyPool (healpy_layers.py:20-84) -----------------------------------------------
+ * y[b,j,f] = max | mean over c < 4^p of x[b, 4^p*j + c, f];  M % 4^p == 0 required. */
+int ds_pool_forward(int64_t B, int64_t M, int64_t F, int32_t p, int32_t pool_type, const float* x, float* y,
+                    void* stream);
+int ds_pool_backward(int64_t B, int64_t M, int64_t F, int32_t p, int32_t pool_type, const float* x,
+                     const float* dy, float* dx, void* stream);
+
+/* ---- HealpyPseudoConv (healpy_layers.py:87-146): Conv1D(Fout, 4^p, strides 4^p) --------
+ * y[b,j,o] = act( sum_{c,f} x[b,4^p*j+c,f] * w[c,f,o] + bias[o] );  w is Keras' [4^p,Fin,Fout]. */
+int ds_pconv_forward(int64_t B, int64_t M, int64_t Fin, int64_t Fout, int32_t p, const float* x, const float* w,
+                     const float* bias, int32_t act, float* y, int32_t mode, void* stream);
+int64_t ds_pconv_backward_workspace_elems(int64_t B, int64_t M, int64_t Fin, int64_t Fout, int32_t p, int32_t act);
+int ds_pconv_backward(int64_t B, int64_t M, int64_t Fin, int64_t Fout, int32_t p, const float* x, const float* w,
+                      const float* y, const float* dy, int32_t act, float* dx, float* dw, float* dbias,
+                      float* workspace, int32_t mode, void* stream);
+
+/* ---- HealpyPseudoConv_Transpose (healpy_layers.py:149-216): Conv2DTranspose (1,4^p) ----
+ * y[b,4^p*j+c,o] = act( sum_f x[b,j,f] * w[0,c,o,f] + bias[o] );  w is Keras' [1,4^p,Fout,Fin]. */
+int ds_pconvT_forward(int64_t B, int64_t M, int64_t Fin, int64_t Fout, int32_t p, const float* x, const float* w,
+                      const float* bias, int32_t act, float* y, int32_t mode, void* stream);
+int64_t ds_pconvT_backward_workspace_elems(int64_t B, int64_t M, int64_t Fin, int64_t Fout, int32_t p, int32_t act);
+int ds_pconvT_backward(int64_t B, int64_t M, int64_t Fin, int64_t Fout, int32_t p, const float* x, const float* w,
+                       const float* y, const float* dy, int32_t act, float* dx, float* dw, float* dbias,
+                       float* workspace, int32_t mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPSPHERE_B200_H */
