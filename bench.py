@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py — HealpyChebyshev layer microbench (BASELINE.json configs[1]): nside 256, K 5,
+Fin = Fout = 64, batch 32 per GPU, forward + backward.
+
+Metric: algorithmic GB/s of the layer (fwd+bwd touches 4*B*M*(3*Fin + 2*Fout)
+bytes = 32.21 GB per GPU per step) — `value` with inputs resident in HBM, `e2e` through the
+public layer API with pinned HOST buffers and the host<->device copies inside the timed region.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference ...                     # the reference's op sequence on the host
+                                                           # CPUs (oracle port, bounded sample)
+Under torchrun (N > 1) every rank runs the same per-GPU workload (weak scaling, batch
+sharding); the per-step exchange is the all-reduce of the kernel gradient.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "deepsphere-cosmo-tf2_b200"), ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "HealpyChebyshev fwd+bwd algorithmic GB/s (nside 256, K 5, Fin=Fout=64, batch 32/GPU)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("DEEPSPHERE_MODE", "fp32"), choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--nside", type=int, default=256)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--features", type=int, default=64)
+    ap.add_argument("--K", type=int, default=5)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-batch", type=int, default=1)
+    return ap.parse_args()
+
+
+def algorithmic_bytes(B, M, Fin, Fout):
+    """fwd: read x, write y; bwd: read x, read dy, write dx (basis recomputed on chip)."""
+    return 4 * B * M * (3 * Fin + 2 * Fout)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (pynvml)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def build_layer(args, mode):
+    from deepsphere import gnn_layers
+    from deepsphere.graph import SphereHealpix
+
+    g = SphereHealpix(args.nside, k=8)
+    layer = gnn_layers.Chebyshev(L=g.L, K=args.K, Fout=args.features, mode=mode)
+    return g, layer
+
+
+def cpu_reference_time(L, args, batch, steps, warmup, Lt=None):
+    """The reference's op sequence (gnn_layers.py:131-150 + autodiff) with torch CPU ops on all
+    host threads — oracle/deepsphere_oracle.py:torch_cpu_graph_conv — fwd + bwd."""
+    from oracle import deepsphere_oracle as orc
+
+    if Lt is None:
+        Lt, _ = orc.prepare_laplacian(L, 0.75)
+    M = Lt.shape[0]
+    F = args.features
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(batch, M, F, generator=g, requires_grad=True)
+    w = (torch.randn(args.K * F, F, generator=g) * 0.075).requires_grad_(True)
+    dy = torch.randn(batch, M, F, generator=g)
+    times = []
+    for i in range(warmup + steps):
+        x.grad = w.grad = None
+        t0 = time.perf_counter()
+        y = orc.torch_cpu_graph_conv(x, Lt, w, args.K, "chebyshev")
+        y.backward(dy)
+        t1 = time.perf_counter()
+        if i >= warmup:
+            times.append(t1 - t0)
+    return float(np.mean(times)), algorithmic_bytes(batch, M, F, F)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from deepsphere.graph import SphereHealpix
+
+        g = SphereHealpix(args.nside, k=8)
+        steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+        t, nbytes = cpu_reference_time(g.L, args, args.cpu_sample_batch, steps, warmup)
+        val = nbytes / t / 1e9
+        sample = (f"batch {args.cpu_sample_batch} of the workload's {args.batch} (same nside/K/F), fwd+bwd, "
+                  f"{steps} timed steps after {warmup} warm-up")
+        line = {
+            "impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": f"HealpyChebyshev nside {args.nside} K {args.K} Fin=Fout={args.features} fwd+bwd",
+                       "parallelism": "host CPU threads"},
+            "cpu_baseline": {"value": val, "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return
+
+    from deepsphere import _native as nat
+    from deepsphere import distributed as dsd
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dsd.init_from_env()
+    mode = args.mode
+    g, layer = build_layer(args, mode)
+    M, F, B, K = g.L.shape[0], args.features, args.batch, args.K
+    layer.build_from_shape((B, M, F))
+    dsd.broadcast_parameters(layer)
+    gen = torch.Generator(device=device).manual_seed(1234 + rank)
+    x = torch.randn(B, M, F, device=device, generator=gen).requires_grad_(True)
+    dy = torch.randn(B, M, F, device=device, generator=gen)
+    nbytes = algorithmic_bytes(B, M, F, F)
+
+    def step():
+        x.grad = None
+        layer.kernel.grad = None
+        y = layer(x)
+        y.backward(dy)
+        dsd.allreduce_gradients([layer.kernel])
+        return y
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    launches0 = nat.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        sync_all()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (nat.launch_count() - launches0)
+    ms = dsd.allreduce_max(ms, device)
+    value = world * nbytes / (ms * 1e-3) / 1e9
+    hbm_peak, bf16_peak, peak_kind = peaks()
+
+    # ---- per-kernel timing of the path's kernels, in isolation, on the launching stream ----------
+    from deepsphere import _ops
+
+    def time_fn(fn, n=5):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    A_bytes = 4 * B * M * F
+    with torch.no_grad():
+        xd = x.detach()
+        t1 = _ops.spmm(layer._plan, xd)
+        hop_ms = time_fn(lambda: _ops.spmm(layer._plan, t1, 2.0, xd, -1.0))
+        fwd_ms = time_fn(lambda: layer(xd))
+    kernels = {
+        "spmm_hop": {"ms": hop_ms, "algorithmic_bytes": 3 * A_bytes, "GBps": 3 * A_bytes / hop_ms / 1e6},
+        "forward": {"ms": fwd_ms, "algorithmic_bytes": 2 * A_bytes, "GBps": 2 * A_bytes / fwd_ms / 1e6},
+        "contraction_fwd_ms_est": max(fwd_ms - (K - 1) * hop_ms, 0.0),
+    }
+    contraction_ms = kernels["contraction_fwd_ms_est"]
+    gemm_flops = 2.0 * B * M * K * F * F
+    if contraction_ms > (K - 1) * hop_ms and mode != "fp32":
+        tf32_peak = bf16_peak / 2
+        roofline = {"kernel": "umma contraction (forward)", "bound": "tensor",
+                    "achieved": gemm_flops / contraction_ms / 1e9, "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": gemm_flops / contraction_ms / 1e9 / tf32_peak, "traffic": None,
+                    "peak_source": f"{peak_kind} bf16 / 2"}
+    else:
+        roofline = {"kernel": "spmm_ell_kernel<4> (one recursion hop)", "bound": "hbm",
+                    "achieved": kernels["spmm_hop"]["GBps"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": kernels["spmm_hop"]["GBps"] / hbm_peak, "traffic": None, "peak_source": peak_kind}
+    layer_roofline = {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                      "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak,
+                      "note": "whole layer fwd+bwd, algorithmic bytes / step time, per GPU"}
+
+    # ---- e2e: public layer API, pinned host buffers, H2D + D2H inside the timed region ------------
+    e2e = None
+    if not args.no_e2e:
+        try:
+            import psutil
+
+            free_host = psutil.virtual_memory().available
+        except Exception:
+            free_host = 0
+        Be = B
+        while Be > 1 and 3 * 4 * Be * M * F > 0.4 * free_host:
+            Be //= 2
+        xh = torch.empty((Be, M, F), dtype=torch.float32).pin_memory()
+        dyh = torch.empty((Be, M, F), dtype=torch.float32).pin_memory()
+        dxh = torch.empty((Be, M, F), dtype=torch.float32).pin_memory()
+        dkh = torch.empty((K * F, F), dtype=torch.float32).pin_memory()
+        xh.normal_()
+        dyh.normal_()
+        del x, dy
+        torch.cuda.empty_cache()
+
+        def e2e_step():
+            xd_ = xh.to(device, non_blocking=True).requires_grad_(True)
+            dyd = dyh.to(device, non_blocking=True)
+            layer.kernel.grad = None
+            y = layer(xd_)
+            y.backward(dyd)
+            dsd.allreduce_gradients([layer.kernel])
+            dxh.copy_(xd_.grad, non_blocking=True)
+            dkh.copy_(layer.kernel.grad, non_blocking=True)
+
+        e2e_step()
+        sync_all()
+        n_e2e = max(2, min(args.steps, 4))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        b.record()
+        sync_all()
+        e2e_ms = dsd.allreduce_max(a.elapsed_time(b) / n_e2e, device)
+        e2e = {"value": world * algorithmic_bytes(Be, M, F, F) / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s",
+               "h2d_bytes_per_step": 2 * 4 * Be * M * F, "d2h_bytes_per_step": 4 * Be * M * F + 4 * K * F * F,
+               "ms_per_step": e2e_ms, "batch": Be, "steps": n_e2e}
+
+    # ---- CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample -------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from scipy import sparse
+
+        Lt = sparse.csr_matrix((layer._L_values.astype(np.float64), (layer._L_indices[:, 0], layer._L_indices[:, 1])),
+                               shape=g.L.shape)  # the layer's own prepared L~ (skips a second ARPACK run)
+        t, nb = cpu_reference_time(g.L, args, args.cpu_sample_batch, 2, 1, Lt=Lt)
+        cpu_baseline = {"value": nb / t / 1e9, "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"batch {args.cpu_sample_batch} of {B} (same nside/K/F), fwd+bwd, torch-CPU "
+                                  f"restatement of gnn_layers.py:131-150, 2 timed steps", "ms_per_step": t * 1e3}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": {"fp32": "fp32", "tf32": "tf32 contraction / fp32 recursion",
+                                           "tf32x3": "3xtf32 contraction / fp32 recursion"}[mode],
+            "data": "synthetic",
+            "config": {"workload": f"HealpyChebyshev layer nside {args.nside} (M={M}) K {K} Fin=Fout={F} "
+                                   f"batch {B}/GPU fwd+bwd, 8-neighbour HEALPix graph",
+                       "mode": mode, "parallelism": f"batch-sharded x{world}", "l2": "inputs (6.4 GB/tensor) >> L2"},
+            "roofline": roofline, "layer_roofline": layer_roofline, "kernels": kernels,
+            "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,78 @@
+"""Multi-GPU plumbing for the hot path: one process per GPU, torch.distributed (NCCL over
+NVLink on the GPU box, gloo in CPU tests).
+
+The reference is single-device (no tf.distribute / NCCL call sites), so this
+is new: the path shards by *batch* — samples are independent through every layer of the
+path — and the only exchange step of a training pass is the sum of the weight gradients
+(plus BatchNorm statistics when use_bn=True), done here as ONE flat all-reduce per step:
+the whole gradient of a HealpyGCNN is 1e2..1e5 floats, i.e. latency-bound, so bucketing by
+size would only add launches.
+"""
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise the default process group from torchrun's environment; returns
+    (rank, world_size, local_rank).  No-op for a single process."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local_rank
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous [begin, end) share of n_items for `rank` (sizes differ by at most one)."""
+    base, rem = divmod(int(n_items), int(world))
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def allreduce_gradients(params, group=None, average=True):
+    """Sum (or average) the .grad of `params` over all ranks with a single flat all-reduce.
+    Parameters without a gradient contribute zeros so every rank issues the same collective."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    params = [p for p in params if p.requires_grad]
+    if not params:
+        return 0
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= dist.get_world_size(group)
+    off = 0
+    for p in params:
+        n = p.numel()
+        g = flat[off : off + n].view_as(p)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += n
+    return flat.numel()
+
+
+def broadcast_parameters(module, src=0, group=None):
+    """Make every rank start from rank `src`'s weights and buffers."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t, src=src, group=group)
+
+
+def allreduce_max(value, device):
+    """Max over ranks of a python float (used for max-over-ranks timing)."""
+    t = torch.tensor([float(value)], device=device, dtype=torch.float64)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
