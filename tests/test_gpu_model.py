@@ -49,7 +49,7 @@ def test_healpy_gcnn_forward_matches_oracle_pipeline():
     torch.manual_seed(0)
     model = deepsphere.HealpyGCNN(nside=nside, indices=np.arange(12 * nside**2), layers=layers, n_neighbors=20)
     x = np.random.default_rng(0).standard_normal((3, 12 * nside**2, 2)).astype(np.float32)
-    y = model(x, training=False).cpu().numpy()
+    y = model(x, training=False).detach().cpu().numpy()
     assert y.shape == (3, 3)
     assert rel_err(y, _reference_forward(model, x)) <= 2e-5
 
