@@ -11,6 +11,10 @@ int umma_supported(int64_t Kc, int nseg, int64_t N);
 int launch_umma_gemm_nn(int64_t R, int64_t N, int64_t Kc, int nseg, const float* A0, const float* Arest,
                         int64_t a_seg_stride, const float* Bm, int64_t b_kc_stride, int64_t b_seg_stride,
                         const float* bias, int act, float* C, int mode, cudaStream_t st);
+int launch_umma_gemm(int64_t R, int64_t N, int64_t Kc, int nseg, const float* A0, const float* Arest,
+                     int64_t a_seg_stride_rows, const float* Bm, int64_t b_k_stride, int64_t b_seg_stride,
+                     int64_t b_n_stride, const float* bias, int64_t bias_mod, int act, float* C, int64_t ldc, int mode,
+                     cudaStream_t st);
 
 namespace {
 
@@ -124,7 +128,11 @@ int ds_graph_conv_backward(const ds_plan_t* plan, int32_t recursion, int32_t K, 
   if (dx == nullptr) return 0;
 
   // 5. dx = sum_k T_k(L~^T) G_k,  G_k[b,m,f] = sum_o dz[b,m,o] kernel[f*K + k, o]   (Clenshaw / Horner)
+  const bool tc_G = mode != DS_MODE_FP32 && umma_supported(Fout, 1, Fin) == 0;
   auto make_G = [&](int k, float* out) {
+    if (tc_G)  // G_k = dz * W_k^T on the tensor cores: B(kc = o, n = f) = kernel[(f*K + k)*Fout + o]
+      return launch_umma_gemm(R, Fin, Fout, 1, dz, dz, R, kernel + (int64_t)k * Fout, 1, 0, (int64_t)K * Fout, nullptr,
+                              1, DS_ACT_LINEAR, out, Fin, mode, st);
     return launch_gemm_nt(R, Fin, Fout, 1, dz, Fout, kernel + (int64_t)k * Fout, Fout, K, 0, nullptr, 1,
                           DS_ACT_LINEAR, out, Fin, 0, st);
   };

@@ -35,51 +35,77 @@ struct Vec<4> {
   }
 };
 
+// streaming (evict-first) access for operands that are touched exactly once per hop
 template <int V>
-__global__ void __launch_bounds__(256) spmm_ell_kernel(const int32_t* __restrict__ ell_col,
-                                                       const float* __restrict__ ell_val, int W, int64_t M,
-                                                       int64_t B, int64_t F, const float* __restrict__ in, float alpha,
-                                                       const float* __restrict__ prev, float beta,
-                                                       const float* __restrict__ add, float gamma,
-                                                       float* __restrict__ out, int lpr_log2) {
+__device__ __forceinline__ Vec<V> load_stream(const float* p);
+template <>
+__device__ __forceinline__ Vec<1> load_stream<1>(const float* p) { Vec<1> r; r.v[0] = __ldcs(p); return r; }
+template <>
+__device__ __forceinline__ Vec<4> load_stream<4>(const float* p) {
+  const float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+  Vec<4> r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+}
+template <int V>
+__device__ __forceinline__ void store_stream(float* p, const Vec<V>& a);
+template <>
+__device__ __forceinline__ void store_stream<1>(float* p, const Vec<1>& a) { __stcs(p, a.v[0]); }
+template <>
+__device__ __forceinline__ void store_stream<4>(float* p, const Vec<4>& a) {
+  __stcs(reinterpret_cast<float4*>(p), make_float4(a.v[0], a.v[1], a.v[2], a.v[3]));
+}
+
+// A CTA owns `unit_rows` CONSECUTIVE rows of one batch element at a time.  In NESTED order that is a
+// compact patch of the sphere, so the ~9 gathers per row hit rows the same CTA (same SM) has just
+// touched: the re-use is served by L1 instead of L2, and HBM sees each input row about once.
+template <int V>
+__global__ void __launch_bounds__(512, 2) spmm_ell_kernel(const int32_t* __restrict__ ell_col,
+                                                           const float* __restrict__ ell_val, int W, int64_t M,
+                                                           int64_t B, int64_t F, const float* __restrict__ in,
+                                                           float alpha, const float* __restrict__ prev, float beta,
+                                                           const float* __restrict__ add, float gamma,
+                                                           float* __restrict__ out, int lpr_log2, int unit_rows) {
   const int lpr = 1 << lpr_log2;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) >> lpr_log2;
-  const int sub = (int)(tid & (lpr - 1));
+  const int groups_per_block = blockDim.x >> lpr_log2;
+  const int g = threadIdx.x >> lpr_log2;
+  const int sub = threadIdx.x & (lpr - 1);
   const int64_t FV = F / V;
-  const int64_t R = B * M;
-  for (int64_t r = tid >> lpr_log2; r < R; r += n_groups) {
-    const int64_t b = r / M;
-    const int64_t m = r - b * M;
+  const int64_t units_per_b = (M + unit_rows - 1) / unit_rows;
+  const int64_t n_units = B * units_per_b;
+  for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+    const int64_t b = u / units_per_b;
+    const int64_t m0 = (u - b * units_per_b) * unit_rows;
+    const int64_t m1 = min(M, m0 + (int64_t)unit_rows);
     const float* inb = in + b * M * F;
-    const int32_t* cols = ell_col + m * W;
-    const float* vals = ell_val + m * W;
-    for (int64_t c = sub; c < FV; c += lpr) {
-      Vec<V> acc;
+    for (int64_t m = m0 + g; m < m1; m += groups_per_block) {
+      const int32_t* cols = ell_col + m * W;
+      const float* vals = ell_val + m * W;
+      for (int64_t c = sub; c < FV; c += lpr) {
+        Vec<V> acc;
 #pragma unroll
-      for (int i = 0; i < V; ++i) acc.v[i] = 0.f;
+        for (int i = 0; i < V; ++i) acc.v[i] = 0.f;
 #pragma unroll 3
-      for (int n = 0; n < W; ++n) {
-        const int32_t col = __ldg(cols + n);
-        const float w = __ldg(vals + n);
-        Vec<V> xv = Vec<V>::load(inb + (int64_t)col * F + c * V);
+        for (int n = 0; n < W; ++n) {
+          const int32_t col = __ldg(cols + n);
+          const float w = __ldg(vals + n);
+          Vec<V> xv = Vec<V>::load(inb + (int64_t)col * F + c * V);
 #pragma unroll
-        for (int i = 0; i < V; ++i) acc.v[i] = fmaf(w, xv.v[i], acc.v[i]);
+          for (int i = 0; i < V; ++i) acc.v[i] = fmaf(w, xv.v[i], acc.v[i]);
+        }
+        const int64_t off = (b * M + m) * F + c * V;
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc.v[i] *= alpha;
+        if (prev != nullptr) {
+          Vec<V> pv = load_stream<V>(prev + off);
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc.v[i] = fmaf(beta, pv.v[i], acc.v[i]);
+        }
+        if (add != nullptr) {
+          Vec<V> av = load_stream<V>(add + off);
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc.v[i] = fmaf(gamma, av.v[i], acc.v[i]);
+        }
+        store_stream<V>(out + off, acc);
       }
-      const int64_t off = r * F + c * V;
-#pragma unroll
-      for (int i = 0; i < V; ++i) acc.v[i] *= alpha;
-      if (prev != nullptr) {
-        Vec<V> pv = Vec<V>::load(prev + off);
-#pragma unroll
-        for (int i = 0; i < V; ++i) acc.v[i] = fmaf(beta, pv.v[i], acc.v[i]);
-      }
-      if (add != nullptr) {
-        Vec<V> av = Vec<V>::load(add + off);
-#pragma unroll
-        for (int i = 0; i < V; ++i) acc.v[i] = fmaf(gamma, av.v[i], acc.v[i]);
-      }
-      acc.store(out + off);
     }
   }
 }
@@ -122,30 +148,34 @@ int launch_spmm(const SparseDev& S, int64_t B, int64_t F, const float* in, float
                 const float* add, float gamma, float* out, cudaStream_t st) {
   DS_CHECK(B > 0 && F > 0, "spmm: empty batch or feature dimension");
   DS_CHECK(in != out, "spmm: in-place hop is not supported (gather hazard)");
-  const int64_t R = B * S.M;
   auto aligned = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool vec4 = (F % 4 == 0) && aligned(in) && aligned(prev) && aligned(add) && aligned(out);
   const int V = vec4 ? 4 : 1;
   const int lpr_log2 = std::min(5, ilog2_ceil(F / V));
-  const int threads = 256;
-  const int64_t groups_per_block = threads >> lpr_log2;
-  int64_t blocks = (R + groups_per_block - 1) / groups_per_block;
-  const int64_t max_blocks = (int64_t)num_sms() * 8 * 4;  // 8 resident CTAs/SM x 4 waves, grid-stride beyond
-  if (blocks > max_blocks) blocks = max_blocks;
+  // unit = rows per CTA visit: ~64 KB of input rows (a square NESTED patch), so two resident CTAs'
+  // patches + halos fit L1
+  int unit_rows = 64;
+  while (unit_rows < 4096 && (int64_t)unit_rows * 4 * F * 4 <= 65536) unit_rows *= 4;
+  const int64_t units_per_b = (S.M + unit_rows - 1) / unit_rows;
+  const int64_t max_blocks = (int64_t)num_sms() * 2 * 8;
+  const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>(B * units_per_b, max_blocks));
+  const int threads = 512;
   if (vec4) {
     spmm_ell_kernel<4><<<(unsigned)blocks, threads, 0, st>>>(S.ell_col, S.ell_val, S.W, S.M, B, F, in, alpha, prev,
-                                                             prev ? beta : 0.f, add, add ? gamma : 0.f, out, lpr_log2);
+                                                             prev ? beta : 0.f, add, add ? gamma : 0.f, out, lpr_log2,
+                                                             unit_rows);
   } else {
     spmm_ell_kernel<1><<<(unsigned)blocks, threads, 0, st>>>(S.ell_col, S.ell_val, S.W, S.M, B, F, in, alpha, prev,
-                                                             prev ? beta : 0.f, add, add ? gamma : 0.f, out, lpr_log2);
+                                                             prev ? beta : 0.f, add, add ? gamma : 0.f, out, lpr_log2,
+                                                             unit_rows);
   }
   DS_LAUNCHED();
   if (S.n_tail_rows > 0) {
     const int tl = std::min(5, ilog2_ceil(F));
-    const int64_t gpb = threads >> tl;
+    const int64_t gpb = 256 >> tl;
     int64_t tb = (B * S.n_tail_rows + gpb - 1) / gpb;
     if (tb > max_blocks) tb = max_blocks;
-    spmm_tail_kernel<<<(unsigned)tb, threads, 0, st>>>(S.tail_rows, S.tail_rowptr, S.tail_col, S.tail_val,
+    spmm_tail_kernel<<<(unsigned)tb, 256, 0, st>>>(S.tail_rows, S.tail_rowptr, S.tail_col, S.tail_val,
                                                        S.n_tail_rows, S.M, B, F, in, alpha, out, tl);
     DS_LAUNCHED();
   }
