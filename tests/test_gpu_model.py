@@ -19,21 +19,21 @@ def _reference_forward(model, x):
         if isinstance(layer, (gnn_layers.Chebyshev, gnn_layers.Monomial)):
             rec = "chebyshev" if isinstance(layer, gnn_layers.Chebyshev) else "monomial"
             Lt, _ = orc.prepare_laplacian(layer.L, 0.75 if rec == "chebyshev" else 1.0)
-            bias = layer.bias.detach().double().cpu().numpy() if layer.use_bias else None
+            bias = layer.bias.detach().double().detach().cpu().numpy() if layer.use_bias else None
             bn = None
             if layer.use_bn:
-                bn = (layer.bn.moving_mean.double().cpu().numpy(), layer.bn.moving_variance.double().cpu().numpy())
+                bn = (layer.bn.moving_mean.double().detach().cpu().numpy(), layer.bn.moving_variance.double().detach().cpu().numpy())
             act = [k for k, v in keras_compat.ACTIVATIONS.items() if v[1] is layer.activation]
-            h = orc.graph_conv_forward(h, Lt, layer.kernel.detach().double().cpu().numpy(), layer.K, rec, bias=bias,
+            h = orc.graph_conv_forward(h, Lt, layer.kernel.detach().double().detach().cpu().numpy(), layer.K, rec, bias=bias,
                                        activation=act[0] if act else None, use_bn=layer.use_bn, training=False,
                                        bn_state=bn, dtype=np.float64)
         elif isinstance(layer, hl.HealpyPool):
             h = orc.healpy_pool(h, layer.p, layer.pool_type)
         elif isinstance(layer, hl.HealpyPseudoConv):
-            h = orc.pseudo_conv(h, layer.kernel.detach().double().cpu().numpy(), layer.bias.detach().double().cpu().numpy())
+            h = orc.pseudo_conv(h, layer.kernel.detach().double().detach().cpu().numpy(), layer.bias.detach().double().detach().cpu().numpy())
         elif isinstance(layer, hl.HealpyPseudoConv_Transpose):
-            h = orc.pseudo_conv_transpose(h, layer.kernel.detach().double().cpu().numpy(),
-                                          layer.bias.detach().double().cpu().numpy())
+            h = orc.pseudo_conv_transpose(h, layer.kernel.detach().double().detach().cpu().numpy(),
+                                          layer.bias.detach().double().detach().cpu().numpy())
         else:
             h = layer(torch.tensor(h)).numpy()
     return h
@@ -83,7 +83,7 @@ def test_training_step_decreases_loss_and_matches_cpu_gradients():
             h = h.reshape(8, npix // 4, 4, 6).max(dim=2).values
             out = orc.torch_cpu_graph_conv(h, Lt2, w2, 3).mean(dim=1)
             ((out - torch.tensor(t, dtype=torch.float64)) ** 2).mean().backward()
-            assert rel_err(l0.kernel.grad.cpu().numpy(), w0.grad.numpy()) <= 5e-5
+            assert rel_err(l0.kernel.grad.detach().cpu().numpy(), w0.grad.numpy()) <= 5e-5
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < losses[0]

@@ -46,7 +46,7 @@ def test_graph_conv_forward_matches_golden(name):
     # the layer's own Laplacian prep must land on the golden L~ (fp64 -> fp32 rounding point, gnn_layers.py:71)
     dense = sparse.csr_matrix((layer._L_values, (layer._L_indices[:, 0], layer._L_indices[:, 1])), shape=g["Lt"].shape)
     assert abs(dense - g["Lt"]).max() < 1e-6
-    y = layer(g["x"].astype(np.float32)).cpu().numpy()
+    y = layer(g["x"].astype(np.float32)).detach().cpu().numpy()
     assert y.shape == g["y64"].shape
     assert rel_err(y, g["y64"]) <= TOL_FP32
     assert rel_err(y, g["y32"]) <= TOL_FP32
@@ -66,9 +66,9 @@ def test_graph_conv_backward_matches_golden(name, save_basis, monkeypatch):
     x = dev(g["x"]).requires_grad_(True)
     y = layer(x)
     y.backward(dev(g["dy"]))
-    assert rel_err(x.grad.cpu().numpy(), g["dx64"]) <= TOL_FP32
-    assert rel_err(layer.kernel.grad.cpu().numpy(), g["dkernel64"]) <= TOL_FP32
-    assert rel_err(layer.bias.grad.cpu().numpy(), g["dbias64"]) <= TOL_FP32
+    assert rel_err(x.grad.detach().cpu().numpy(), g["dx64"]) <= TOL_FP32
+    assert rel_err(layer.kernel.grad.detach().cpu().numpy(), g["dkernel64"]) <= TOL_FP32
+    assert rel_err(layer.bias.grad.detach().cpu().numpy(), g["dbias64"]) <= TOL_FP32
 
 
 @pytest.mark.parametrize("act", ["relu", "elu", "sigmoid", "tanh", "softplus", "gelu"])
@@ -98,13 +98,13 @@ def test_bias_bn_activation_forward_backward(act, use_bn):
     yr.backward(torch.tensor(g["dy"]))
     tol = 2e-5 if use_bn else TOL_FP32
     assert rel_err(y.detach().cpu().numpy(), yr.detach().numpy()) <= tol
-    assert rel_err(x.grad.cpu().numpy(), xr.grad.numpy()) <= 5 * tol
-    assert rel_err(layer.kernel.grad.cpu().numpy(), wr.grad.numpy()) <= 5 * tol
-    assert rel_err(layer.bias.grad.cpu().numpy(), br.grad.numpy()) <= 5 * tol
+    assert rel_err(x.grad.detach().cpu().numpy(), xr.grad.numpy()) <= 5 * tol
+    assert rel_err(layer.kernel.grad.detach().cpu().numpy(), wr.grad.numpy()) <= 5 * tol
+    assert rel_err(layer.bias.grad.detach().cpu().numpy(), br.grad.numpy()) <= 5 * tol
     if use_bn:  # moving statistics, momentum 0.9 (gnn_layers.py:53)
         zz = orc.torch_cpu_graph_conv(xr, g["Lt"], wr, g["K"], "chebyshev").detach()
-        assert rel_err(layer.bn.moving_mean.cpu().numpy(), 0.1 * zz.mean(dim=(0, 1)).numpy()) < 1e-4
-        assert rel_err(layer.bn.moving_variance.cpu().numpy(),
+        assert rel_err(layer.bn.moving_mean.detach().cpu().numpy(), 0.1 * zz.mean(dim=(0, 1)).numpy()) < 1e-4
+        assert rel_err(layer.bn.moving_variance.detach().cpu().numpy(),
                        0.9 + 0.1 * zz.var(dim=(0, 1), unbiased=False).numpy()) < 1e-4
 
 
@@ -125,12 +125,12 @@ def test_spmm_generic_shapes_tail_and_transpose(F, transpose):
     assert info["tail_rows"] >= 2 and info["symmetric"] == 0 and info["nnz"] == A.nnz
     B = 3
     x, prev, add = (rng.standard_normal((B, M, F)).astype(np.float32) for _ in range(3))
-    out = _ops.spmm(plan, dev(x), 2.0, dev(prev), -1.0, dev(add), 0.5, transpose=transpose).cpu().numpy()
+    out = _ops.spmm(plan, dev(x), 2.0, dev(prev), -1.0, dev(add), 0.5, transpose=transpose).detach().cpu().numpy()
     Aop = A.T.tocsr() if transpose else A
     ref = np.stack([2.0 * (Aop @ x[b].astype(np.float64)) - prev[b] + 0.5 * add[b] for b in range(B)])
     assert rel_err(out, ref) <= TOL_FP32
     # the 2-D reference signature
-    out2 = utils.split_sparse_dense_matmul(plan, dev(x[0]), n_splits=4).cpu().numpy()
+    out2 = utils.split_sparse_dense_matmul(plan, dev(x[0]), n_splits=4).detach().cpu().numpy()
     assert rel_err(out2, A @ x[0].astype(np.float64)) <= TOL_FP32
 
 
@@ -144,15 +144,15 @@ def test_small_K_and_default_fout(K, cls):
     xt = dev(x).requires_grad_(True)
     y = layer(xt)
     assert tuple(y.shape) == (2, 192, 3)
-    w = layer.kernel.detach().double().cpu().numpy()
+    w = layer.kernel.detach().double().detach().cpu().numpy()
     Lt, _ = orc.prepare_laplacian(g["L"], 0.75 if cls == "Chebyshev" else 1.0)
     rec = cls.lower()
     assert rel_err(y.detach().cpu().numpy(), orc.graph_conv_forward(x, Lt, w, K, rec, dtype=np.float64)) <= TOL_FP32
     dy = rng.standard_normal((2, 192, 3))
     y.backward(dev(dy))
     dx, dk, _ = orc.graph_conv_backward(x, Lt, w, K, dy, rec)
-    assert rel_err(xt.grad.cpu().numpy(), dx) <= TOL_FP32
-    assert rel_err(layer.kernel.grad.cpu().numpy(), dk) <= TOL_FP32
+    assert rel_err(xt.grad.detach().cpu().numpy(), dx) <= TOL_FP32
+    assert rel_err(layer.kernel.grad.detach().cpu().numpy(), dk) <= TOL_FP32
 
 
 def test_unsymmetric_laplacian_gradient():
@@ -168,17 +168,17 @@ def test_unsymmetric_laplacian_gradient():
     y.backward(dev(dy))
     Lt = sparse.csr_matrix((layer._L_values.astype(np.float64), (layer._L_indices[:, 0], layer._L_indices[:, 1])),
                            shape=(M, M))
-    w = layer.kernel.detach().double().cpu().numpy()
+    w = layer.kernel.detach().double().detach().cpu().numpy()
     dx, dk, _ = orc.graph_conv_backward(x, Lt, w, 4, dy, "monomial")
     assert rel_err(y.detach().cpu().numpy(), orc.graph_conv_forward(x, Lt, w, 4, "monomial", dtype=np.float64)) <= 2e-5
-    assert rel_err(xt.grad.cpu().numpy(), dx) <= 2e-5 and rel_err(layer.kernel.grad.cpu().numpy(), dk) <= 2e-5
+    assert rel_err(xt.grad.detach().cpu().numpy(), dx) <= 2e-5 and rel_err(layer.kernel.grad.detach().cpu().numpy(), dk) <= 2e-5
 
 
 def test_pool_bit_exact_and_reference_known_answer():
     g = np.load(f"{GOLDEN}/pool_nside4.npz")
     m_in = g["m_in"]  # float64 in the reference test; the layer computes in floatx = float32
-    avg = healpy_layers.HealpyPool(1, pool_type="AVG")(m_in[None, :, None]).cpu().numpy().ravel()
-    mx = healpy_layers.HealpyPool(1, pool_type="MAX")(m_in[None, :, None]).cpu().numpy().ravel()
+    avg = healpy_layers.HealpyPool(1, pool_type="AVG")(m_in[None, :, None]).detach().cpu().numpy().ravel()
+    mx = healpy_layers.HealpyPool(1, pool_type="MAX")(m_in[None, :, None]).detach().cpu().numpy().ravel()
     assert np.all(np.abs(g["avg"] - avg) < 1e-5) and np.all(np.abs(g["max"] - mx) < 1e-5)  # the reference's bar
     rng = np.random.default_rng(0)
     for (B, M, F, p) in [(2, 192, 1, 1), (3, 768, 5, 2), (2, 3072, 16, 3), (1, 768, 64, 1), (2, 48, 3, 1)]:
@@ -191,7 +191,7 @@ def test_pool_bit_exact_and_reference_known_answer():
             assert np.array_equal(y.detach().cpu().numpy(), ref), (B, M, F, p, typ)  # bit-exact
             dy = rng.standard_normal(ref.shape).astype(np.float32)
             y.backward(torch.tensor(dy).cuda())
-            assert np.array_equal(xt.grad.cpu().numpy(), orc.healpy_pool_backward(x, dy, p, typ)), (typ, p)
+            assert np.array_equal(xt.grad.detach().cpu().numpy(), orc.healpy_pool_backward(x, dy, p, typ)), (typ, p)
     with pytest.raises(IOError):
         healpy_layers.HealpyPool(1)(np.zeros((1, 10, 1), np.float32))
 
@@ -220,9 +220,9 @@ def test_pseudo_conv_and_transpose(act):
     dy = np.random.default_rng(1).standard_normal(ref.shape)
     y.backward(dev(dy))
     yr.backward(torch.tensor(dy))
-    assert rel_err(xt.grad.cpu().numpy(), xr.grad.numpy()) <= TOL_FP32
-    assert rel_err(pc.kernel.grad.cpu().numpy(), wr.grad.numpy()) <= TOL_FP32
-    assert rel_err(pc.bias.grad.cpu().numpy(), br.grad.numpy()) <= TOL_FP32
+    assert rel_err(xt.grad.detach().cpu().numpy(), xr.grad.numpy()) <= TOL_FP32
+    assert rel_err(pc.kernel.grad.detach().cpu().numpy(), wr.grad.numpy()) <= TOL_FP32
+    assert rel_err(pc.bias.grad.detach().cpu().numpy(), br.grad.numpy()) <= TOL_FP32
 
     xs = x[:, :48]
     pt = healpy_layers.HealpyPseudoConv_Transpose(p=2, Fout=5, activation=act)
@@ -243,9 +243,9 @@ def test_pseudo_conv_and_transpose(act):
     dy = np.random.default_rng(2).standard_normal(ref.shape)
     y.backward(dev(dy))
     yr.backward(torch.tensor(dy))
-    assert rel_err(xt.grad.cpu().numpy(), xr.grad.numpy()) <= TOL_FP32
-    assert rel_err(pt.kernel.grad.cpu().numpy(), wr.grad.numpy()) <= TOL_FP32
-    assert rel_err(pt.bias.grad.cpu().numpy(), br.grad.numpy()) <= TOL_FP32
+    assert rel_err(xt.grad.detach().cpu().numpy(), xr.grad.numpy()) <= TOL_FP32
+    assert rel_err(pt.kernel.grad.detach().cpu().numpy(), wr.grad.numpy()) <= TOL_FP32
+    assert rel_err(pt.bias.grad.detach().cpu().numpy(), br.grad.numpy()) <= TOL_FP32
 
 
 def test_reference_shape_tests():
@@ -271,8 +271,8 @@ def test_property_constant_eigenvector_closed_form():
         K, Fin, Fout = 6, 4, 3
         layer = gnn_layers.Chebyshev(L=g.L, K=K, Fout=Fout)
         x = np.repeat(v[None, :, None], Fin, axis=2).astype(np.float32) * np.arange(1, Fin + 1, dtype=np.float32)
-        y = layer(x).cpu().numpy()
-        w = layer.kernel.detach().double().cpu().numpy().reshape(Fin, K, Fout)
+        y = layer(x).detach().cpu().numpy()
+        w = layer.kernel.detach().double().detach().cpu().numpy().reshape(Fin, K, Fout)
         coef = np.einsum("f,fko,k->o", np.arange(1, Fin + 1.0), w, (-1.0) ** np.arange(K))
         ref = v[None, :, None] * coef[None, None, :]
         assert rel_err(y, ref) <= 5e-5  # K hops of fp32 round-off on top of the fp32 L~ values
