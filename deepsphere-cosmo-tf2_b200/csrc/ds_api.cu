@@ -1,6 +1,8 @@
 // C-ABI compute entries: graph convolution forward/backward (Chebyshev / Monomial),
 // bias+activation, pseudo-convolutions.  Each entry is a short sequence of launches of the
 // kernels in ds_spmm.cu / ds_gemm.cu / ds_umma.cu on the caller's stream.
+#include <algorithm>
+
 #include "ds_common.cuh"
 
 namespace ds {
@@ -15,6 +17,12 @@ int launch_umma_gemm(int64_t R, int64_t N, int64_t Kc, int nseg, const float* A0
                      int64_t a_seg_stride_rows, const float* Bm, int64_t b_k_stride, int64_t b_seg_stride,
                      int64_t b_n_stride, const float* bias, int64_t bias_mod, int act, float* C, int64_t ldc, int mode,
                      cudaStream_t st);
+
+int umma_tn_supported(int64_t R, int64_t N, int64_t Kc, int nseg);
+int64_t umma_tn_workspace_elems(int64_t R, int64_t N, int64_t Kc, int nseg);
+int launch_umma_gemm_tn(int64_t R, int64_t N, int64_t Kc, int nseg, const float* A0, const float* Arest, const float* D,
+                        float* C, int64_t ldc, int64_t c_kc_stride, int64_t c_seg_stride, float* partial, int mode,
+                        cudaStream_t st);
 
 namespace {
 
@@ -84,7 +92,8 @@ int64_t ds_graph_conv_backward_workspace_elems(int64_t M, int64_t B, int64_t Fin
   if (act != DS_ACT_LINEAR) n += R * Fout;                  // dz
   if (!have_basis && K > 1) n += (int64_t)(K - 1) * A;      // recomputed basis
   n += 4 * A;                                               // G_k + three Clenshaw buffers
-  n += gemm_tn_workspace_elems(R, Fin, K, Fout);            // dkernel split partials
+  n += std::max(gemm_tn_workspace_elems(R, Fin, K, Fout),   // dkernel split partials (fp32 / tensor-core kernel)
+                umma_tn_workspace_elems(R, Fout, Fin, K));
   n += colsum_workspace_elems(Fout);                        // dbias partials
   return n + 64;
 }
@@ -118,13 +127,17 @@ int ds_graph_conv_backward(const ds_plan_t* plan, int32_t recursion, int32_t K, 
   }
   float* G = take(A);
   float* buf[3] = {take(A), take(A), take(A)};
-  float* tn_partial = take(gemm_tn_workspace_elems(R, Fin, K, Fout));
+  float* tn_partial = take(std::max(gemm_tn_workspace_elems(R, Fin, K, Fout), umma_tn_workspace_elems(R, Fout, Fin, K)));
   float* cs_partial = take(colsum_workspace_elems(Fout));
 
   // 3. dbias = sum_{b,m} dz
   if (dbias != nullptr) DS_TRY(launch_colsum(R, Fout, Fout, dz, dbias, cs_partial, st));
   // 4. dkernel[f*K + k, o] = sum_{b,m} T_k[b,m,f] dz[b,m,o]
-  DS_TRY(launch_gemm_tn(R, Fout, Fin, K, x, T, A, Fin, dz, Fout, dkernel, Fout, K, 1, tn_partial, st));
+  if (mode != DS_MODE_FP32 && umma_tn_supported(R, Fout, Fin, K) == 0) {
+    DS_TRY(launch_umma_gemm_tn(R, Fout, Fin, K, x, T, dz, dkernel, Fout, K, 1, tn_partial, mode, st));
+  } else {
+    DS_TRY(launch_gemm_tn(R, Fout, Fin, K, x, T, A, Fin, dz, Fout, dkernel, Fout, K, 1, tn_partial, st));
+  }
   if (dx == nullptr) return 0;
 
   // 5. dx = sum_k T_k(L~^T) G_k,  G_k[b,m,f] = sum_o dz[b,m,o] kernel[f*K + k, o]   (Clenshaw / Horner)

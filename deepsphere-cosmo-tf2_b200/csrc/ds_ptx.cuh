@@ -65,6 +65,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, int
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// 3-D tiled load: coordinates (c0 = innermost element index, c1 = row, c2 = slab)
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, int32_t c0, int32_t c1, int32_t c2,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // 1-D bulk copy global -> shared (16-byte aligned, size multiple of 16)
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile(

@@ -58,12 +58,13 @@ __device__ __forceinline__ void store_stream<4>(float* p, const Vec<4>& a) {
 // compact patch of the sphere, so the ~9 gathers per row hit rows the same CTA (same SM) has just
 // touched: the re-use is served by L1 instead of L2, and HBM sees each input row about once.
 template <int V>
-__global__ void __launch_bounds__(512, 2) spmm_ell_kernel(const int32_t* __restrict__ ell_col,
-                                                           const float* __restrict__ ell_val, int W, int64_t M,
-                                                           int64_t B, int64_t F, const float* __restrict__ in,
-                                                           float alpha, const float* __restrict__ prev, float beta,
-                                                           const float* __restrict__ add, float gamma,
-                                                           float* __restrict__ out, int lpr_log2, int unit_rows) {
+__global__ void __launch_bounds__(256, 3) spmm_ell_kernel(const int32_t* __restrict__ ell_col,
+                                                          const float* __restrict__ ell_val, int W, int64_t M,
+                                                          int64_t B, int64_t F, const float* __restrict__ in,
+                                                          float alpha, const float* __restrict__ prev, float beta,
+                                                          const float* __restrict__ add, float gamma,
+                                                          float* __restrict__ out, int lpr_log2, int unit_rows) {
+  constexpr int CH = 9;  // gathers kept in flight per thread (= the HEALPix row length: 8 neighbours + diagonal)
   const int lpr = 1 << lpr_log2;
   const int groups_per_block = blockDim.x >> lpr_log2;
   const int g = threadIdx.x >> lpr_log2;
@@ -80,27 +81,38 @@ __global__ void __launch_bounds__(512, 2) spmm_ell_kernel(const int32_t* __restr
       const int32_t* cols = ell_col + m * W;
       const float* vals = ell_val + m * W;
       for (int64_t c = sub; c < FV; c += lpr) {
+        const int64_t off = (b * M + m) * F + c * V;
+        // the two streamed operands first, so their latency overlaps the gathers
+        Vec<V> pv, av;
+        if (prev != nullptr) pv = load_stream<V>(prev + off);
+        if (add != nullptr) av = load_stream<V>(add + off);
         Vec<V> acc;
 #pragma unroll
         for (int i = 0; i < V; ++i) acc.v[i] = 0.f;
-#pragma unroll 3
-        for (int n = 0; n < W; ++n) {
-          const int32_t col = __ldg(cols + n);
-          const float w = __ldg(vals + n);
-          Vec<V> xv = Vec<V>::load(inb + (int64_t)col * F + c * V);
+        for (int n0 = 0; n0 < W; n0 += CH) {
+          int32_t col[CH];
+          float w[CH];
 #pragma unroll
-          for (int i = 0; i < V; ++i) acc.v[i] = fmaf(w, xv.v[i], acc.v[i]);
+          for (int i = 0; i < CH; ++i) {
+            const bool ok = n0 + i < W;
+            col[i] = ok ? __ldg(cols + n0 + i) : (int32_t)m;
+            w[i] = ok ? __ldg(vals + n0 + i) : 0.f;
+          }
+          Vec<V> xv[CH];
+#pragma unroll
+          for (int i = 0; i < CH; ++i) xv[i] = Vec<V>::load(inb + (int64_t)col[i] * F + c * V);
+#pragma unroll
+          for (int i = 0; i < CH; ++i)
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc.v[e] = fmaf(w[i], xv[i].v[e], acc.v[e]);
         }
-        const int64_t off = (b * M + m) * F + c * V;
 #pragma unroll
         for (int i = 0; i < V; ++i) acc.v[i] *= alpha;
         if (prev != nullptr) {
-          Vec<V> pv = load_stream<V>(prev + off);
 #pragma unroll
           for (int i = 0; i < V; ++i) acc.v[i] = fmaf(beta, pv.v[i], acc.v[i]);
         }
         if (add != nullptr) {
-          Vec<V> av = load_stream<V>(add + off);
 #pragma unroll
           for (int i = 0; i < V; ++i) acc.v[i] = fmaf(gamma, av.v[i], acc.v[i]);
         }
@@ -157,9 +169,9 @@ int launch_spmm(const SparseDev& S, int64_t B, int64_t F, const float* in, float
   int unit_rows = 64;
   while (unit_rows < 4096 && (int64_t)unit_rows * 4 * F * 4 <= 65536) unit_rows *= 4;
   const int64_t units_per_b = (S.M + unit_rows - 1) / unit_rows;
-  const int64_t max_blocks = (int64_t)num_sms() * 2 * 8;
+  const int64_t max_blocks = (int64_t)num_sms() * 3 * 8;
   const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>(B * units_per_b, max_blocks));
-  const int threads = 512;
+  const int threads = 256;
   if (vec4) {
     spmm_ell_kernel<4><<<(unsigned)blocks, threads, 0, st>>>(S.ell_col, S.ell_val, S.W, S.M, B, F, in, alpha, prev,
                                                              prev ? beta : 0.f, add, add ? gamma : 0.f, out, lpr_log2,

@@ -47,8 +47,26 @@ def run(M, B, Fin, Fout, K, mode, pattern):
     return err
 
 
+def tf32_conversion_probe():
+    """x = 1 + 2^-11 + 2^-12 sits between two TF32 values (1 and 1 + 2^-10): truncation gives 1,
+    round-to-nearest gives 1 + 2^-10.  K = 1, W = identity-ish so y = tf32(x) * 1."""
+    M, Fin, Fout = 128, 32, 32
+    layer = gnn_layers.Chebyshev(L=np.eye(M), K=1, Fout=Fout, mode="tf32")
+    layer.build_from_shape((1, M, Fin))
+    W = np.zeros((Fin, Fout), np.float32)
+    W[np.arange(Fout), np.arange(Fout)] = 1.0
+    x = np.full((1, M, Fin), 1.0 + 2.0**-11 + 2.0**-12, np.float32)
+    with torch.no_grad():
+        layer.kernel.copy_(torch.tensor(W).cuda())
+        y = layer(torch.tensor(x).cuda()).cpu().numpy()
+    v = float(y[0, 0, 0])
+    kind = "truncation" if v == 1.0 else ("round-to-nearest" if v == 1.0 + 2.0**-10 else f"other ({v!r})")
+    print(f"hardware fp32->tf32 conversion of the A operand: {kind} (y = 1 + {v - 1.0:.3e})")
+
+
 if __name__ == "__main__":
     torch.cuda.set_device(0)
+    tf32_conversion_probe()
     worst = {}
     for mode in ("tf32", "tf32x3"):
         errs = []
