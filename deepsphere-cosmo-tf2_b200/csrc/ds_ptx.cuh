@@ -96,7 +96,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
 //   [46,48) version = 1 (sm_100) | [49,52) base offset | [61,64) layout type
-constexpr uint64_t LAYOUT_SWIZZLE_NONE = 0, LAYOUT_SWIZZLE_128B = 2, LAYOUT_SWIZZLE_64B = 4, LAYOUT_SWIZZLE_32B = 6;
+constexpr uint64_t LAYOUT_SWIZZLE_NONE = 0, LAYOUT_SWIZZLE_128B_BASE32B = 1, LAYOUT_SWIZZLE_128B = 2, LAYOUT_SWIZZLE_64B = 4, LAYOUT_SWIZZLE_32B = 6;
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                                    uint64_t layout_type) {
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |

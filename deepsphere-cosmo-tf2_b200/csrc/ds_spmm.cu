@@ -77,6 +77,25 @@ __global__ void __launch_bounds__(256, 3) spmm_ell_kernel(const int32_t* __restr
     const int64_t m0 = (u - b * units_per_b) * unit_rows;
     const int64_t m1 = min(M, m0 + (int64_t)unit_rows);
     const float* inb = in + b * M * F;
+    {
+      // software prefetch of the NEXT unit this CTA will visit (its own rows of `in`, `prev`, `add`) into
+      // L2: the kernel is bound by DRAM latency x requests in flight, and this doubles the latter
+      const int64_t u2 = u + gridDim.x;
+      if (u2 < n_units) {
+        const int64_t b2 = u2 / units_per_b;
+        const int64_t r2 = b2 * M + (u2 - b2 * units_per_b) * unit_rows;
+        const int64_t rows2 = min((int64_t)unit_rows, M - (u2 - b2 * units_per_b) * unit_rows);
+        const int64_t bytes = rows2 * F * 4;
+        const char* p_in = reinterpret_cast<const char*>(in + r2 * F);
+        const char* p_prev = prev ? reinterpret_cast<const char*>(prev + r2 * F) : nullptr;
+        const char* p_add = add ? reinterpret_cast<const char*>(add + r2 * F) : nullptr;
+        for (int64_t o = (int64_t)threadIdx.x * 128; o < bytes; o += (int64_t)blockDim.x * 128) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p_in + o));
+          if (p_prev) asm volatile("prefetch.global.L2 [%0];" ::"l"(p_prev + o));
+          if (p_add) asm volatile("prefetch.global.L2 [%0];" ::"l"(p_add + o));
+        }
+      }
+    }
     for (int64_t m = m0 + g; m < m1; m += groups_per_block) {
       const int32_t* cols = ell_col + m * W;
       const float* vals = ell_val + m * W;

@@ -2,8 +2,10 @@
 //   dW[(kc*c_kc_stride + seg*c_seg_stride), n] = sum_r A_seg[r, kc] * D[r, n]        (reduction over R rows)
 // i.e. dkernel = X_stack^T * dY of the contraction at gnn_layers.py:149, with the K basis
 // tensors read in place.  The reduction dimension r is the *strided* one for both operands, so both
-// are fed MN-major: a TMA box {32 channels, 16 rows} with SWIZZLE_128B lands exactly as the canonical
-// MN-major UMMA atom (8 k-rows x 128 B), no transposes anywhere.
+// are fed MN-major.  For 32-bit (tf32) MN-major operands the only UMMA shared-memory layout is the
+// "128-byte swizzle with 32-byte atoms" (UMMA layout type SWIZZLE_128B_BASE32B: 4 k-rows x 128 B atoms,
+// 32-byte chunk index XOR k-row % 4), which is exactly what a TMA box {32 channels, 16 rows} written with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B produces - no transposes anywhere.
 //
 // Work split: each persistent CTA reduces a contiguous range of rows for ALL nseg*Kc x N outputs,
 // accumulated in TMEM (ceil(nseg*ceil(Kc/32)/4) accumulators of 128 lanes x N columns), so every input
@@ -110,13 +112,13 @@ umma_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
       ptx::tc_fence_after_sync();
       if (ptx::elect_one()) {
         const uint32_t st = ptx::smem_u32(stage_base + (size_t)s * p.stage_bytes);
-        // MN-major SWIZZLE_128B: LBO = distance between 32-channel blocks, SBO = 1024 (8 k-rows)
-        const uint64_t d_hi = ptx::make_smem_desc(st + off_d, BLK_BYTES, 1024, ptx::LAYOUT_SWIZZLE_128B);
-        const uint64_t d_lo = ptx::make_smem_desc(st + off_lo + off_d, BLK_BYTES, 1024, ptx::LAYOUT_SWIZZLE_128B);
+        // MN-major, 32-byte-atom 128B swizzle: LBO = distance between 32-channel blocks, SBO = 512 (4 k-rows)
+        const uint64_t d_hi = ptx::make_smem_desc(st + off_d, BLK_BYTES, 512, ptx::LAYOUT_SWIZZLE_128B_BASE32B);
+        const uint64_t d_lo = ptx::make_smem_desc(st + off_lo + off_d, BLK_BYTES, 512, ptx::LAYOUT_SWIZZLE_128B_BASE32B);
         for (int mt = 0; mt < p.m_tiles; ++mt) {
-          const uint64_t a_hi = ptx::make_smem_desc(st + mt * 4 * BLK_BYTES, BLK_BYTES, 1024, ptx::LAYOUT_SWIZZLE_128B);
+          const uint64_t a_hi = ptx::make_smem_desc(st + mt * 4 * BLK_BYTES, BLK_BYTES, 512, ptx::LAYOUT_SWIZZLE_128B_BASE32B);
           const uint64_t a_lo =
-              ptx::make_smem_desc(st + off_lo + mt * 4 * BLK_BYTES, BLK_BYTES, 1024, ptx::LAYOUT_SWIZZLE_128B);
+              ptx::make_smem_desc(st + off_lo + mt * 4 * BLK_BYTES, BLK_BYTES, 512, ptx::LAYOUT_SWIZZLE_128B_BASE32B);
           const uint32_t d_tmem = tmem_base + (uint32_t)(mt * p.N);
 #pragma unroll
           for (int j = 0; j < BKR / 8; ++j) {
@@ -228,7 +230,7 @@ EncodeTiledFn encode_fn_tn() {
   return fn;
 }
 
-// 3-D fp32 tensor [slabs, rows, cols] (contiguous), box = {32 cols, 16 rows, 1 slab}, SWIZZLE_128B;
+// 3-D fp32 tensor [slabs, rows, cols] (contiguous), box = {32 cols, 16 rows, 1 slab}, SWIZZLE_128B_ATOM_32B;
 // out-of-range rows / columns are zero-filled, which is what makes ragged R and Kc < 32 exact.
 int make_rows_map(CUtensorMap* map, const float* base, int64_t slabs, int64_t rows, int64_t cols) {
   EncodeTiledFn fn = encode_fn_tn();
@@ -238,7 +240,7 @@ int make_rows_map(CUtensorMap* map, const float* base, int64_t slabs, int64_t ro
   cuuint32_t box[3] = {(cuuint32_t)BLK, (cuuint32_t)BKR, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DS_CHECK(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed with code %d (slabs=%lld rows=%lld cols=%lld)",
            (int)rc, (long long)slabs, (long long)rows, (long long)cols);
