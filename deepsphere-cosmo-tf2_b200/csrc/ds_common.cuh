@@ -59,6 +59,8 @@ struct SparseDev {
   int32_t W = 0;              // ELL width
   int32_t* ell_col = nullptr; // [M, W]  padded with col = row, val = 0
   float* ell_val = nullptr;   // [M, W]
+  int32_t Wp = 0;             // packed row length (W rounded up to even)
+  int4* ell_pk = nullptr;     // [M, Wp/2] of (col0, val0 bits, col1, val1 bits): one 16-byte load = 2 entries
   int64_t n_tail_rows = 0;    // rows with more than W entries
   int64_t tail_nnz = 0;
   int32_t* tail_rows = nullptr;   // [n_tail_rows]

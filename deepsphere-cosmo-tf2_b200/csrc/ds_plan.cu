@@ -113,6 +113,21 @@ int build_sparse_dev(const HostCsr& A, int32_t width, SparseDev& S, int64_t& byt
       trowptr.push_back((int64_t)tcol.size());
     }
   }
+  // packed copy for the vectorised hop kernel: (col, val) pairs, two per 16-byte word
+  S.Wp = (W + 1) & ~1;
+  std::vector<int4> pk((size_t)M * (S.Wp / 2));
+  for (int64_t r = 0; r < M; ++r)
+    for (int32_t j = 0; j < S.Wp; j += 2) {
+      int4 q;
+      q.x = j < W ? ecol[(size_t)r * W + j] : (int32_t)r;
+      const float v0 = j < W ? eval[(size_t)r * W + j] : 0.f;
+      q.z = j + 1 < W ? ecol[(size_t)r * W + j + 1] : (int32_t)r;
+      const float v1 = j + 1 < W ? eval[(size_t)r * W + j + 1] : 0.f;
+      std::memcpy(&q.y, &v0, 4);
+      std::memcpy(&q.w, &v1, 4);
+      pk[(size_t)r * (S.Wp / 2) + j / 2] = q;
+    }
+  DS_TRY(upload(pk, &S.ell_pk, bytes));
   S.n_tail_rows = (int64_t)trows.size();
   S.tail_nnz = (int64_t)tcol.size();
   DS_TRY(upload(ecol, &S.ell_col, bytes));
@@ -127,6 +142,7 @@ int build_sparse_dev(const HostCsr& A, int32_t width, SparseDev& S, int64_t& byt
 void free_sparse_dev(SparseDev& S) {
   cudaFree(S.ell_col);
   cudaFree(S.ell_val);
+  cudaFree(S.ell_pk);
   cudaFree(S.tail_rows);
   cudaFree(S.tail_rowptr);
   cudaFree(S.tail_col);

@@ -77,25 +77,6 @@ __global__ void __launch_bounds__(256, 3) spmm_ell_kernel(const int32_t* __restr
     const int64_t m0 = (u - b * units_per_b) * unit_rows;
     const int64_t m1 = min(M, m0 + (int64_t)unit_rows);
     const float* inb = in + b * M * F;
-    {
-      // software prefetch of the NEXT unit this CTA will visit (its own rows of `in`, `prev`, `add`) into
-      // L2: the kernel is bound by DRAM latency x requests in flight, and this doubles the latter
-      const int64_t u2 = u + gridDim.x;
-      if (u2 < n_units) {
-        const int64_t b2 = u2 / units_per_b;
-        const int64_t r2 = b2 * M + (u2 - b2 * units_per_b) * unit_rows;
-        const int64_t rows2 = min((int64_t)unit_rows, M - (u2 - b2 * units_per_b) * unit_rows);
-        const int64_t bytes = rows2 * F * 4;
-        const char* p_in = reinterpret_cast<const char*>(in + r2 * F);
-        const char* p_prev = prev ? reinterpret_cast<const char*>(prev + r2 * F) : nullptr;
-        const char* p_add = add ? reinterpret_cast<const char*>(add + r2 * F) : nullptr;
-        for (int64_t o = (int64_t)threadIdx.x * 128; o < bytes; o += (int64_t)blockDim.x * 128) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(p_in + o));
-          if (p_prev) asm volatile("prefetch.global.L2 [%0];" ::"l"(p_prev + o));
-          if (p_add) asm volatile("prefetch.global.L2 [%0];" ::"l"(p_add + o));
-        }
-      }
-    }
     for (int64_t m = m0 + g; m < m1; m += groups_per_block) {
       const int32_t* cols = ell_col + m * W;
       const float* vals = ell_val + m * W;
@@ -137,6 +118,66 @@ __global__ void __launch_bounds__(256, 3) spmm_ell_kernel(const int32_t* __restr
         }
         store_stream<V>(out + off, acc);
       }
+    }
+  }
+}
+
+// Fast path (F % 4 == 0, F <= 128): packed ELL - one 16-byte load brings two (column, value) entries -
+// 32-bit index arithmetic and all gathers of a 10-entry chunk in flight before the FMAs.  Roughly half
+// the instructions per row of the generic kernel above, which ncu showed to be issue-bound (r1b).
+__global__ void __launch_bounds__(256, 2) spmm_ell_pk_kernel(const int4* __restrict__ ell_pk, int NP, int64_t M,
+                                                             int64_t B, int FV, const float4* __restrict__ in,
+                                                             float alpha, const float4* __restrict__ prev, float beta,
+                                                             const float4* __restrict__ add, float gamma,
+                                                             float4* __restrict__ out, int lpr_log2, int unit_rows) {
+  constexpr int CHP = 5;  // 16-byte words per chunk = 10 entries (HEALPix rows: 9 + 1 pad)
+  const int groups_per_block = blockDim.x >> lpr_log2;
+  const int g = threadIdx.x >> lpr_log2;
+  const int c = threadIdx.x & ((1 << lpr_log2) - 1);
+  const int64_t units_per_b = (M + unit_rows - 1) / unit_rows;
+  const int64_t n_units = B * units_per_b;
+  if (c >= FV) return;
+  for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+    const int64_t b = u / units_per_b;
+    const int m0 = (int)((u - b * units_per_b) * unit_rows);
+    const int m1 = (int)min(M, (int64_t)m0 + unit_rows);
+    const float4* inb = in + b * M * FV;
+    for (int m = m0 + g; m < m1; m += groups_per_block) {
+      const int64_t off = (b * M + m) * FV + c;
+      float4 pv, av;
+      if (prev != nullptr) pv = __ldcs(prev + off);
+      if (add != nullptr) av = __ldcs(add + off);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int4* row = ell_pk + (int64_t)m * NP;
+      for (int n0 = 0; n0 < NP; n0 += CHP) {
+        int4 q[CHP];
+#pragma unroll
+        for (int i = 0; i < CHP; ++i) q[i] = n0 + i < NP ? __ldg(row + n0 + i) : make_int4(m, 0, m, 0);
+        float4 x0[CHP], x1[CHP];
+#pragma unroll
+        for (int i = 0; i < CHP; ++i) {
+          x0[i] = __ldg(inb + (uint32_t)(q[i].x * FV + c));
+          x1[i] = __ldg(inb + (uint32_t)(q[i].z * FV + c));
+        }
+#pragma unroll
+        for (int i = 0; i < CHP; ++i) {
+          const float w0 = __int_as_float(q[i].y), w1 = __int_as_float(q[i].w);
+          acc.x = fmaf(w0, x0[i].x, acc.x); acc.y = fmaf(w0, x0[i].y, acc.y);
+          acc.z = fmaf(w0, x0[i].z, acc.z); acc.w = fmaf(w0, x0[i].w, acc.w);
+          acc.x = fmaf(w1, x1[i].x, acc.x); acc.y = fmaf(w1, x1[i].y, acc.y);
+          acc.z = fmaf(w1, x1[i].z, acc.z); acc.w = fmaf(w1, x1[i].w, acc.w);
+        }
+      }
+      acc.x *= alpha; acc.y *= alpha; acc.z *= alpha; acc.w *= alpha;
+      if (prev != nullptr) {
+        acc.x = fmaf(beta, pv.x, acc.x); acc.y = fmaf(beta, pv.y, acc.y);
+        acc.z = fmaf(beta, pv.z, acc.z); acc.w = fmaf(beta, pv.w, acc.w);
+      }
+      if (add != nullptr) {
+        acc.x = fmaf(gamma, av.x, acc.x); acc.y = fmaf(gamma, av.y, acc.y);
+        acc.z = fmaf(gamma, av.z, acc.z); acc.w = fmaf(gamma, av.w, acc.w);
+      }
+      __stcs(out + off, acc);
     }
   }
 }
@@ -191,7 +232,12 @@ int launch_spmm(const SparseDev& S, int64_t B, int64_t F, const float* in, float
   const int64_t max_blocks = (int64_t)num_sms() * 3 * 8;
   const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>(B * units_per_b, max_blocks));
   const int threads = 256;
-  if (vec4) {
+  if (vec4 && F <= 128 && S.M * (F / 4) < (int64_t)1 << 31) {
+    spmm_ell_pk_kernel<<<(unsigned)blocks, threads, 0, st>>>(
+        S.ell_pk, S.Wp / 2, S.M, B, (int)(F / 4), reinterpret_cast<const float4*>(in), alpha,
+        reinterpret_cast<const float4*>(prev), prev ? beta : 0.f, reinterpret_cast<const float4*>(add),
+        add ? gamma : 0.f, reinterpret_cast<float4*>(out), lpr_log2, unit_rows);
+  } else if (vec4) {
     spmm_ell_kernel<4><<<(unsigned)blocks, threads, 0, st>>>(S.ell_col, S.ell_val, S.W, S.M, B, F, in, alpha, prev,
                                                              prev ? beta : 0.f, add, add ? gamma : 0.f, out, lpr_log2,
                                                              unit_rows);
