@@ -11,6 +11,7 @@
 // 9x re-use of each input row is served by L1/L2.  HBM-bound: algorithmic traffic is
 // read in + read prev + write out = 3 * B*M*F*4 bytes per hop (plan: M*W*8 bytes).
 #include "ds_common.cuh"
+#include "ds_ptx.cuh"
 
 namespace ds {
 namespace {
@@ -182,6 +183,118 @@ __global__ void __launch_bounds__(256, 2) spmm_ell_pk_kernel(const int4* __restr
   }
 }
 
+// Main path (F % 4 == 0, F <= 128): bulk-async staged hop.
+// A CTA walks "units" of U consecutive rows of one batch element (a compact NESTED patch).  One producer
+// thread streams each unit's contiguous slabs - its rows of `in`, of `prev` / `add`, and its packed ELL
+// words - into shared memory with cp.async.bulk, NSTAGE units ahead, completing on an mbarrier; the
+// consumer warps gather from shared memory and only go to global (L1/L2) for neighbours outside the unit.
+// Bytes in flight are therefore set by the pipeline depth (>= 150 KB per SM), not by how many loads a
+// thread can keep pending - which is what capped the register-gather kernels at ~3 TB/s (r1c bw_probe).
+struct TileStage {
+  uint64_t full;
+  uint64_t empty;
+};
+
+__global__ void __launch_bounds__(544, 1) spmm_tile_kernel(const int4* __restrict__ ell_pk, int NP, int64_t M, int64_t B,
+                                                           int FV, const float4* __restrict__ in, float alpha,
+                                                           const float4* __restrict__ prev, float beta,
+                                                           const float4* __restrict__ add, float gamma,
+                                                           float4* __restrict__ out, int lpr_log2, int U, int nstage) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t in_bytes = (uint32_t)U * FV * 16;
+  const uint32_t ell_bytes = (uint32_t)U * NP * 16;
+  const uint32_t n_slabs = 1u + (prev ? 1u : 0u) + (add ? 1u : 0u);
+  const uint32_t stage_bytes = n_slabs * in_bytes + ell_bytes;
+  TileStage* bars = reinterpret_cast<TileStage*>(smem + (size_t)nstage * stage_bytes);
+  const int n_consumers = blockDim.x - 32;
+  const int64_t units_per_b = (M + U - 1) / U;
+  const int64_t n_units = B * units_per_b;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstage; ++s) {
+      ptx::mbar_init(&bars[s].full, 1);
+      ptx::mbar_init(&bars[s].empty, n_consumers);
+    }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) {
+      uint32_t it = 0;
+      for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+        const int s = it % nstage;
+        ptx::mbar_wait(&bars[s].empty, ((it / nstage) & 1) ^ 1);
+        const int64_t b = u / units_per_b;
+        const int64_t m0 = (u - b * units_per_b) * U;
+        const uint32_t rows = (uint32_t)min((int64_t)U, M - m0);
+        const uint32_t nb = rows * FV * 16, eb = rows * NP * 16;
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        ptx::mbar_arrive_expect_tx(&bars[s].full, n_slabs * nb + eb);
+        const int64_t goff = (b * M + m0) * FV;
+        ptx::bulk_load_1d(st, in + goff, nb, &bars[s].full);
+        uint32_t o = in_bytes;
+        if (prev) { ptx::bulk_load_1d(st + o, prev + goff, nb, &bars[s].full); o += in_bytes; }
+        if (add) { ptx::bulk_load_1d(st + o, add + goff, nb, &bars[s].full); o += in_bytes; }
+        ptx::bulk_load_1d(st + o, ell_pk + m0 * NP, eb, &bars[s].full);
+      }
+    }
+    return;
+  }
+
+  const int t = threadIdx.x - 32;
+  const int groups = n_consumers >> lpr_log2;
+  const int g = t >> lpr_log2;
+  const int c = t & ((1 << lpr_log2) - 1);
+  const bool active = c < FV;
+  uint32_t it = 0;
+  for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+    const int s = it % nstage;
+    ptx::mbar_wait(&bars[s].full, (it / nstage) & 1);
+    const int64_t b = u / units_per_b;
+    const int m0 = (int)((u - b * units_per_b) * U);
+    const int rows = (int)min((int64_t)U, M - m0);
+    const uint8_t* st = smem + (size_t)s * stage_bytes;
+    const float4* s_in = reinterpret_cast<const float4*>(st);
+    const float4* s_prev = reinterpret_cast<const float4*>(st + in_bytes);
+    const float4* s_add = reinterpret_cast<const float4*>(st + (prev ? 2 : 1) * in_bytes);
+    const int4* s_ell = reinterpret_cast<const int4*>(st + n_slabs * in_bytes);
+    const float4* inb = in + b * M * FV;
+    float4* outb = out + (b * M + m0) * FV;
+    if (active) {
+      for (int r = g; r < rows; r += groups) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int4* row = s_ell + r * NP;
+#pragma unroll 2
+        for (int n = 0; n < NP; ++n) {
+          const int4 q = row[n];
+          const uint32_t l0 = (uint32_t)(q.x - m0), l1 = (uint32_t)(q.z - m0);
+          const float4 x0 = l0 < (uint32_t)rows ? s_in[l0 * FV + c] : __ldg(inb + (uint32_t)(q.x * FV + c));
+          const float4 x1 = l1 < (uint32_t)rows ? s_in[l1 * FV + c] : __ldg(inb + (uint32_t)(q.z * FV + c));
+          const float w0 = __int_as_float(q.y), w1 = __int_as_float(q.w);
+          acc.x = fmaf(w0, x0.x, acc.x); acc.y = fmaf(w0, x0.y, acc.y);
+          acc.z = fmaf(w0, x0.z, acc.z); acc.w = fmaf(w0, x0.w, acc.w);
+          acc.x = fmaf(w1, x1.x, acc.x); acc.y = fmaf(w1, x1.y, acc.y);
+          acc.z = fmaf(w1, x1.z, acc.z); acc.w = fmaf(w1, x1.w, acc.w);
+        }
+        acc.x *= alpha; acc.y *= alpha; acc.z *= alpha; acc.w *= alpha;
+        if (prev != nullptr) {
+          const float4 pv = s_prev[r * FV + c];
+          acc.x = fmaf(beta, pv.x, acc.x); acc.y = fmaf(beta, pv.y, acc.y);
+          acc.z = fmaf(beta, pv.z, acc.z); acc.w = fmaf(beta, pv.w, acc.w);
+        }
+        if (add != nullptr) {
+          const float4 av = s_add[r * FV + c];
+          acc.x = fmaf(gamma, av.x, acc.x); acc.y = fmaf(gamma, av.y, acc.y);
+          acc.z = fmaf(gamma, av.z, acc.z); acc.w = fmaf(gamma, av.w, acc.w);
+        }
+        __stcs(outb + r * FV + c, acc);
+      }
+    }
+    ptx::mbar_arrive(&bars[s].empty);  // this thread is done reading the stage
+  }
+}
+
 // rows longer than the ELL width: out[b,row,:] += alpha * sum_tail val * in[b,col,:]
 __global__ void __launch_bounds__(256) spmm_tail_kernel(const int32_t* __restrict__ tail_rows,
                                                         const int64_t* __restrict__ tail_rowptr,
@@ -232,7 +345,35 @@ int launch_spmm(const SparseDev& S, int64_t B, int64_t F, const float* in, float
   const int64_t max_blocks = (int64_t)num_sms() * 3 * 8;
   const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>(B * units_per_b, max_blocks));
   const int threads = 256;
-  if (vec4 && F <= 128 && S.M * (F / 4) < (int64_t)1 << 31) {
+  if (vec4 && F <= 128 && S.M * (F / 4) < (int64_t)1 << 31 && S.Wp <= 64) {
+    // unit: rows so that one slab is <= 32 KB; stages from the shared-memory budget
+    int U = 1024;
+    while (U > 16 && (int64_t)U * F * 4 > 32768) U >>= 1;
+    const int n_slabs = 1 + (prev ? 1 : 0) + (add ? 1 : 0);
+    const size_t stage_bytes = (size_t)n_slabs * U * F * 4 + (size_t)U * (S.Wp / 2) * 16;
+    int dev = 0, max_smem = 0;
+    DS_CUDA(cudaGetDevice(&dev));
+    DS_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    int nstage = (int)std::min<size_t>(4, (max_smem - 1024) / stage_bytes);
+    if (nstage >= 2) {
+      static bool attr_done = false;
+      if (!attr_done) {
+        DS_CUDA(cudaFuncSetAttribute(spmm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        attr_done = true;
+      }
+      const int64_t upb = (S.M + U - 1) / U;
+      const int64_t nblk = std::max<int64_t>(1, std::min<int64_t>(B * upb, num_sms()));
+      spmm_tile_kernel<<<(unsigned)nblk, 544, nstage * stage_bytes + nstage * sizeof(TileStage) + 64, st>>>(
+          S.ell_pk, S.Wp / 2, S.M, B, (int)(F / 4), reinterpret_cast<const float4*>(in), alpha,
+          reinterpret_cast<const float4*>(prev), prev ? beta : 0.f, reinterpret_cast<const float4*>(add),
+          add ? gamma : 0.f, reinterpret_cast<float4*>(out), lpr_log2, U, nstage);
+    } else {
+      spmm_ell_pk_kernel<<<(unsigned)blocks, threads, 0, st>>>(
+          S.ell_pk, S.Wp / 2, S.M, B, (int)(F / 4), reinterpret_cast<const float4*>(in), alpha,
+          reinterpret_cast<const float4*>(prev), prev ? beta : 0.f, reinterpret_cast<const float4*>(add),
+          add ? gamma : 0.f, reinterpret_cast<float4*>(out), lpr_log2, unit_rows);
+    }
+  } else if (vec4 && F <= 128 && S.M * (F / 4) < (int64_t)1 << 31) {
     spmm_ell_pk_kernel<<<(unsigned)blocks, threads, 0, st>>>(
         S.ell_pk, S.Wp / 2, S.M, B, (int)(F / 4), reinterpret_cast<const float4*>(in), alpha,
         reinterpret_cast<const float4*>(prev), prev ? beta : 0.f, reinterpret_cast<const float4*>(add),
