@@ -24,6 +24,10 @@ int launch_umma_gemm_tn(int64_t R, int64_t N, int64_t Kc, int nseg, const float*
                         float* C, int64_t ldc, int64_t c_kc_stride, int64_t c_seg_stride, float* partial, int mode,
                         cudaStream_t st);
 
+bool lattice_usable(const ds_plan* plan, int32_t K, int64_t B, int64_t F);
+int lattice_recursion(const ds_plan* plan, int64_t B, int F, int nsteps, const float* in0, const float* const* add,
+                      float* const* out, const float* alpha, const float* beta, const float* gamma, cudaStream_t st);
+
 namespace {
 
 int check_common(const ds_plan_t* plan, int32_t recursion, int32_t K, int64_t B, int64_t Fin, int64_t Fout,
@@ -40,9 +44,24 @@ int check_common(const ds_plan_t* plan, int32_t recursion, int32_t K, int64_t B,
 }
 
 // T_1..T_{K-1} into basis ([K-1, B, M, Fin]); T_0 = x
-int compute_basis(const SparseDev& S, int32_t recursion, int32_t K, int64_t B, int64_t Fin, const float* x,
+int compute_basis(const ds_plan* plan, int32_t recursion, int32_t K, int64_t B, int64_t Fin, const float* x,
                   float* basis, cudaStream_t st) {
+  const SparseDev& S = plan->fwd;
   const int64_t A = B * S.M * Fin;
+  if (lattice_usable(plan, K, B, Fin)) {
+    // all K-1 hops fused on chip (ds_lattice.cu); every hop's own-tile result goes to its basis slot
+    const float* add[16] = {};
+    float* out[16] = {};
+    float al[16], be[16], ga[16];
+    for (int s = 1; s < K; ++s) {
+      const bool cheb2 = recursion == DS_RECURSION_CHEBYSHEV && s >= 2;
+      al[s - 1] = cheb2 ? 2.f : 1.f;
+      be[s - 1] = cheb2 ? -1.f : 0.f;
+      ga[s - 1] = 0.f;
+      out[s - 1] = basis + (int64_t)(s - 1) * A;
+    }
+    return lattice_recursion(plan, B, (int)Fin, K - 1, x, add, out, al, be, ga, st);
+  }
   auto T = [&](int k) -> const float* { return k == 0 ? x : basis + (int64_t)(k - 1) * A; };
   for (int k = 1; k < K; ++k) {
     float* out = basis + (int64_t)(k - 1) * A;
@@ -73,7 +92,7 @@ int ds_graph_conv_forward(const ds_plan_t* plan, int32_t recursion, int32_t K, i
   DS_CHECK(K == 1 || basis != nullptr, "ds_graph_conv_forward: basis workspace required for K > 1");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t M = plan->M, R = B * M, A = R * Fin;
-  DS_TRY(compute_basis(plan->fwd, recursion, K, B, Fin, x, basis, st));
+  DS_TRY(compute_basis(plan, recursion, K, B, Fin, x, basis, st));
   if (mode == DS_MODE_FP32) {
     return launch_gemm_nn(R, Fout, Fin, K, x, basis, A, Fin, kernel, Fout, K, 1, bias, Fout, act, y, Fout, st);
   }
@@ -91,7 +110,7 @@ int64_t ds_graph_conv_backward_workspace_elems(int64_t M, int64_t B, int64_t Fin
   int64_t n = 0;
   if (act != DS_ACT_LINEAR) n += R * Fout;                  // dz
   if (!have_basis && K > 1) n += (int64_t)(K - 1) * A;      // recomputed basis
-  n += 4 * A;                                               // G_k + three Clenshaw buffers
+  n += (int64_t)std::max(4, K) * A;                         // G_k + three Clenshaw buffers, or all K G_k (fused path)
   n += std::max(gemm_tn_workspace_elems(R, Fin, K, Fout),   // dkernel split partials (fp32 / tensor-core kernel)
                 umma_tn_workspace_elems(R, Fout, Fin, K));
   n += colsum_workspace_elems(Fout);                        // dbias partials
@@ -122,11 +141,12 @@ int ds_graph_conv_backward(const ds_plan_t* plan, int32_t recursion, int32_t K, 
   const float* T = basis;
   if (T == nullptr && K > 1) {
     float* tb = take((int64_t)(K - 1) * A);
-    DS_TRY(compute_basis(plan->fwd, recursion, K, B, Fin, x, tb, st));
+    DS_TRY(compute_basis(plan, recursion, K, B, Fin, x, tb, st));
     T = tb;
   }
-  float* G = take(A);
-  float* buf[3] = {take(A), take(A), take(A)};
+  float* Gall = take((int64_t)std::max(4, K) * A);
+  float* G = Gall;
+  float* buf[3] = {Gall + A, Gall + 2 * A, Gall + 3 * A};
   float* tn_partial = take(std::max(gemm_tn_workspace_elems(R, Fin, K, Fout), umma_tn_workspace_elems(R, Fout, Fin, K)));
   float* cs_partial = take(colsum_workspace_elems(Fout));
 
@@ -152,6 +172,22 @@ int ds_graph_conv_backward(const ds_plan_t* plan, int32_t recursion, int32_t K, 
   const SparseDev& St = plan->bwd;
   if (K == 1) return make_G(0, dx);
   const bool cheb = recursion == DS_RECURSION_CHEBYSHEV;
+  if (lattice_usable(plan, K, B, Fin)) {
+    // fused Clenshaw / Horner: all G_k first, then one lattice launch: cur = G_{K-1}; step s handles k = K-1-s
+    for (int k = 0; k < K; ++k) DS_TRY(make_G(k, Gall + (int64_t)k * A));
+    const float* add[16] = {};
+    float* out[16] = {};
+    float al[16], be[16], ga[16];
+    for (int s = 1; s < K; ++s) {
+      const int k = K - 1 - s;
+      add[s - 1] = Gall + (int64_t)k * A;
+      al[s - 1] = (cheb && k > 0) ? 2.f : 1.f;
+      be[s - 1] = (cheb && s > 1) ? -1.f : 0.f;
+      ga[s - 1] = 1.f;
+    }
+    out[K - 2] = dx;
+    return lattice_recursion(plan, B, (int)Fin, K - 1, Gall + (int64_t)(K - 1) * A, add, out, al, be, ga, st);
+  }
   int cur = 0, old = -1, nxt = 1;
   DS_TRY(make_G(K - 1, buf[cur]));  // b_{K-1} = G_{K-1}
   for (int k = K - 2; k >= 1; --k) {

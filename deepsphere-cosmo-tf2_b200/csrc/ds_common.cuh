@@ -71,7 +71,10 @@ struct SparseDev {
 
 }  // namespace ds
 
+namespace ds { struct LatticeAttachment; }
+
 struct ds_plan {
+  ds::LatticeAttachment* lattice = nullptr;  // optional fused-recursion plan (ds_lattice_api.cu)
   int64_t M = 0;
   int64_t nnz = 0;
   int device = 0;

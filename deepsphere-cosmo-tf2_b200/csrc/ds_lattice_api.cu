@@ -1,0 +1,174 @@
+// C-ABI glue of the fused lattice recursion: attaching the tile plan to a ds_plan, and the forward basis /
+// backward Clenshaw drivers that combine the lattice kernel (regular tiles) with the generic kernels on a
+// compact sub-problem (the few irregular tiles around the valence-3 vertices of the HEALPix tessellation).
+#include <vector>
+
+#include "ds_lattice.cuh"
+
+namespace ds {
+
+struct LatticeAttachment {
+  LatticeDev dev;
+  int H = 0;
+  // irregular tiles: generic kernels on the closure (all rows within H hops of the irregular tiles' pixels)
+  ds_plan* sub_plan = nullptr;   // L~ restricted to the closure (owned)
+  int64_t n_closure = 0, n_own = 0;
+  int32_t* closure_rows = nullptr;  // [n_closure] global row of each closure row
+  int32_t* own_sub = nullptr;       // [n_own] closure rows whose results are exact (the irregular tiles' own pixels)
+  int64_t device_bytes = 0;
+};
+
+namespace {
+
+// dst[b, j, :] = src[b, rows[j], :]        (float4 granularity)
+__global__ void gather_rows_kernel(int64_t B, int64_t M, int64_t n, int FV, const int32_t* __restrict__ rows,
+                                   const float4* __restrict__ src, float4* __restrict__ dst) {
+  const int64_t total = B * n * FV;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % FV);
+    const int64_t j = (e / FV) % n, b = e / (FV * n);
+    dst[e] = __ldg(src + (b * M + rows[j]) * FV + c);
+  }
+}
+// dst[b, closure_rows[own[j]], :] = src[b, own[j], :]
+__global__ void scatter_rows_kernel(int64_t B, int64_t M, int64_t n_closure, int64_t n_own, int FV,
+                                    const int32_t* __restrict__ closure_rows, const int32_t* __restrict__ own,
+                                    const float4* __restrict__ src, float4* __restrict__ dst) {
+  const int64_t total = B * n_own * FV;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % FV);
+    const int64_t j = (e / FV) % n_own, b = e / (FV * n_own);
+    const int32_t s = own[j];
+    dst[(b * M + closure_rows[s]) * FV + c] = src[(b * n_closure + s) * FV + c];
+  }
+}
+
+inline unsigned grid_for(int64_t n) {
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 16));
+}
+
+}  // namespace
+
+void lattice_free(LatticeAttachment* L) {
+  if (!L) return;
+  cudaFree(L->dev.pix);
+  cudaFree(L->dev.w);
+  cudaFree(L->closure_rows);
+  cudaFree(L->own_sub);
+  if (L->sub_plan) ds_plan_destroy(L->sub_plan);
+  delete L;
+}
+
+// can the fused path serve this call?
+bool lattice_usable(const ds_plan* plan, int32_t K, int64_t B, int64_t F) {
+  if (!plan->lattice || !plan->symmetric) return false;
+  const LatticeAttachment* L = plan->lattice;
+  if (K - 1 != L->H || K < 2 || F % 4 != 0) return false;
+  LatticeArgs a;
+  int threads = 0, smem = 0;
+  return lattice_configure(L->dev, B, plan->M, (int)F, a, &threads, &smem) == 0;
+}
+
+// generic (unfused) recursion on the closure sub-problem, used for the irregular tiles
+// steps: out_s = alpha_s * S cur + beta_s * old + gamma_s * add_s on gathered tensors; results scattered
+static int sub_problem_recursion(const ds_plan* plan, int64_t B, int F, int nsteps, const float* in0,
+                                 const float* const* add, float* const* out, const float* alpha, const float* beta,
+                                 const float* gamma, cudaStream_t st) {
+  const LatticeAttachment* L = plan->lattice;
+  if (L->n_own == 0) return 0;
+  const int FV = F / 4;
+  const int64_t n = L->n_closure, A = B * n * F;
+  float* ws = nullptr;  // cur, old, new, add
+  DS_CUDA(cudaMallocAsync((void**)&ws, sizeof(float) * 4 * A, st));
+  float *cur = ws, *old = ws + A, *nxt = ws + 2 * A, *addb = ws + 3 * A;
+  auto gather = [&](const float* src, float* dst) {
+    gather_rows_kernel<<<grid_for(B * n * FV), 256, 0, st>>>(B, plan->M, n, FV, L->closure_rows,
+                                                            reinterpret_cast<const float4*>(src),
+                                                            reinterpret_cast<float4*>(dst));
+    g_launches.fetch_add(1);
+  };
+  gather(in0, cur);
+  int rc = 0;
+  for (int s = 1; s <= nsteps && rc == 0; ++s) {
+    const float* addp = nullptr;
+    if (add[s - 1] != nullptr) {
+      gather(add[s - 1], addb);
+      addp = addb;
+    }
+    rc = launch_spmm(L->sub_plan->fwd, B, F, cur, alpha[s - 1], beta[s - 1] != 0.f ? old : nullptr, beta[s - 1], addp,
+                     gamma[s - 1], nxt, st);
+    if (rc == 0 && out[s - 1] != nullptr) {
+      scatter_rows_kernel<<<grid_for(B * L->n_own * FV), 256, 0, st>>>(
+          B, plan->M, n, L->n_own, FV, L->closure_rows, L->own_sub, reinterpret_cast<const float4*>(nxt),
+          reinterpret_cast<float4*>(out[s - 1]));
+      g_launches.fetch_add(1);
+    }
+    float* t = old; old = cur; cur = nxt; nxt = t;
+  }
+  cudaFreeAsync(ws, st);
+  if (rc == 0) DS_CUDA(cudaGetLastError());
+  return rc;
+}
+
+// the whole recursion (lattice kernel + irregular sub-problem)
+int lattice_recursion(const ds_plan* plan, int64_t B, int F, int nsteps, const float* in0, const float* const* add,
+                      float* const* out, const float* alpha, const float* beta, const float* gamma, cudaStream_t st) {
+  const LatticeAttachment* L = plan->lattice;
+  DS_CHECK(L != nullptr && nsteps == L->H && nsteps <= LAT_MAX_STEPS, "lattice_recursion: plan mismatch");
+  LatticeArgs a;
+  int threads = 0, smem = 0;
+  DS_CHECK(lattice_configure(L->dev, B, plan->M, F, a, &threads, &smem) == 0, "lattice_recursion: cannot configure");
+  a.nsteps = nsteps;
+  a.in0 = in0;
+  for (int s = 0; s < LAT_MAX_STEPS; ++s) {
+    a.add[s] = s < nsteps ? add[s] : nullptr;
+    a.out[s] = s < nsteps ? out[s] : nullptr;
+    a.alpha[s] = s < nsteps ? alpha[s] : 0.f;
+    a.beta[s] = s < nsteps ? beta[s] : 0.f;
+    a.gamma[s] = s < nsteps ? gamma[s] : 0.f;
+  }
+  DS_TRY(launch_lattice(L->dev, a, threads, smem, st));
+  return sub_problem_recursion(plan, B, F, nsteps, in0, add, out, alpha, beta, gamma, st);
+}
+
+}  // namespace ds
+
+extern "C" int ds_plan_attach_lattice(ds_plan_t* plan, int32_t n_tiles, int32_t LW, int32_t H, int32_t T,
+                                      const int32_t* pix, const float* w, ds_plan_t* sub_plan, int64_t n_closure,
+                                      const int32_t* closure_rows, int64_t n_own, const int32_t* own_sub) {
+  using namespace ds;
+  DS_CHECK(plan != nullptr, "ds_plan_attach_lattice: NULL plan");
+  DS_CHECK(n_tiles >= 0 && LW == T + 2 * H && H >= 1 && H <= LAT_MAX_STEPS && T >= 4, "ds_plan_attach_lattice: bad geometry");
+  DS_CHECK(n_tiles == 0 || (pix && w), "ds_plan_attach_lattice: NULL tables");
+  DS_CHECK(n_own == 0 || (sub_plan && closure_rows && own_sub && sub_plan->M == n_closure),
+           "ds_plan_attach_lattice: inconsistent irregular sub-problem");
+  if (plan->lattice) {
+    lattice_free(plan->lattice);
+    plan->lattice = nullptr;
+  }
+  LatticeAttachment* L = new LatticeAttachment();
+  L->H = H;
+  L->dev.n_tiles = n_tiles; L->dev.LW = LW; L->dev.H = H; L->dev.T = T;
+  const size_t P = (size_t)LW * LW;
+  auto up = [&](const void* src, size_t bytes, void** dst) -> int {
+    *dst = nullptr;
+    DS_CUDA(cudaMalloc(dst, std::max<size_t>(bytes, 16)));
+    if (bytes) DS_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    L->device_bytes += (int64_t)bytes;
+    return 0;
+  };
+  int rc = up(pix, sizeof(int32_t) * n_tiles * P, (void**)&L->dev.pix);
+  if (rc == 0) rc = up(w, sizeof(float) * n_tiles * P * 9, (void**)&L->dev.w);
+  L->n_closure = n_closure;
+  L->n_own = n_own;
+  if (rc == 0) rc = up(closure_rows, sizeof(int32_t) * n_closure, (void**)&L->closure_rows);
+  if (rc == 0) rc = up(own_sub, sizeof(int32_t) * n_own, (void**)&L->own_sub);
+  if (rc != 0) {
+    lattice_free(L);
+    return rc;
+  }
+  L->sub_plan = n_own > 0 ? sub_plan : nullptr;  // ownership moves to the parent plan
+  plan->lattice = L;
+  plan->device_bytes += L->device_bytes;
+  return 0;
+}

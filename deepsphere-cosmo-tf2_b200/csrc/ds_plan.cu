@@ -10,6 +10,8 @@
 
 namespace ds {
 
+void lattice_free(LatticeAttachment* L);  // ds_lattice_api.cu
+
 std::string& last_error_ref() {
   thread_local std::string s;
   return s;
@@ -210,6 +212,7 @@ int ds_plan_create_coo(int64_t M, int64_t nnz, const int64_t* indices, const flo
 
 int ds_plan_destroy(ds_plan_t* plan) {
   if (!plan) return 0;
+  if (plan->lattice) ds::lattice_free(plan->lattice);
   if (!plan->symmetric) ds::free_sparse_dev(plan->bwd);
   ds::free_sparse_dev(plan->fwd);
   delete plan;
@@ -229,6 +232,7 @@ int ds_plan_info(const ds_plan_t* plan, int32_t what, int64_t* value_out) {
     case 6: *value_out = plan->bwd.n_tail_rows; break;
     case 7: *value_out = plan->device_bytes; break;
     case 8: *value_out = plan->symmetric ? 1 : 0; break;
+    case 9: *value_out = plan->lattice ? 1 : 0; break;
     default: return fail("ds_plan_info: unknown selector %d", what);
   }
   return 0;

@@ -33,6 +33,9 @@ SIGNATURES = {
     "ds_plan_create_coo": (ctypes.c_int, [_i64, _i64, _ptr, _ptr, _i32, ctypes.POINTER(_ptr)]),
     "ds_plan_destroy": (ctypes.c_int, [_ptr]),
     "ds_plan_info": (ctypes.c_int, [_ptr, _i32, ctypes.POINTER(_i64)]),
+    "ds_plan_attach_lattice": (
+        ctypes.c_int, [_ptr, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _ptr]
+    ),
     "ds_spmm": (ctypes.c_int, [_ptr, _i32, _i64, _i64, _ptr, _f32, _ptr, _f32, _ptr, _f32, _ptr, _ptr]),
     "ds_graph_conv_basis_elems": (_i64, [_i64, _i64, _i64, _i32]),
     "ds_graph_conv_forward": (
@@ -123,13 +126,17 @@ class GraphPlan:
     (gnn_layers.py:68-72): COO ``indices`` int64 [nnz, 2], ``values`` float32 [nnz],
     ``shape``.  One plan per device, created lazily on first use."""
 
-    def __init__(self, indices, values, shape, ell_width=0):
+    def __init__(self, indices, values, shape, ell_width=0, lattice_builder=None):
         self.indices = np.ascontiguousarray(indices, dtype=np.int64)
         self.values = np.ascontiguousarray(values, dtype=np.float32)
         self.shape = (int(shape[0]), int(shape[1]))
         if self.shape[0] != self.shape[1]:
             raise ValueError(f"the graph Laplacian must be square, got {self.shape}")
         self.ell_width = int(ell_width)
+        # optional callable -> dict(n_tiles, LW, H, T, pix, w, sub=(indices, values, n), closure_rows, own_sub)
+        # enabling the fused HEALPix lattice kernel (deepsphere/lattice.py); evaluated once, lazily
+        self.lattice_builder = lattice_builder
+        self._lattice_payload = None
         self._handles = {}
 
     @property
@@ -156,11 +163,40 @@ class GraphPlan:
                     "ds_plan_create_coo",
                 )
             h = self._handles[device_index] = out
+            self._attach_lattice(h, device_index)
         return h
+
+    def _attach_lattice(self, h, device_index):
+        if self.lattice_builder is None or os.environ.get("DEEPSPHERE_LATTICE", "1") == "0":
+            return
+        if self._lattice_payload is None:
+            self._lattice_payload = self.lattice_builder() or {}
+        p = self._lattice_payload
+        if not p:
+            return
+        import torch
+
+        def cptr(a):
+            return a.ctypes.data_as(ctypes.c_void_p)
+
+        with torch.cuda.device(device_index):
+            sub = ctypes.c_void_p()
+            n_own = len(p["own_sub"])
+            if n_own > 0:
+                si, sv, sn = p["sub"]
+                check(lib().ds_plan_create_coo(sn, len(sv), cptr(si), cptr(sv), 0, ctypes.byref(sub)),
+                      "ds_plan_create_coo (lattice sub-problem)")
+            check(
+                lib().ds_plan_attach_lattice(
+                    h, p["n_tiles"], p["LW"], p["H"], p["T"], cptr(p["pix"]), cptr(p["w"]), sub,
+                    len(p["closure_rows"]), cptr(p["closure_rows"]), n_own, cptr(p["own_sub"]),
+                ),
+                "ds_plan_attach_lattice",
+            )
 
     def info(self, device_index=0):
         names = ["M", "nnz", "ell_width", "tail_rows", "tail_nnz", "ell_width_T", "tail_rows_T", "device_bytes",
-                 "symmetric"]
+                 "symmetric", "lattice"]
         h = self.handle(device_index)
         out = {}
         for i, n in enumerate(names):

@@ -70,6 +70,9 @@ class _GraphConvBase(Model):
         # accepted for API compatibility; the kernel has no 2^31 size limit (utils.py:59)
         self.n_matmul_splits = n_matmul_splits
         self.mode = kwargs.pop("mode", None)
+        # optional HEALPix geometry (nside, NESTED pixel ids of the rows of L): enables the fused lattice
+        # kernel; HealpyGCNN provides it, and a full-sphere Laplacian is recognised automatically
+        self._healpix = kwargs.pop("healpix", None)
         self.kwargs = kwargs
 
         # gnn_layers.py:64-72: rescale the Laplacian and keep it as COO (indices, values, shape)
@@ -81,7 +84,38 @@ class _GraphConvBase(Model):
         self._L_indices = np.column_stack((L_coo.row, L_coo.col)).astype(np.int64)
         self._L_values = L_coo.data.astype(np.float32)  # floatx
         self._L_shape = np.asarray(L_coo.shape, dtype=np.int64)
-        self._plan = nat.GraphPlan(self._L_indices, self._L_values, self._L_shape)
+        self._plan = nat.GraphPlan(self._L_indices, self._L_values, self._L_shape, lattice_builder=self._lattice_payload)
+
+    def _attach_healpix(self, nside, indices):
+        """Tell the layer which HEALPix pixels its graph lives on (called by HealpyGCNN)."""
+        self._healpix = (int(nside), np.asarray(indices, dtype=np.int64))
+
+    def _lattice_payload(self):
+        """Tile plan of the fused K-hop kernel, or None when it does not apply (K = 1, no HEALPix
+        geometry, not an 8-neighbour graph, resolution below the 16 x 16 tile)."""
+        from . import healpix as hpx
+        from . import lattice
+
+        if self.K < 2:
+            return None
+        geo = self._healpix
+        M = int(self._L_shape[0])
+        if geo is None:
+            if M % 12 != 0:
+                return None
+            nside = int(round(np.sqrt(M // 12)))
+            if 12 * nside * nside != M or not hpx.isnsideok(nside, nest=True):
+                return None
+            geo = (nside, np.arange(M, dtype=np.int64))
+        nside, indices = geo
+        if len(indices) != M or nside < 16:
+            return None
+        Lt = sparse.csr_matrix((self._L_values, (self._L_indices[:, 0], self._L_indices[:, 1])), shape=(M, M))
+        try:
+            return lattice.make_payload(Lt, nside, indices, self.K - 1)
+        except Exception as exc:  # never let the optional fast path break the layer
+            logger.warning(f"lattice plan construction failed ({exc!r}); using the generic kernels")
+            return None
 
     def _default_initializer(self, Fin):
         raise NotImplementedError

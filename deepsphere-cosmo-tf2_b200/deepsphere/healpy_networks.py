@@ -112,6 +112,10 @@ class HealpyGCNN(Sequential):
                     actual_layer = layer._get_layer(current_L, n_matmul_splits)
                 else:
                     actual_layer = layer._get_layer(current_L)
+                # HEALPix geometry of this layer's graph (enables the fused lattice kernel)
+                for sub in (actual_layer, getattr(actual_layer, "layer1", None), getattr(actual_layer, "layer2", None)):
+                    if hasattr(sub, "_attach_healpix"):
+                        sub._attach_healpix(current_nside, current_indices)
                 self.layers_use.append(actual_layer)
             elif isinstance(layer, (hp_nn.HealpyPool, hp_nn.HealpyPseudoConv)):
                 new_nside = int(current_nside // 2**layer.p)

@@ -1,0 +1,244 @@
+"""Tile plan for the fused K-hop lattice kernel (host side, numpy).
+
+On the 8-neighbour HEALPix graph every NESTED block of 4^t pixels is a 2^t x 2^t square of a
+base face, and - away from the 8 valence-3 vertices of the base tessellation - its H-ring
+neighbourhood is a regular (2^t + 2H)^2 lattice even across face boundaries (the neighbouring
+face continues the grid, possibly with its x/y frame rotated by a multiple of 90 degrees).
+The fused kernel keeps that lattice in shared memory and applies L~ as a 3x3 stencil with
+per-pixel weights, so all K-1 recursion hops happen on chip.
+
+This module embeds each tile's neighbourhood into the lattice (walking the HEALPix neighbour
+function ring by ring while tracking the frame rotation), VERIFIES the embedding against the
+actual sparsity of L~ (a tile that does not verify - the 24 tiles that touch a valence-3
+vertex, or anything unexpected in a user-supplied L - is marked irregular and is processed by
+the generic kernels instead), and emits per tile:
+
+  pix [LW*LW] int32   row of L~ sitting at each lattice position (-1: hole / outside the mask)
+  w   [LW*LW, 9] f32  stencil weights in the tile frame: 8 directions (SW, W, NW, N, NE, E, SE, S)
+                      + centre, i.e. w[p, d] = L~[row(p), row(p + off_d)]
+
+There is no reference code for this (the reference multiplies by a tf.SparseTensor,
+utils.py:76); correctness is established by `check_plan` below and the parity tests.
+"""
+
+import numpy as np
+from scipy import sparse
+
+from . import healpix as hpx
+
+# tile-frame lattice offsets (di, dj) of the 8 directions, i along x, j along y
+DI = hpx.NB_XOFF
+DJ = hpx.NB_YOFF
+
+
+class LatticePlan:
+    def __init__(self, nside, H, tile_side, LW, tile_face, tile_x0, tile_y0, pix, w, regular, n_rows):
+        self.nside, self.H, self.tile_side, self.LW = nside, H, tile_side, LW
+        self.tile_face, self.tile_x0, self.tile_y0 = tile_face, tile_x0, tile_y0
+        self.pix, self.w, self.regular, self.n_rows = pix, w, regular, n_rows
+
+    @property
+    def n_tiles(self):
+        return self.pix.shape[0]
+
+    def own_mask(self):
+        """Boolean [LW*LW]: lattice positions of the tile's own pixels."""
+        H, LW, T = self.H, self.LW, self.tile_side
+        m = np.zeros((LW, LW), dtype=bool)
+        m[H : H + T, H : H + T] = True  # [j, i]
+        return m.ravel()
+
+    def irregular_rows(self):
+        """Rows of L~ owned by irregular tiles (to be handled by the generic path)."""
+        own = self.own_mask()
+        rows = self.pix[~self.regular][:, own].ravel()
+        return np.sort(rows[rows >= 0])
+
+
+def graph_is_healpix8(Lt, nside, indices):
+    """True if every off-diagonal non-zero of Lt connects HEALPix 8-neighbours (within `indices`)."""
+    npix = hpx.nside2npix(nside)
+    indices = np.asarray(indices, dtype=np.int64)
+    M = len(indices)
+    if Lt.shape != (M, M):
+        return False
+    lut = np.full(npix + 1, -1, dtype=np.int64)
+    lut[indices] = np.arange(M)
+    nb = hpx.neighbours(nside, indices)
+    nbrow = lut[nb]  # -1 (missing) indexes the sentinel slot -> -1
+    coo = sparse.coo_matrix(Lt)
+    off = coo.row != coo.col
+    r, c = coo.row[off], coo.col[off]
+    return bool(np.all((nbrow[r] == c[:, None]).any(axis=1)))
+
+
+def build_lattice_plan(Lt, nside, indices, H, tile_order=4):
+    """Lt: prepared L~ (scipy sparse, M x M, rows ordered like `indices`, NESTED pixel ids, sorted).
+    H: halo rings = K - 1.  Returns a LatticePlan, or None if the graph is not an 8-neighbour
+    HEALPix graph or the tile does not fit the resolution."""
+    nside = int(nside)
+    order = hpx.nside2order(nside)
+    if tile_order > order or H < 1:
+        return None
+    indices = np.asarray(indices, dtype=np.int64)
+    if np.any(np.diff(indices) <= 0):
+        return None
+    if not graph_is_healpix8(Lt, nside, indices):
+        return None
+    npix = hpx.nside2npix(nside)
+    M = len(indices)
+    T = 1 << tile_order
+    LW = T + 2 * H
+    lut = np.full(npix + 1, -1, dtype=np.int64)  # pixel -> row, sentinel slot for pixel -1
+    lut[indices] = np.arange(M)
+
+    # tiles: NESTED blocks of T*T pixels holding at least one selected pixel
+    tile_ids = np.unique(indices >> (2 * tile_order))
+    nt = len(tile_ids)
+    tx, ty, tf = hpx.nest2xyf(nside, tile_ids << (2 * tile_order))  # lower-left pixel of each block
+
+    pixel = np.full((nt, LW, LW), -2, dtype=np.int64)  # HEALPix pixel at [tile, j, i]; -1 hole, -2 unknown
+    rot = np.zeros((nt, LW, LW), dtype=np.int64)
+    jj, ii = np.meshgrid(np.arange(T), np.arange(T), indexing="ij")
+    own_pix = hpx.xyf2nest(nside, tx[:, None, None] + ii[None], ty[:, None, None] + jj[None], tf[:, None, None])
+    pixel[:, H : H + T, H : H + T] = own_pix
+
+    # neighbour table of every pixel of the sphere (chunked lookup keeps this vectorised)
+    def nbr_of(p):
+        return hpx.neighbours(nside, p)
+
+    # grow ring by ring: position P at ring r is reached from Q = P clamped one step towards the box
+    for r in range(1, H + 1):
+        lo, hi = H - r, H + T + r - 1
+        ring = [(j, i) for j in range(lo, hi + 1) for i in range(lo, hi + 1) if j in (lo, hi) or i in (lo, hi)]
+        Pj = np.array([p[0] for p in ring])
+        Pi = np.array([p[1] for p in ring])
+        Qj = np.clip(Pj, lo + 1, hi - 1)
+        Qi = np.clip(Pi, lo + 1, hi - 1)
+        d_tile = np.array([int(np.where((DI == pi - qi) & (DJ == pj - qj))[0][0])
+                           for pj, pi, qj, qi in zip(Pj, Pi, Qj, Qi)])
+        qpix = pixel[:, Qj, Qi]  # [nt, nring]
+        qrot = rot[:, Qj, Qi]
+        valid = qpix >= 0
+        qn = nbr_of(np.where(valid, qpix, 0))  # [nt, nring, 8]
+        d_face = (d_tile[None, :] + qrot) % 8
+        ppix = np.take_along_axis(qn, d_face[..., None], axis=2)[..., 0]
+        ppix = np.where(valid, ppix, -1)
+        # rotation of P's face frame relative to the tile frame
+        pv = ppix >= 0
+        pn = nbr_of(np.where(pv, ppix, 0))
+        back = np.argmax(pn == qpix[..., None], axis=2)
+        prot = (back - (d_tile[None, :] + 4)) % 8
+        pixel[:, Pj, Pi] = ppix
+        rot[:, Pj, Pi] = np.where(pv, prot, 0)
+
+    pixel = pixel.reshape(nt, LW * LW)
+    rot = rot.reshape(nt, LW * LW)
+    row = lut[pixel]  # -1 for holes and for pixels outside the selection
+
+    # L~ by face-frame direction: ldir[r, d] = L~[r, row(nb[pix_r][d])], ldir[r, 8] = L~[r, r]
+    csr = sparse.csr_matrix(Lt)
+    csr.sort_indices()
+    keys = np.repeat(np.arange(M, dtype=np.int64), np.diff(csr.indptr)) * M + csr.indices.astype(np.int64)
+    nbrow = lut[hpx.neighbours(nside, indices)]  # [M, 8]
+    cols = np.concatenate([nbrow, np.arange(M)[:, None]], axis=1)  # [M, 9]
+    q = np.arange(M, dtype=np.int64)[:, None] * M + np.where(cols >= 0, cols, 0)
+    loc = np.searchsorted(keys, q)
+    loc = np.minimum(loc, len(keys) - 1)
+    found = (keys[loc] == q) & (cols >= 0)
+    ldir = np.where(found, csr.data[loc], 0.0).astype(np.float32)  # [M, 9]
+
+    # stencil weights in the tile frame
+    has = row >= 0
+    rsafe = np.where(has, row, 0)
+    w = np.zeros((nt, LW * LW, 9), dtype=np.float32)
+    for d in range(8):
+        w[:, :, d] = np.where(has, ldir[rsafe, (d + rot) % 8], 0.0)
+    w[:, :, 8] = np.where(has, ldir[rsafe, 8], 0.0)
+
+    # verification: for every position that gets computed (ring <= H-1) the lattice neighbour in
+    # direction d must be the true graph neighbour in that direction (or both absent)
+    pos_j, pos_i = np.divmod(np.arange(LW * LW), LW)
+    inner = (pos_j >= 1) & (pos_j <= LW - 2) & (pos_i >= 1) & (pos_i <= LW - 2)
+    regular = np.ones(nt, dtype=bool)
+    nbr_true_all = hpx.neighbours(nside, np.where(pixel >= 0, pixel, 0))  # [nt, P, 8] face-frame order
+    for d in range(8):
+        tgt = (pos_j + DJ[d]) * LW + (pos_i + DI[d])
+        tgt = np.where(inner, tgt, 0)
+        lat_pix = pixel[:, tgt]  # pixel sitting at the lattice neighbour
+        true_pix = np.take_along_axis(nbr_true_all, ((d + rot) % 8)[..., None], axis=2)[..., 0]
+        # only selected pixels matter: compare rows (a neighbour outside the selection == absent)
+        ok = (lut[np.where(lat_pix >= 0, lat_pix, npix)] == lut[np.where(true_pix >= 0, true_pix, npix)])
+        ok = ok | ~has | ~inner[None, :]
+        regular &= ok.all(axis=1)
+    # every row must be owned by exactly one tile
+    plan = LatticePlan(nside, H, T, LW, tf, tx, ty, row.astype(np.int32), w, regular, M)
+    own_rows = plan.pix[:, plan.own_mask()]
+    owned = np.sort(own_rows[own_rows >= 0])
+    if len(owned) != M or np.any(owned != np.arange(M)):
+        return None
+    return plan
+
+
+def check_plan(plan, Lt, rng=None, n_tiles=None):
+    """Numerical self-check: one application of the stencil on random data equals Lt @ x on the
+    computed region of every (sampled) regular tile.  Returns the max abs error."""
+    rng = rng or np.random.default_rng(0)
+    M = plan.n_rows
+    x = rng.standard_normal(M)
+    y = sparse.csr_matrix(Lt, dtype=np.float64) @ x
+    LW = plan.LW
+    tiles = np.flatnonzero(plan.regular)
+    if n_tiles is not None and len(tiles) > n_tiles:
+        tiles = rng.choice(tiles, n_tiles, replace=False)
+    pos_j, pos_i = np.divmod(np.arange(LW * LW), LW)
+    inner = (pos_j >= 1) & (pos_j <= LW - 2) & (pos_i >= 1) & (pos_i <= LW - 2)
+    worst = 0.0
+    pix = plan.pix[tiles]
+    xv = np.where(pix >= 0, x[np.where(pix >= 0, pix, 0)], 0.0)  # [t, P]
+    acc = plan.w[tiles][:, :, 8].astype(np.float64) * xv
+    for d in range(8):
+        tgt = np.where(inner, (pos_j + DJ[d]) * LW + (pos_i + DI[d]), 0)
+        acc += plan.w[tiles][:, :, d].astype(np.float64) * xv[:, tgt]
+    sel = (pix >= 0) & inner[None, :]
+    ref = y[np.where(pix >= 0, pix, 0)]
+    worst = float(np.abs(np.where(sel, acc - ref, 0.0)).max()) if sel.any() else 0.0
+    return worst
+
+
+def make_payload(Lt, nside, indices, H, tile_order=4):
+    """Everything ds_plan_attach_lattice needs, as contiguous numpy arrays (or None if the fused path does
+    not apply): tables of the regular tiles + the compact generic sub-problem covering the irregular ones."""
+    plan = build_lattice_plan(Lt, nside, indices, H, tile_order)
+    if plan is None or not plan.regular.any():
+        return None
+    csr = sparse.csr_matrix(Lt)
+    if abs(csr - csr.T).max() != 0:  # the backward pass re-uses the same stencil for L~^T
+        return None
+    M = plan.n_rows
+    rows_irr = plan.irregular_rows()
+    if len(rows_irr):
+        mask = np.zeros(M, dtype=bool)
+        mask[rows_irr] = True
+        pattern = sparse.csr_matrix((np.ones(csr.nnz, dtype=np.float32), csr.indices, csr.indptr), shape=csr.shape)
+        for _ in range(H):
+            mask = mask | ((pattern @ mask.astype(np.float32)) > 0)
+        closure = np.flatnonzero(mask)
+        sub = sparse.coo_matrix(csr[closure][:, closure])
+        sub_idx = np.ascontiguousarray(np.column_stack((sub.row, sub.col)).astype(np.int64))
+        sub_val = np.ascontiguousarray(sub.data.astype(np.float32))
+        own_sub = np.searchsorted(closure, rows_irr).astype(np.int32)
+    else:
+        closure = np.zeros(0, dtype=np.int64)
+        sub_idx, sub_val = np.zeros((0, 2), np.int64), np.zeros(0, np.float32)
+        own_sub = np.zeros(0, dtype=np.int32)
+    reg = plan.regular
+    return {
+        "n_tiles": int(reg.sum()), "LW": int(plan.LW), "H": int(plan.H), "T": int(plan.tile_side),
+        "pix": np.ascontiguousarray(plan.pix[reg], dtype=np.int32),
+        "w": np.ascontiguousarray(plan.w[reg], dtype=np.float32),
+        "sub": (sub_idx, sub_val, int(len(closure))),
+        "closure_rows": np.ascontiguousarray(closure, dtype=np.int32),
+        "own_sub": np.ascontiguousarray(own_sub, dtype=np.int32),
+        "n_irregular_tiles": int((~reg).sum()),
+    }

@@ -77,8 +77,20 @@ int ds_plan_create_coo(int64_t M, int64_t nnz, const int64_t* indices /* [nnz,2]
                        const float* values /* [nnz] */, int32_t ell_width, ds_plan_t** plan_out);
 int ds_plan_destroy(ds_plan_t* plan);
 /* info: 0 M, 1 nnz, 2 ell_width, 3 tail_rows, 4 tail_nnz, 5 ell_width of L~^T,
- *       6 tail_rows of L~^T, 7 device bytes held by the plan, 8 is L~ symmetric (0/1) */
+ *       6 tail_rows of L~^T, 7 device bytes held by the plan, 8 is L~ symmetric (0/1),
+ *       9 has a lattice attachment (0/1) */
 int ds_plan_info(const ds_plan_t* plan, int32_t what, int64_t* value_out);
+
+/* Optional: attach the HEALPix tile plan that enables the fused K-hop recursion kernel (all K-1 hops of
+ * gnn_layers.py:135-143 in shared memory) for layers with K = H + 1 on a symmetric 8-neighbour graph.
+ * HOST arrays: pix [n_tiles, LW*LW] row of L~ at each lattice position (-1 = hole), w [n_tiles, LW*LW, 9]
+ * stencil weights (8 directions + centre), LW = T + 2H.  Rows owned by tiles that are not regular lattices
+ * (the vertex tiles) are served by the generic kernels on a compact sub-problem: `sub_plan` is L~ restricted
+ * to `closure_rows` (ownership passes to `plan`), `own_sub` lists the closure rows to scatter back.
+ * Without an attachment (or when it does not apply) the generic per-hop kernels run. */
+int ds_plan_attach_lattice(ds_plan_t* plan, int32_t n_tiles, int32_t LW, int32_t H, int32_t T, const int32_t* pix,
+                           const float* w, ds_plan_t* sub_plan, int64_t n_closure, const int32_t* closure_rows,
+                           int64_t n_own, const int32_t* own_sub);
 
 /* ---- utils.split_sparse_dense_matmul (utils.py:49-78) ---------------------------------
  * out[b,m,f] = alpha * sum_j L~[m,j] in[b,j,f] + beta * prev[b,m,f] + gamma * add[b,m,f]

@@ -1,0 +1,77 @@
+"""Fused lattice kernel (ds_lattice.cu) against the oracle and against the generic per-hop kernels."""
+import numpy as np
+import pytest
+import torch
+
+from deepsphere import _native as nat
+from deepsphere import gnn_layers, healpix as hpx, utils
+from deepsphere.graph import SphereHealpix
+from helpers import orc, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(layer, x, dy):
+    xt = torch.tensor(x, dtype=torch.float32, device="cuda", requires_grad=True)
+    y = layer(xt)
+    y.backward(torch.tensor(dy, dtype=torch.float32, device="cuda"))
+    return y.detach().cpu().numpy(), xt.grad.cpu().numpy(), layer.kernel.grad.cpu().numpy()
+
+
+@pytest.mark.parametrize("cls", ["Chebyshev", "Monomial"])
+@pytest.mark.parametrize("nside,B,Fin,Fout,K", [(32, 3, 4, 4, 5), (32, 2, 16, 8, 3), (64, 2, 64, 64, 5), (32, 5, 8, 4, 2),
+                                                (32, 2, 12, 4, 8)])
+def test_lattice_forward_backward_matches_oracle(cls, nside, B, Fin, Fout, K):
+    g = SphereHealpix(nside, k=8)
+    M = g.L.shape[0]
+    torch.manual_seed(0)
+    layer = getattr(gnn_layers, cls)(L=g.L, K=K, Fout=Fout)
+    rng = np.random.default_rng(K)
+    x = rng.standard_normal((B, M, Fin))
+    dy = rng.standard_normal((B, M, Fout))
+    y, dx, dk = _run(layer, x, dy)
+    assert layer._plan.info(0)["lattice"] == 1, "the fused lattice path was expected to be active"
+    rec = cls.lower()
+    Lt, _ = orc.prepare_laplacian(g.L, 0.75 if rec == "chebyshev" else 1.0)
+    w = layer.kernel.detach().double().cpu().numpy()
+    assert rel_err(y, orc.graph_conv_forward(x, Lt, w, K, rec, dtype=np.float64)) <= 1e-5
+    rdx, rdk, _ = orc.graph_conv_backward(x, Lt, w, K, dy, rec)
+    assert rel_err(dx, rdx) <= 1e-5 and rel_err(dk, rdk) <= 1e-5
+
+
+def test_lattice_equals_generic_path(monkeypatch):
+    """Same layer with the lattice attachment disabled: results agree to fp32 round-off."""
+    g = SphereHealpix(64, k=8)
+    M = g.L.shape[0]
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((2, M, 16))
+    dy = rng.standard_normal((2, M, 16))
+    torch.manual_seed(0)
+    fused = gnn_layers.Chebyshev(L=g.L, K=5)
+    a = _run(fused, x, dy)
+    monkeypatch.setenv("DEEPSPHERE_LATTICE", "0")
+    plain = gnn_layers.Chebyshev(L=g.L, K=5)
+    plain.build_from_shape(x.shape)
+    with torch.no_grad():
+        plain.kernel.copy_(fused.kernel)
+    b = _run(plain, x, dy)
+    assert plain._plan.info(0)["lattice"] == 0 and fused._plan.info(0)["lattice"] == 1
+    for u, v in zip(a, b):
+        assert rel_err(u, v) <= 2e-6
+
+
+def test_lattice_masked_sky():
+    ext = utils.extend_indices(hpx.query_disc(64, [1, 0, 0], 1.2), 64, 8)
+    g = SphereHealpix(64, indexes=ext, k=8)
+    M = len(ext)
+    layer = gnn_layers.Chebyshev(L=g.L, K=4, Fout=8, healpix=(64, ext))
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((3, M, 8))
+    dy = rng.standard_normal((3, M, 8))
+    y, dx, dk = _run(layer, x, dy)
+    assert layer._plan.info(0)["lattice"] == 1
+    Lt, _ = orc.prepare_laplacian(g.L, 0.75)
+    w = layer.kernel.detach().double().cpu().numpy()
+    assert rel_err(y, orc.graph_conv_forward(x, Lt, w, 4, "chebyshev", dtype=np.float64)) <= 1e-5
+    rdx, rdk, _ = orc.graph_conv_backward(x, Lt, w, 4, dy, "chebyshev")
+    assert rel_err(dx, rdx) <= 1e-5 and rel_err(dk, rdk) <= 1e-5
