@@ -20,11 +20,30 @@ namespace ds {
 
 namespace {
 
-constexpr int LAT_MAX_LD = 8;  // float4 prefetch registers per thread
+// ---- compile-time geometry of one (H, FC) instantiation ---------------------------------------------
+constexpr int LAT_T = 16;  // tile side
+__host__ __device__ constexpr int lat_lwp(int LW) {  // padded row stride: >= LW + 2 and == 3 (mod 4) so that consecutive strips
+  int v = LW + 2;                // (8 rows apart) start 24 banks apart
+  while (v % 4 != 3) ++v;
+  return v;
+}
+__host__ __device__ constexpr int lat_ps(int LW) {  // feature-plane stride: == 4 (mod 16); 8 spare rows so that the window of the
+  int v = (LW + 2 + LAT_S) * lat_lwp(LW);  // last (partial) strip stays inside the plane
+  while (v % 16 != 4) ++v;
+  return v;
+}
+__host__ __device__ constexpr int lat_tasks(int LW) { return LW * ((LW + LAT_S - 1) / LAT_S); }
+__host__ __device__ constexpr int lat_nfg(int LW, int FC) {
+  int n = 320 / lat_tasks(LW);
+  if (n > FC) n = FC;
+  while (n > 1 && FC % n != 0) --n;
+  return n < 1 ? 1 : n;
+}
+__host__ __device__ constexpr int lat_threads(int LW, int FC) { return ((lat_tasks(LW) * lat_nfg(LW, FC) + 31) / 32) * 32; }
+__host__ __device__ constexpr int lat_nld(int LW, int FC) {  // float4 prefetch registers per thread
+  return (LW * LW * (FC / 4) + lat_threads(LW, FC) - 1) / lat_threads(LW, FC);
+}
 
-// One "load event" = the lattice positions within ring limit `lo` (lo <= i, j <= LW-1-lo) of one
-// [B, M, F] tensor for one (batch element, channel chunk), fetched into registers and later scattered
-// into (or folded onto) a feature-major buffer.
 struct LoadEvent {
   const float* src;
   int64_t b;
@@ -32,63 +51,68 @@ struct LoadEvent {
   bool valid;
 };
 
-__global__ void __launch_bounds__(320, 1) lattice_recursion_kernel(const LatticeArgs a) {
+template <int H, int FC>
+__global__ void __launch_bounds__(lat_threads(LAT_T + 2 * H, FC), 1) lattice_recursion_kernel(const LatticeArgs a) {
+  constexpr int T = LAT_T, LW = T + 2 * H, P = LW * LW;
+  constexpr int LWP = lat_lwp(LW), PS = lat_ps(LW);
+  constexpr int TASKS = lat_tasks(LW), NFG = lat_nfg(LW, FC), FPT = FC / NFG;
+  constexpr int NT = lat_threads(LW, FC);
+  constexpr int VPP = FC / 4, N_LD = P * VPP, NLD = lat_nld(LW, FC);
   extern __shared__ __align__(16) float lat_smem[];
-  const int LW = a.LW, LWP = a.LWP, PS = a.PS, H = a.H, T = a.T, FC = a.FC;
-  const int P = LW * LW;
   float* bufA = lat_smem;
   float* bufB = bufA + (size_t)FC * PS;
   int32_t* s_pix = reinterpret_cast<int32_t*>(bufB + (size_t)FC * PS);  // [P]
 
-  const int tid = threadIdx.x, NT = blockDim.x;
-  const int task = tid % a.tasks;
-  const int fg = tid / a.tasks;
+  const int tid = threadIdx.x;
+  const int task = tid % TASKS;
+  const int fg = tid / TASKS;
   const int ci = task % LW;            // lattice column of this thread's strip
   const int j0 = (task / LW) * LAT_S;  // first lattice row of the strip
-  const bool computes = tid < a.tasks * a.nfg;
+  const bool computes = tid < TASKS * NFG;
   const int n_chunks = a.F / FC;
-  const int vpp = FC / 4;       // float4 per lattice position per chunk
-  const int n_ld = P * vpp;     // float4 per load event (<= LAT_MAX_LD * NT, checked on the host)
   const int64_t b_per = (a.B + a.b_split - 1) / a.b_split;
   const int n_units = a.n_tiles * a.b_split;
+  // position (j, i) of plane f lives at f * PS + (j + 1) * LWP + (i + 1): one pad row / column around
+  const int strip_off = (j0 + 1) * LWP + (ci + 1);
 
-  float4 pre[LAT_MAX_LD];
+  float4 pre[NLD];
   auto issue = [&](const LoadEvent& ev) {
     if (!ev.valid) return;
+    const float4* base = reinterpret_cast<const float4*>(ev.src + (ev.b * a.M * a.F + ev.c * FC));
+    const int FV = a.F / 4;
 #pragma unroll
-    for (int r = 0; r < LAT_MAX_LD; ++r) {
+    for (int r = 0; r < NLD; ++r) {
       const int u = tid + r * NT;
       pre[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (u < n_ld) {
-        const int p = u / vpp, q = u - p * vpp;
-        const int j = p / LW, i = p - j * LW;
+      if (u < N_LD) {
+        const int p = u / VPP, q = u % VPP;
+        const int j = p / LW, i = p % LW;
         const int row = s_pix[p];
         if (row >= 0 && i >= ev.lo && j >= ev.lo && i <= LW - 1 - ev.lo && j <= LW - 1 - ev.lo)
-          pre[r] = __ldg(reinterpret_cast<const float4*>(ev.src + ((ev.b * a.M + row) * a.F + ev.c * FC)) + q);
+          pre[r] = __ldg(base + (int64_t)row * FV + q);
       }
     }
   };
-  // position (j, i) of plane f lives at f * PS + (j + 1) * LWP + (i + 1): one pad row / column around
-  auto scatter = [&](float* dst) {  // dst = prefetched values (every lattice position)
+  auto scatter = [&](float* dst) {
 #pragma unroll
-    for (int r = 0; r < LAT_MAX_LD; ++r) {
+    for (int r = 0; r < NLD; ++r) {
       const int u = tid + r * NT;
-      if (u < n_ld) {
-        const int p = u / vpp, q = u - p * vpp;
-        const int j = p / LW, i = p - j * LW;
-        float* d = dst + (size_t)(4 * q) * PS + (j + 1) * LWP + (i + 1);
+      if (u < N_LD) {
+        const int p = u / VPP, q = u % VPP;
+        const int j = p / LW, i = p % LW;
+        float* d = dst + (4 * q) * PS + (j + 1) * LWP + (i + 1);
         d[0] = pre[r].x; d[PS] = pre[r].y; d[2 * PS] = pre[r].z; d[3 * PS] = pre[r].w;
       }
     }
   };
   auto fold = [&](float* dst, float be, float ga) {  // dst = be * dst + ga * prefetched
 #pragma unroll
-    for (int r = 0; r < LAT_MAX_LD; ++r) {
+    for (int r = 0; r < NLD; ++r) {
       const int u = tid + r * NT;
-      if (u < n_ld) {
-        const int p = u / vpp, q = u - p * vpp;
-        const int j = p / LW, i = p - j * LW;
-        float* d = dst + (size_t)(4 * q) * PS + (j + 1) * LWP + (i + 1);
+      if (u < N_LD) {
+        const int p = u / VPP, q = u % VPP;
+        const int j = p / LW, i = p % LW;
+        float* d = dst + (4 * q) * PS + (j + 1) * LWP + (i + 1);
         if (be == 0.f) {
           d[0] = ga * pre[r].x; d[PS] = ga * pre[r].y; d[2 * PS] = ga * pre[r].z; d[3 * PS] = ga * pre[r].w;
         } else {
@@ -119,10 +143,9 @@ __global__ void __launch_bounds__(320, 1) lattice_recursion_kernel(const Lattice
     __syncthreads();
 
     const int64_t n_items = (b_end - b_begin) * n_chunks;
-    // the event that follows (item it, step s_done): next add-input of the same item, else next item's input
     auto next_event = [&](int64_t it, int s_done) {
       LoadEvent ev;
-      for (int s = s_done + 1; s <= a.nsteps; ++s)
+      for (int s = s_done + 1; s <= H; ++s)
         if (a.add[s - 1] != nullptr) {
           ev.src = a.add[s - 1]; ev.b = b_begin + it / n_chunks; ev.c = (int)(it % n_chunks); ev.lo = s;
           ev.valid = true;
@@ -142,10 +165,11 @@ __global__ void __launch_bounds__(320, 1) lattice_recursion_kernel(const Lattice
       const int c = (int)(it % n_chunks);
       float* cur = bufA;
       float* oth = bufB;
-      scatter(cur);            // consumes the prefetched input of this item ...
+      scatter(cur);              // consumes the prefetched input of this item ...
       issue(next_event(it, 0));  // ... and immediately puts the next event in flight
       __syncthreads();
-      for (int s = 1; s <= a.nsteps; ++s) {
+#pragma unroll 1
+      for (int s = 1; s <= H; ++s) {
         const float al = a.alpha[s - 1];
         float be = a.beta[s - 1];
         if (a.add[s - 1] != nullptr) {
@@ -156,30 +180,30 @@ __global__ void __launch_bounds__(320, 1) lattice_recursion_kernel(const Lattice
           __syncthreads();
         }
         const int lo = s, hi = LW - 1 - s;  // region computed by this step
-        if (computes && ci >= lo && ci <= hi) {
-          for (int e = 0; e < a.fpt; ++e) {
-            const int f = fg * a.fpt + e;
-            const float* cp = cur + (size_t)f * PS + (j0 + 1) * LWP + (ci + 1);
-            float* op = oth + (size_t)f * PS + (j0 + 1) * LWP + (ci + 1);
+        if (computes && ci >= lo && ci <= hi && j0 <= hi && j0 + LAT_S - 1 >= lo) {
+          const bool use_old = be != 0.f;
+#pragma unroll
+          for (int e = 0; e < FPT; ++e) {
+            const float* cp = cur + (fg * FPT + e) * PS + strip_off;
+            float* op = oth + (fg * FPT + e) * PS + strip_off;
             float a0 = cp[-LWP - 1], a1 = cp[-LWP], a2 = cp[-LWP + 1];
             float b0 = cp[-1], b1 = cp[0], b2 = cp[1];
 #pragma unroll
             for (int jj = 0; jj < LAT_S; ++jj) {
-              const int j = j0 + jj;
               const float c0 = cp[(jj + 1) * LWP - 1], c1 = cp[(jj + 1) * LWP], c2 = cp[(jj + 1) * LWP + 1];
-              if (j >= lo && j <= hi) {
-                float acc = w[jj][8] * b1;
-                acc = fmaf(w[jj][0], b0, acc);  // SW (-1, 0)
-                acc = fmaf(w[jj][1], c0, acc);  // W  (-1,+1)
-                acc = fmaf(w[jj][2], c1, acc);  // NW ( 0,+1)
-                acc = fmaf(w[jj][3], c2, acc);  // N  (+1,+1)
-                acc = fmaf(w[jj][4], b2, acc);  // NE (+1, 0)
-                acc = fmaf(w[jj][5], a2, acc);  // E  (+1,-1)
-                acc = fmaf(w[jj][6], a1, acc);  // SE ( 0,-1)
-                acc = fmaf(w[jj][7], a0, acc);  // S  (-1,-1)
-                const float oldv = be != 0.f ? be * op[jj * LWP] : 0.f;
-                op[jj * LWP] = fmaf(al, acc, oldv);
-              }
+              float acc = w[jj][8] * b1;
+              acc = fmaf(w[jj][0], b0, acc);  // SW (-1, 0)
+              acc = fmaf(w[jj][1], c0, acc);  // W  (-1,+1)
+              acc = fmaf(w[jj][2], c1, acc);  // NW ( 0,+1)
+              acc = fmaf(w[jj][3], c2, acc);  // N  (+1,+1)
+              acc = fmaf(w[jj][4], b2, acc);  // NE (+1, 0)
+              acc = fmaf(w[jj][5], a2, acc);  // E  (+1,-1)
+              acc = fmaf(w[jj][6], a1, acc);  // SE ( 0,-1)
+              acc = fmaf(w[jj][7], a0, acc);  // S  (-1,-1)
+              float r = al * acc;
+              if (use_old) r = fmaf(be, op[jj * LWP], r);
+              const int j = j0 + jj;
+              if (j >= lo && j <= hi) op[jj * LWP] = r;
               a0 = b0; a1 = b1; a2 = b2;
               b0 = c0; b1 = c1; b2 = c2;
             }
@@ -189,15 +213,15 @@ __global__ void __launch_bounds__(320, 1) lattice_recursion_kernel(const Lattice
         // the step's result sits in `oth`: store the tile's own pixels if this step has an output
         float* outp = a.out[s - 1];
         if (outp != nullptr) {
-          const int n_st = T * T * vpp;
-          for (int u = tid; u < n_st; u += NT) {
-            const int po = u / vpp, q = u - po * vpp;
+          float4* ob = reinterpret_cast<float4*>(outp + (b * a.M * a.F + c * FC));
+          const int FV = a.F / 4;
+          for (int u = tid; u < T * T * VPP; u += NT) {
+            const int po = u / VPP, q = u % VPP;
             const int j = H + po / T, i = H + po % T;
             const int row = s_pix[j * LW + i];
             if (row >= 0) {
-              const float* d = oth + (size_t)(4 * q) * PS + (j + 1) * LWP + (i + 1);
-              __stcs(reinterpret_cast<float4*>(outp + ((b * a.M + row) * a.F + c * FC)) + q,
-                     make_float4(d[0], d[PS], d[2 * PS], d[3 * PS]));
+              const float* d = oth + (4 * q) * PS + (j + 1) * LWP + (i + 1);
+              __stcs(ob + (int64_t)row * FV + q, make_float4(d[0], d[PS], d[2 * PS], d[3 * PS]));
             }
           }
         }
@@ -208,62 +232,50 @@ __global__ void __launch_bounds__(320, 1) lattice_recursion_kernel(const Lattice
   }
 }
 
-}  // namespace
-
-int lattice_smem_bytes(int LW, int FC, int* LWP_out, int* PS_out) {
-  int LWP = LW + 2;
-  while (LWP % 4 != 3) ++LWP;  // 8 * LWP == 24 (mod 32): consecutive strips land on disjoint banks
-  int PS = (LW + 2) * LWP;
-  while (PS % 16 != 4) ++PS;   // feature-plane stride: 2 * PS == 8 (mod 32)
-  if (LWP_out) *LWP_out = LWP;
-  if (PS_out) *PS_out = PS;
-  return (int)(2 * (size_t)FC * PS * 4 + (size_t)LW * LW * 4 + 64);
-}
-
-// choose the chunk width / thread layout; returns -1 if the lattice does not fit
-int lattice_configure(const LatticeDev& L, int64_t B, int64_t M, int F, LatticeArgs& a, int* threads, int* smem) {
-  if (L.n_tiles <= 0 || F % 4 != 0) return -1;
-  int dev = 0, max_smem = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
-  if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return -1;
-  const int P = L.LW * L.LW;
-  const int strips = (L.LW + LAT_S - 1) / LAT_S;
-  const int tasks = L.LW * strips;
-  if (tasks > 320) return -1;
-  int FC = 16;
-  while (FC > 4 && (F % FC != 0 || lattice_smem_bytes(L.LW, FC, nullptr, nullptr) > max_smem)) FC >>= 1;
-  if (F % FC != 0 || lattice_smem_bytes(L.LW, FC, nullptr, nullptr) > max_smem) return -1;
-  int nfg = std::min(FC, 320 / tasks);
-  while (nfg > 1 && FC % nfg != 0) --nfg;
-  const int nt = ((tasks * nfg + 31) / 32) * 32;
-  if ((int64_t)P * (FC / 4) > (int64_t)8 * nt) return -1;  // prefetch registers (LAT_MAX_LD)
-  a.n_tiles = L.n_tiles; a.LW = L.LW; a.H = L.H; a.T = L.T;
-  a.pix = L.pix; a.w = L.w;
-  a.B = B; a.M = M; a.F = F; a.FC = FC;
-  *smem = lattice_smem_bytes(L.LW, FC, &a.LWP, &a.PS);
-  a.tasks = tasks; a.nfg = nfg; a.fpt = FC / nfg;
-  // enough work units to balance the SMs: split the batch when there are few tiles
-  int split = 1;
-  while ((int64_t)L.n_tiles * split < (int64_t)8 * num_sms() && split < B) split *= 2;
-  a.b_split = (int)std::min<int64_t>(split, B);
-  *threads = nt;
-  return 0;
-}
-
-int launch_lattice(const LatticeDev& L, LatticeArgs& a, int threads, int smem, cudaStream_t st) {
+template <int H, int FC>
+int launch_instance(const LatticeArgs& a, cudaStream_t st) {
+  constexpr int LW = LAT_T + 2 * H;
+  constexpr int smem = (2 * FC * lat_ps(LW) + LW * LW) * 4 + 64;
   static bool attr_done = false;
   if (!attr_done) {
-    int dev = 0, max_smem = 0;
-    DS_CUDA(cudaGetDevice(&dev));
-    DS_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    DS_CUDA(cudaFuncSetAttribute(lattice_recursion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    DS_CUDA(cudaFuncSetAttribute(lattice_recursion_kernel<H, FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
   const int n_units = a.n_tiles * a.b_split;
   const int grid = std::min(n_units, num_sms());
-  lattice_recursion_kernel<<<grid, threads, smem, st>>>(a);
+  lattice_recursion_kernel<H, FC><<<grid, lat_threads(LW, FC), smem, st>>>(a);
   DS_LAUNCHED();
   return 0;
+}
+
+}  // namespace
+
+// instantiated geometries: H = K - 1 in 1..6, channel chunk 16 (F % 16 == 0) or 4
+int lattice_configure(const LatticeDev& L, int64_t B, int64_t M, int F, LatticeArgs& a, int* threads, int* smem) {
+  if (L.n_tiles <= 0 || F % 4 != 0 || L.T != LAT_T || L.H < 1 || L.H > 6 || L.LW != LAT_T + 2 * L.H) return -1;
+  a.n_tiles = L.n_tiles; a.LW = L.LW; a.H = L.H; a.T = L.T;
+  a.pix = L.pix; a.w = L.w;
+  a.B = B; a.M = M; a.F = F; a.FC = F % 16 == 0 ? 16 : 4;
+  a.LWP = 0; a.PS = 0; a.tasks = 0; a.nfg = 0; a.fpt = 0;
+  int split = 1;  // enough work units to balance the SMs: split the batch when there are few tiles
+  while ((int64_t)L.n_tiles * split < (int64_t)8 * num_sms() && split < B) split *= 2;
+  a.b_split = (int)std::min<int64_t>(split, B);
+  *threads = 0;
+  *smem = 0;
+  return 0;
+}
+
+int launch_lattice(const LatticeDev& L, LatticeArgs& a, int threads, int smem, cudaStream_t st) {
+  (void)L; (void)threads; (void)smem;
+#define DS_LAT_CASE(HH)                                                        \
+  case HH:                                                                     \
+    return a.FC == 16 ? launch_instance<HH, 16>(a, st) : launch_instance<HH, 4>(a, st);
+  switch (a.H) {
+    DS_LAT_CASE(1) DS_LAT_CASE(2) DS_LAT_CASE(3) DS_LAT_CASE(4) DS_LAT_CASE(5) DS_LAT_CASE(6)
+    default: break;
+  }
+#undef DS_LAT_CASE
+  return fail("launch_lattice: no instantiation for H=%d", a.H);
 }
 
 }  // namespace ds
