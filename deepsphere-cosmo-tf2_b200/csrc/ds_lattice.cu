@@ -21,25 +21,16 @@ namespace ds {
 namespace {
 
 // ---- compile-time geometry of one (H, FC) instantiation ---------------------------------------------
+// Shared-memory layout: float4 planes [FC/4][(LW + 2 + LAT_S) rows][LW columns]; a float4 holds 4 consecutive
+// channels of one lattice position, so one 16-byte global load/store maps to one shared-memory access and the
+// stencil runs on 4 channels per instruction.  Lattice position (j, i) sits at row j + 1 (one spare row above,
+// LAT_S + 1 below for the last partial strip); there is no column padding: the i - 1 / i + 1 window of an edge
+// column wraps into the neighbouring row, which only ever feeds the outermost ring that is never computed.
+// With LW a multiple of 8 this is also the canonical no-swizzle K-major UMMA operand layout.
 constexpr int LAT_T = 16;  // tile side
-__host__ __device__ constexpr int lat_lwp(int LW) {  // padded row stride: >= LW + 2 and == 3 (mod 4) so that consecutive strips
-  int v = LW + 2;                // (8 rows apart) start 24 banks apart
-  while (v % 4 != 3) ++v;
-  return v;
-}
-__host__ __device__ constexpr int lat_ps(int LW) {  // feature-plane stride: == 4 (mod 16); 8 spare rows so that the window of the
-  int v = (LW + 2 + LAT_S) * lat_lwp(LW);  // last (partial) strip stays inside the plane
-  while (v % 16 != 4) ++v;
-  return v;
-}
+__host__ __device__ constexpr int lat_plane(int LW) { return (LW + 2 + LAT_S) * LW; }  // float4 per plane
 __host__ __device__ constexpr int lat_tasks(int LW) { return LW * ((LW + LAT_S - 1) / LAT_S); }
-__host__ __device__ constexpr int lat_nfg(int LW, int FC) {
-  int n = 320 / lat_tasks(LW);
-  if (n > FC) n = FC;
-  while (n > 1 && FC % n != 0) --n;
-  return n < 1 ? 1 : n;
-}
-__host__ __device__ constexpr int lat_threads(int LW, int FC) { return ((lat_tasks(LW) * lat_nfg(LW, FC) + 31) / 32) * 32; }
+__host__ __device__ constexpr int lat_threads(int LW, int FC) { return ((lat_tasks(LW) * (FC / 4) + 31) / 32) * 32; }
 __host__ __device__ constexpr int lat_nld(int LW, int FC) {  // float4 prefetch registers per thread
   return (LW * LW * (FC / 4) + lat_threads(LW, FC) - 1) / lat_threads(LW, FC);
 }
@@ -51,35 +42,41 @@ struct LoadEvent {
   bool valid;
 };
 
+__device__ __forceinline__ float4 f4_fma(float w, const float4& x, const float4& acc) {
+  return make_float4(fmaf(w, x.x, acc.x), fmaf(w, x.y, acc.y), fmaf(w, x.z, acc.z), fmaf(w, x.w, acc.w));
+}
+__device__ __forceinline__ float4 f4_scale(float w, const float4& x) {
+  return make_float4(w * x.x, w * x.y, w * x.z, w * x.w);
+}
+
 template <int H, int FC>
 __global__ void __launch_bounds__(lat_threads(LAT_T + 2 * H, FC), 1) lattice_recursion_kernel(const LatticeArgs a) {
   constexpr int T = LAT_T, LW = T + 2 * H, P = LW * LW;
-  constexpr int LWP = lat_lwp(LW), PS = lat_ps(LW);
-  constexpr int TASKS = lat_tasks(LW), NFG = lat_nfg(LW, FC), FPT = FC / NFG;
+  constexpr int PL = lat_plane(LW);
+  constexpr int TASKS = lat_tasks(LW), VPP = FC / 4;
   constexpr int NT = lat_threads(LW, FC);
-  constexpr int VPP = FC / 4, N_LD = P * VPP, NLD = lat_nld(LW, FC);
-  extern __shared__ __align__(16) float lat_smem[];
-  float* bufA = lat_smem;
-  float* bufB = bufA + (size_t)FC * PS;
-  int32_t* s_pix = reinterpret_cast<int32_t*>(bufB + (size_t)FC * PS);  // [P]
+  constexpr int N_LD = P * VPP, NLD = lat_nld(LW, FC);
+  extern __shared__ __align__(16) float4 lat_smem4[];
+  float4* bufA = lat_smem4;
+  float4* bufB = bufA + VPP * PL;
+  int32_t* s_pix = reinterpret_cast<int32_t*>(bufB + VPP * PL);  // [P]
 
   const int tid = threadIdx.x;
   const int task = tid % TASKS;
-  const int fg = tid / TASKS;
+  const int fq = tid / TASKS;          // which float4 channel group this thread computes
   const int ci = task % LW;            // lattice column of this thread's strip
   const int j0 = (task / LW) * LAT_S;  // first lattice row of the strip
-  const bool computes = tid < TASKS * NFG;
+  const bool computes = tid < TASKS * VPP;
   const int n_chunks = a.F / FC;
+  const int FV = a.F / 4;
   const int64_t b_per = (a.B + a.b_split - 1) / a.b_split;
   const int n_units = a.n_tiles * a.b_split;
-  // position (j, i) of plane f lives at f * PS + (j + 1) * LWP + (i + 1): one pad row / column around
-  const int strip_off = (j0 + 1) * LWP + (ci + 1);
+  const int strip_off = fq * PL + (j0 + 1) * LW + ci;
 
   float4 pre[NLD];
   auto issue = [&](const LoadEvent& ev) {
     if (!ev.valid) return;
     const float4* base = reinterpret_cast<const float4*>(ev.src + (ev.b * a.M * a.F + ev.c * FC));
-    const int FV = a.F / 4;
 #pragma unroll
     for (int r = 0; r < NLD; ++r) {
       const int u = tid + r * NT;
@@ -93,32 +90,26 @@ __global__ void __launch_bounds__(lat_threads(LAT_T + 2 * H, FC), 1) lattice_rec
       }
     }
   };
-  auto scatter = [&](float* dst) {
+  auto scatter = [&](float4* dst) {
 #pragma unroll
     for (int r = 0; r < NLD; ++r) {
       const int u = tid + r * NT;
       if (u < N_LD) {
         const int p = u / VPP, q = u % VPP;
-        const int j = p / LW, i = p % LW;
-        float* d = dst + (4 * q) * PS + (j + 1) * LWP + (i + 1);
-        d[0] = pre[r].x; d[PS] = pre[r].y; d[2 * PS] = pre[r].z; d[3 * PS] = pre[r].w;
+        dst[q * PL + LW + p] = pre[r];  // (j + 1) * LW + i == LW + p
       }
     }
   };
-  auto fold = [&](float* dst, float be, float ga) {  // dst = be * dst + ga * prefetched
+  auto fold = [&](float4* dst, float be, float ga) {  // dst = be * dst + ga * prefetched
 #pragma unroll
     for (int r = 0; r < NLD; ++r) {
       const int u = tid + r * NT;
       if (u < N_LD) {
         const int p = u / VPP, q = u % VPP;
-        const int j = p / LW, i = p % LW;
-        float* d = dst + (4 * q) * PS + (j + 1) * LWP + (i + 1);
-        if (be == 0.f) {
-          d[0] = ga * pre[r].x; d[PS] = ga * pre[r].y; d[2 * PS] = ga * pre[r].z; d[3 * PS] = ga * pre[r].w;
-        } else {
-          d[0] = fmaf(be, d[0], ga * pre[r].x); d[PS] = fmaf(be, d[PS], ga * pre[r].y);
-          d[2 * PS] = fmaf(be, d[2 * PS], ga * pre[r].z); d[3 * PS] = fmaf(be, d[3 * PS], ga * pre[r].w);
-        }
+        float4* d = dst + q * PL + LW + p;
+        float4 v = f4_scale(ga, pre[r]);
+        if (be != 0.f) v = f4_fma(be, *d, v);
+        *d = v;
       }
     }
   };
@@ -130,7 +121,7 @@ __global__ void __launch_bounds__(lat_threads(LAT_T + 2 * H, FC), 1) lattice_rec
     if (b_begin >= b_end) continue;
     __syncthreads();  // previous unit is done with s_pix and the buffers
     for (int p = tid; p < P; p += NT) s_pix[p] = a.pix[(size_t)tile * P + p];
-    for (int e = tid; e < 2 * FC * PS; e += NT) bufA[e] = 0.f;  // pads (and holes) stay zero for the whole tile
+    for (int e = tid; e < 2 * VPP * PL; e += NT) bufA[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     // stencil weights of this thread's strip, register-resident for every item of the tile
     float w[LAT_S][9];
 #pragma unroll
@@ -163,8 +154,8 @@ __global__ void __launch_bounds__(lat_threads(LAT_T + 2 * H, FC), 1) lattice_rec
     for (int64_t it = 0; it < n_items; ++it) {
       const int64_t b = b_begin + it / n_chunks;
       const int c = (int)(it % n_chunks);
-      float* cur = bufA;
-      float* oth = bufB;
+      float4* cur = bufA;
+      float4* oth = bufB;
       scatter(cur);              // consumes the prefetched input of this item ...
       issue(next_event(it, 0));  // ... and immediately puts the next event in flight
       __syncthreads();
@@ -182,31 +173,28 @@ __global__ void __launch_bounds__(lat_threads(LAT_T + 2 * H, FC), 1) lattice_rec
         const int lo = s, hi = LW - 1 - s;  // region computed by this step
         if (computes && ci >= lo && ci <= hi && j0 <= hi && j0 + LAT_S - 1 >= lo) {
           const bool use_old = be != 0.f;
+          const float4* cp = cur + strip_off;
+          float4* op = oth + strip_off;
+          float4 a0 = cp[-LW - 1], a1 = cp[-LW], a2 = cp[-LW + 1];
+          float4 b0 = cp[-1], b1 = cp[0], b2 = cp[1];
 #pragma unroll
-          for (int e = 0; e < FPT; ++e) {
-            const float* cp = cur + (fg * FPT + e) * PS + strip_off;
-            float* op = oth + (fg * FPT + e) * PS + strip_off;
-            float a0 = cp[-LWP - 1], a1 = cp[-LWP], a2 = cp[-LWP + 1];
-            float b0 = cp[-1], b1 = cp[0], b2 = cp[1];
-#pragma unroll
-            for (int jj = 0; jj < LAT_S; ++jj) {
-              const float c0 = cp[(jj + 1) * LWP - 1], c1 = cp[(jj + 1) * LWP], c2 = cp[(jj + 1) * LWP + 1];
-              float acc = w[jj][8] * b1;
-              acc = fmaf(w[jj][0], b0, acc);  // SW (-1, 0)
-              acc = fmaf(w[jj][1], c0, acc);  // W  (-1,+1)
-              acc = fmaf(w[jj][2], c1, acc);  // NW ( 0,+1)
-              acc = fmaf(w[jj][3], c2, acc);  // N  (+1,+1)
-              acc = fmaf(w[jj][4], b2, acc);  // NE (+1, 0)
-              acc = fmaf(w[jj][5], a2, acc);  // E  (+1,-1)
-              acc = fmaf(w[jj][6], a1, acc);  // SE ( 0,-1)
-              acc = fmaf(w[jj][7], a0, acc);  // S  (-1,-1)
-              float r = al * acc;
-              if (use_old) r = fmaf(be, op[jj * LWP], r);
-              const int j = j0 + jj;
-              if (j >= lo && j <= hi) op[jj * LWP] = r;
-              a0 = b0; a1 = b1; a2 = b2;
-              b0 = c0; b1 = c1; b2 = c2;
-            }
+          for (int jj = 0; jj < LAT_S; ++jj) {
+            const float4 c0 = cp[(jj + 1) * LW - 1], c1 = cp[(jj + 1) * LW], c2 = cp[(jj + 1) * LW + 1];
+            float4 acc = f4_scale(w[jj][8], b1);
+            acc = f4_fma(w[jj][0], b0, acc);  // SW (-1, 0)
+            acc = f4_fma(w[jj][1], c0, acc);  // W  (-1,+1)
+            acc = f4_fma(w[jj][2], c1, acc);  // NW ( 0,+1)
+            acc = f4_fma(w[jj][3], c2, acc);  // N  (+1,+1)
+            acc = f4_fma(w[jj][4], b2, acc);  // NE (+1, 0)
+            acc = f4_fma(w[jj][5], a2, acc);  // E  (+1,-1)
+            acc = f4_fma(w[jj][6], a1, acc);  // SE ( 0,-1)
+            acc = f4_fma(w[jj][7], a0, acc);  // S  (-1,-1)
+            float4 r = f4_scale(al, acc);
+            if (use_old) r = f4_fma(be, op[jj * LW], r);
+            const int j = j0 + jj;
+            if (j >= lo && j <= hi) op[jj * LW] = r;
+            a0 = b0; a1 = b1; a2 = b2;
+            b0 = c0; b1 = c1; b2 = c2;
           }
         }
         __syncthreads();
@@ -214,18 +202,14 @@ __global__ void __launch_bounds__(lat_threads(LAT_T + 2 * H, FC), 1) lattice_rec
         float* outp = a.out[s - 1];
         if (outp != nullptr) {
           float4* ob = reinterpret_cast<float4*>(outp + (b * a.M * a.F + c * FC));
-          const int FV = a.F / 4;
           for (int u = tid; u < T * T * VPP; u += NT) {
             const int po = u / VPP, q = u % VPP;
             const int j = H + po / T, i = H + po % T;
             const int row = s_pix[j * LW + i];
-            if (row >= 0) {
-              const float* d = oth + (4 * q) * PS + (j + 1) * LWP + (i + 1);
-              __stcs(ob + (int64_t)row * FV + q, make_float4(d[0], d[PS], d[2 * PS], d[3 * PS]));
-            }
+            if (row >= 0) __stcs(ob + (int64_t)row * FV + q, oth[q * PL + (j + 1) * LW + i]);
           }
         }
-        float* t = cur; cur = oth; oth = t;
+        float4* t = cur; cur = oth; oth = t;
       }
       __syncthreads();  // stores above read the buffers the next item overwrites
     }
@@ -235,14 +219,16 @@ __global__ void __launch_bounds__(lat_threads(LAT_T + 2 * H, FC), 1) lattice_rec
 template <int H, int FC>
 int launch_instance(const LatticeArgs& a, cudaStream_t st) {
   constexpr int LW = LAT_T + 2 * H;
-  constexpr int smem = (2 * FC * lat_ps(LW) + LW * LW) * 4 + 64;
-  static bool attr_done = false;
-  if (!attr_done) {
+  constexpr int smem = 2 * (FC / 4) * lat_plane(LW) * 16 + LW * LW * 4 + 64;
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
     DS_CUDA(cudaFuncSetAttribute(lattice_recursion_kernel<H, FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
+    int n = 1;
+    DS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lattice_recursion_kernel<H, FC>, lat_threads(LW, FC), smem));
+    ctas_per_sm = std::max(1, n);
   }
   const int n_units = a.n_tiles * a.b_split;
-  const int grid = std::min(n_units, num_sms());
+  const int grid = std::min(n_units, num_sms() * ctas_per_sm);
   lattice_recursion_kernel<H, FC><<<grid, lat_threads(LW, FC), smem, st>>>(a);
   DS_LAUNCHED();
   return 0;
