@@ -13,6 +13,7 @@
 // Tiles whose neighbourhood is not a regular lattice (the 24 tiles at the valence-3 vertices) are not
 // in the tile list; the caller runs the generic kernels on a compact sub-problem for them.
 #include <algorithm>
+#include <cstdlib>
 
 #include "ds_lattice.cuh"
 
@@ -28,11 +29,17 @@ namespace {
 // column wraps into the neighbouring row, which only ever feeds the outermost ring that is never computed.
 // With LW a multiple of 8 this is also the canonical no-swizzle K-major UMMA operand layout.
 constexpr int LAT_T = 16;  // tile side
-__host__ __device__ constexpr int lat_plane(int LW) { return (LW + 2 + LAT_S) * LW; }  // float4 per plane
-__host__ __device__ constexpr int lat_tasks(int LW) { return LW * ((LW + LAT_S - 1) / LAT_S); }
-__host__ __device__ constexpr int lat_threads(int LW, int FC) { return ((lat_tasks(LW) * (FC / 4) + 31) / 32) * 32; }
-__host__ __device__ constexpr int lat_nld(int LW, int FC) {  // float4 prefetch registers per thread
-  return (LW * LW * (FC / 4) + lat_threads(LW, FC) - 1) / lat_threads(LW, FC);
+__host__ __device__ constexpr int lat_plane(int LW) {  // float4 per plane; == 2 (mod 8) so that the 4 channel
+  int v = (LW + 2 + 8) * LW;  // groups of a position land on disjoint banks in the scatter / store phases
+  while (v % 8 != 2) ++v;
+  return v;
+}
+__host__ __device__ constexpr int lat_tasks(int LW, int S) { return LW * ((LW + S - 1) / S); }
+__host__ __device__ constexpr int lat_threads(int LW, int FC, int S) {
+  return ((lat_tasks(LW, S) * (FC / 4) + 31) / 32) * 32;
+}
+__host__ __device__ constexpr int lat_nld(int LW, int FC, int S) {  // float4 prefetch registers per thread
+  return (LW * LW * (FC / 4) + lat_threads(LW, FC, S) - 1) / lat_threads(LW, FC, S);
 }
 
 struct LoadEvent {
@@ -49,13 +56,13 @@ __device__ __forceinline__ float4 f4_scale(float w, const float4& x) {
   return make_float4(w * x.x, w * x.y, w * x.z, w * x.w);
 }
 
-template <int H, int FC>
-__global__ void __launch_bounds__(lat_threads(LAT_T + 2 * H, FC), 1) lattice_recursion_kernel(const LatticeArgs a) {
+template <int H, int FC, int S>
+__global__ void __launch_bounds__(lat_threads(LAT_T + 2 * H, FC, S), 1) lattice_recursion_kernel(const LatticeArgs a) {
   constexpr int T = LAT_T, LW = T + 2 * H, P = LW * LW;
   constexpr int PL = lat_plane(LW);
-  constexpr int TASKS = lat_tasks(LW), VPP = FC / 4;
-  constexpr int NT = lat_threads(LW, FC);
-  constexpr int N_LD = P * VPP, NLD = lat_nld(LW, FC);
+  constexpr int TASKS = lat_tasks(LW, S), VPP = FC / 4;
+  constexpr int NT = lat_threads(LW, FC, S);
+  constexpr int N_LD = P * VPP, NLD = lat_nld(LW, FC, S);
   extern __shared__ __align__(16) float4 lat_smem4[];
   float4* bufA = lat_smem4;
   float4* bufB = bufA + VPP * PL;
@@ -65,7 +72,7 @@ __global__ void __launch_bounds__(lat_threads(LAT_T + 2 * H, FC), 1) lattice_rec
   const int task = tid % TASKS;
   const int fq = tid / TASKS;          // which float4 channel group this thread computes
   const int ci = task % LW;            // lattice column of this thread's strip
-  const int j0 = (task / LW) * LAT_S;  // first lattice row of the strip
+  const int j0 = (task / LW) * S;      // first lattice row of the strip
   const bool computes = tid < TASKS * VPP;
   const int n_chunks = a.F / FC;
   const int FV = a.F / 4;
@@ -123,9 +130,9 @@ __global__ void __launch_bounds__(lat_threads(LAT_T + 2 * H, FC), 1) lattice_rec
     for (int p = tid; p < P; p += NT) s_pix[p] = a.pix[(size_t)tile * P + p];
     for (int e = tid; e < 2 * VPP * PL; e += NT) bufA[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     // stencil weights of this thread's strip, register-resident for every item of the tile
-    float w[LAT_S][9];
+    float w[S][9];
 #pragma unroll
-    for (int jj = 0; jj < LAT_S; ++jj) {
+    for (int jj = 0; jj < S; ++jj) {
       const int j = j0 + jj;
       const float* wp = a.w + ((size_t)tile * P + (size_t)min(j, LW - 1) * LW + ci) * 9;
 #pragma unroll
@@ -171,14 +178,14 @@ __global__ void __launch_bounds__(lat_threads(LAT_T + 2 * H, FC), 1) lattice_rec
           __syncthreads();
         }
         const int lo = s, hi = LW - 1 - s;  // region computed by this step
-        if (computes && ci >= lo && ci <= hi && j0 <= hi && j0 + LAT_S - 1 >= lo) {
+        if (computes && ci >= lo && ci <= hi && j0 <= hi && j0 + S - 1 >= lo) {
           const bool use_old = be != 0.f;
           const float4* cp = cur + strip_off;
           float4* op = oth + strip_off;
           float4 a0 = cp[-LW - 1], a1 = cp[-LW], a2 = cp[-LW + 1];
           float4 b0 = cp[-1], b1 = cp[0], b2 = cp[1];
 #pragma unroll
-          for (int jj = 0; jj < LAT_S; ++jj) {
+          for (int jj = 0; jj < S; ++jj) {
             const float4 c0 = cp[(jj + 1) * LW - 1], c1 = cp[(jj + 1) * LW], c2 = cp[(jj + 1) * LW + 1];
             float4 acc = f4_scale(w[jj][8], b1);
             acc = f4_fma(w[jj][0], b0, acc);  // SW (-1, 0)
@@ -216,20 +223,20 @@ __global__ void __launch_bounds__(lat_threads(LAT_T + 2 * H, FC), 1) lattice_rec
   }
 }
 
-template <int H, int FC>
+template <int H, int FC, int S>
 int launch_instance(const LatticeArgs& a, cudaStream_t st) {
   constexpr int LW = LAT_T + 2 * H;
   constexpr int smem = 2 * (FC / 4) * lat_plane(LW) * 16 + LW * LW * 4 + 64;
   static int ctas_per_sm = 0;
   if (ctas_per_sm == 0) {
-    DS_CUDA(cudaFuncSetAttribute(lattice_recursion_kernel<H, FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    DS_CUDA(cudaFuncSetAttribute(lattice_recursion_kernel<H, FC, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int n = 1;
-    DS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lattice_recursion_kernel<H, FC>, lat_threads(LW, FC), smem));
+    DS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lattice_recursion_kernel<H, FC, S>, lat_threads(LW, FC, S), smem));
     ctas_per_sm = std::max(1, n);
   }
   const int n_units = a.n_tiles * a.b_split;
   const int grid = std::min(n_units, num_sms() * ctas_per_sm);
-  lattice_recursion_kernel<H, FC><<<grid, lat_threads(LW, FC), smem, st>>>(a);
+  lattice_recursion_kernel<H, FC, S><<<grid, lat_threads(LW, FC, S), smem, st>>>(a);
   DS_LAUNCHED();
   return 0;
 }
@@ -253,9 +260,11 @@ int lattice_configure(const LatticeDev& L, int64_t B, int64_t M, int F, LatticeA
 
 int launch_lattice(const LatticeDev& L, LatticeArgs& a, int threads, int smem, cudaStream_t st) {
   (void)L; (void)threads; (void)smem;
+  static const bool strip4 = [] { const char* e = getenv("DEEPSPHERE_LATTICE_STRIP"); return !(e && atoi(e) == 8); }();
 #define DS_LAT_CASE(HH)                                                        \
   case HH:                                                                     \
-    return a.FC == 16 ? launch_instance<HH, 16>(a, st) : launch_instance<HH, 4>(a, st);
+    return a.FC == 16 ? (strip4 ? launch_instance<HH, 16, 4>(a, st) : launch_instance<HH, 16, 8>(a, st)) \
+                      : launch_instance<HH, 4, 8>(a, st);
   switch (a.H) {
     DS_LAT_CASE(1) DS_LAT_CASE(2) DS_LAT_CASE(3) DS_LAT_CASE(4) DS_LAT_CASE(5) DS_LAT_CASE(6)
     default: break;
