@@ -96,11 +96,13 @@ struct SmemLayout {
 
 __global__ void __launch_bounds__(NUM_THREADS_3X, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_arest,
-                 const UmmaParams p) {
+                 const __grid_constant__ CUtensorMap map_c, const UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // stage buffers first (1024-byte aligned for SWIZZLE_128B), control block after them
   uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  SmemLayout* ctl = reinterpret_cast<SmemLayout*>(stage_base + (size_t)p.stages * p.stage_bytes);
+  // epilogue staging: ceil(N/32) blocks of [128 rows x 128 B], SWIZZLE_128B (what the C tensor map expects)
+  uint8_t* c_stage = stage_base + (size_t)p.stages * p.stage_bytes;
+  SmemLayout* ctl = reinterpret_cast<SmemLayout*>(c_stage + (size_t)((p.N + 31) / 32) * A_TILE_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -127,6 +129,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   if (warp == 0) {
     ptx::tma_prefetch_desc(&map_a0);
     ptx::tma_prefetch_desc(&map_arest);
+    ptx::tma_prefetch_desc(&map_c);
   }
   if (warp == 1) ptx::tmem_alloc(&ctl->tmem_base, p.tmem_cols);
   ptx::tc_fence_before_sync();
@@ -195,48 +198,54 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     }
   } else if (warp < 6) {
     // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
+    // TMEM -> registers (lane = row) -> bias/activation -> swizzled shared-memory tile -> one TMA store per
+    // 32-column block: full 128-byte lines leave the SM instead of 16-byte pieces at a 256-byte stride
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int et = threadIdx.x - 2 * 32;  // 0..127 among the epilogue threads
+    const int r_in_tile = q * 32 + lane;
     uint32_t tile_it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
       const uint32_t acc = tile_it & 1;
       const uint32_t acc_ph = (tile_it >> 1) & 1;
       ptx::mbar_wait(&ctl->tmem_full[acc], acc_ph);
       ptx::tc_fence_after_sync();
-      const int64_t row = tile * BM + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.N;
-      float* crow = p.C + row * p.ldc;
-      for (int c0 = 0; c0 < p.N; c0 += 32) {
-        uint32_t r0[16], r1[16];
-        ptx::tmem_ld_32x32b_x16(taddr + c0, r0);
-        const bool two = c0 + 16 < p.N;
-        if (two) ptx::tmem_ld_32x32b_x16(taddr + c0 + 16, r1);
+      // the previous tile's TMA stores must have finished reading the staging buffer
+      if (et == 0) ptx::tma_store_wait_read();
+      ptx::named_bar_sync(1, 128);
+      for (int c0 = 0; c0 < p.N; c0 += 16) {
+        uint32_t r[16];
+        ptx::tmem_ld_32x32b_x16(taddr + c0, r);
         ptx::tmem_ld_wait();
-        if (c0 + 32 >= p.N) {
-          // accumulator fully read: hand it back to the issuer before doing the math / stores
+        if (c0 + 16 >= p.N) {
+          // accumulator fully read: hand it back to the issuer before the math / stores
           ptx::tc_fence_before_sync();
           ptx::mbar_arrive(&ctl->tmem_empty[acc]);
         }
-        if (row < p.R) {
+        uint8_t* blk = c_stage + (size_t)(c0 >> 5) * A_TILE_BYTES + (size_t)r_in_tile * 128;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (h == 1 && !two) break;
-            const uint32_t* r = h == 0 ? r0 : r1;
+        for (int v = 0; v < 4; ++v) {
+          float o[4];
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              float o[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int c = c0 + h * 16 + v * 4 + e;
-                float val = __uint_as_float(r[v * 4 + e]);
-                if (p.bias != nullptr) val += __ldg(p.bias + (c % p.bias_mod));
-                o[e] = act_apply(val, p.act);
-              }
-              *reinterpret_cast<float4*>(crow + c0 + h * 16 + v * 4) = make_float4(o[0], o[1], o[2], o[3]);
-            }
+          for (int e = 0; e < 4; ++e) {
+            const int c = c0 + v * 4 + e;
+            float val = __uint_as_float(r[v * 4 + e]);
+            if (p.bias != nullptr) val += __ldg(p.bias + (c % p.bias_mod));
+            o[e] = act_apply(val, p.act);
           }
+          const int chunk = (((c0 & 31) >> 2) + v) ^ (r_in_tile & 7);  // 16-byte chunk, 128B swizzle
+          *reinterpret_cast<float4*>(blk + chunk * 16) = make_float4(o[0], o[1], o[2], o[3]);
         }
       }
+      ptx::fence_proxy_async_smem();
+      ptx::named_bar_sync(1, 128);
+      if (et == 0) {
+        for (int cb = 0; cb < (p.N + 31) / 32; ++cb)
+          ptx::tma_store_2d(&map_c, c_stage + (size_t)cb * A_TILE_BYTES, cb * 32, (int32_t)(tile * BM));
+        ptx::tma_store_commit();
+      }
     }
+    if (et == 0) ptx::tma_store_wait_all();
   } else if (p.three_pass) {
     // ===================== 3xTF32 operand splitter (4 warps) =====================
     const int t = threadIdx.x - 6 * 32;  // 0..127
@@ -294,6 +303,7 @@ EncodeTiledFn encode_fn() {
 }
 
 // 2-D fp32 tensor [rows, cols] (row stride = ld elements), box = 128 rows x 32 columns, SWIZZLE_128B
+// (used for the A operand loads and for the C tile stores)
 int make_a_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld) {
   EncodeTiledFn fn = encode_fn();
   DS_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -354,7 +364,7 @@ int launch_umma_gemm(int64_t R, int64_t N, int64_t Kc, int nseg, const float* A0
   int dev = 0, max_smem = 0;
   DS_CUDA(cudaGetDevice(&dev));
   DS_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const int ctl_bytes = (int)sizeof(SmemLayout) + 1024 /* alignment slack */;
+  const int ctl_bytes = (int)sizeof(SmemLayout) + 1024 /* alignment slack */ + (int)((N + 31) / 32) * A_TILE_BYTES;
   int stages = (max_smem - ctl_bytes) / (int)p.stage_bytes;
   stages = std::min(stages, std::min(MAX_STAGES, three ? 4 : 6));
   DS_CHECK(stages >= 2, "umma gemm: tile does not fit shared memory (stage %u bytes)", p.stage_bytes);
@@ -374,8 +384,9 @@ int launch_umma_gemm(int64_t R, int64_t N, int64_t Kc, int nseg, const float* A0
   }
   p.b_img = img;
 
-  CUtensorMap map0, map1;
-  int rc = make_a_map(&map0, A0, R, Kc, Kc);
+  CUtensorMap map0, map1, mapc;
+  int rc = make_a_map(&mapc, C, R, N, ldc);
+  if (rc == 0) rc = make_a_map(&map0, A0, R, Kc, Kc);
   if (rc == 0) rc = nseg > 1 ? make_a_map(&map1, Arest, (int64_t)(nseg - 1) * R, Kc, Kc) : make_a_map(&map1, A0, R, Kc, Kc);
   if (rc != 0) {
     cudaFreeAsync(img, st);
@@ -389,7 +400,7 @@ int launch_umma_gemm(int64_t R, int64_t N, int64_t Kc, int nseg, const float* A0
   DS_CHECK(attr_err == cudaSuccess, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(attr_err));
   const int64_t n_tiles = (R + BM - 1) / BM;
   const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, num_sms());
-  umma_gemm_kernel<<<grid, three ? NUM_THREADS_3X : NUM_THREADS_TF32, smem_bytes, st>>>(map0, map1, p);
+  umma_gemm_kernel<<<grid, three ? NUM_THREADS_3X : NUM_THREADS_TF32, smem_bytes, st>>>(map0, map1, mapc, p);
   g_launches.fetch_add(1);
   cudaError_t le = cudaGetLastError();
   cudaFreeAsync(img, st);
