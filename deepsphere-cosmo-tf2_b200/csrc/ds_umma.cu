@@ -94,15 +94,73 @@ struct SmemLayout {
   uint32_t tmem_base;
 };
 
+// TMEM -> registers (lane = row) -> bias/activation -> swizzled shared-memory tile -> one TMA store per
+// 32-column block: full 128-byte lines leave the SM instead of 16-byte pieces at a 256-byte stride.
+// The staging buffer holds 64 columns; wider outputs are flushed in 64-column groups.
+template <int ACT>
+__device__ __noinline__ void epilogue_loop(const UmmaParams& p, SmemLayout* ctl, uint8_t* c_stage,
+                                           const CUtensorMap* map_c, uint32_t tmem_base, int64_t n_tiles) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3;               // TMEM lane quarter this warp may access
+  const int et = threadIdx.x - 2 * 32;  // 0..127 among the epilogue threads
+  const int r_in_tile = q * 32 + lane;
+  const bool has_bias = p.bias != nullptr;
+  uint32_t tile_it = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+    const uint32_t acc = tile_it & 1;
+    const uint32_t acc_ph = (tile_it >> 1) & 1;
+    ptx::mbar_wait(&ctl->tmem_full[acc], acc_ph);
+    ptx::tc_fence_after_sync();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.N;
+    for (int g0 = 0; g0 < p.N; g0 += 64) {
+      // the previous TMA stores must have finished reading the staging buffer
+      if (et == 0) ptx::tma_store_wait_read();
+      ptx::named_bar_sync(1, 128);
+      const int g1 = min(p.N, g0 + 64);
+      for (int c0 = g0; c0 < g1; c0 += 16) {
+        uint32_t r[16];
+        ptx::tmem_ld_32x32b_x16(taddr + c0, r);
+        ptx::tmem_ld_wait();
+        if (c0 + 16 >= p.N) {
+          // accumulator fully read: hand it back to the issuer before the math / stores
+          ptx::tc_fence_before_sync();
+          ptx::mbar_arrive(&ctl->tmem_empty[acc]);
+        }
+        uint8_t* blk = c_stage + (size_t)((c0 - g0) >> 5) * A_TILE_BYTES + (size_t)r_in_tile * 128;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float val = __uint_as_float(r[v * 4 + e]);
+            if (has_bias) val += __ldg(p.bias + ((c0 + v * 4 + e) % p.bias_mod));
+            o[e] = act_apply(val, ACT);
+          }
+          const int chunk = (((c0 & 31) >> 2) + v) ^ (r_in_tile & 7);  // 16-byte chunk, 128B swizzle
+          *reinterpret_cast<float4*>(blk + chunk * 16) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::named_bar_sync(1, 128);
+      if (et == 0) {
+        for (int cb = 0; cb < (g1 - g0 + 31) / 32; ++cb)
+          ptx::tma_store_2d(map_c, c_stage + (size_t)cb * A_TILE_BYTES, g0 + cb * 32, (int32_t)(tile * BM));
+        ptx::tma_store_commit();
+      }
+    }
+  }
+  if (et == 0) ptx::tma_store_wait_all();
+}
+
 __global__ void __launch_bounds__(NUM_THREADS_3X, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_arest,
                  const __grid_constant__ CUtensorMap map_c, const UmmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // stage buffers first (1024-byte aligned for SWIZZLE_128B), control block after them
   uint8_t* stage_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // epilogue staging: ceil(N/32) blocks of [128 rows x 128 B], SWIZZLE_128B (what the C tensor map expects)
+  // epilogue staging: up to 2 blocks of [128 rows x 128 B], SWIZZLE_128B (what the C tensor map expects)
   uint8_t* c_stage = stage_base + (size_t)p.stages * p.stage_bytes;
-  SmemLayout* ctl = reinterpret_cast<SmemLayout*>(c_stage + (size_t)((p.N + 31) / 32) * A_TILE_BYTES);
+  SmemLayout* ctl = reinterpret_cast<SmemLayout*>(c_stage + (size_t)min((p.N + 31) / 32, 2) * A_TILE_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -198,54 +256,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     }
   } else if (warp < 6) {
     // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
-    // TMEM -> registers (lane = row) -> bias/activation -> swizzled shared-memory tile -> one TMA store per
-    // 32-column block: full 128-byte lines leave the SM instead of 16-byte pieces at a 256-byte stride
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int et = threadIdx.x - 2 * 32;  // 0..127 among the epilogue threads
-    const int r_in_tile = q * 32 + lane;
-    uint32_t tile_it = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
-      const uint32_t acc = tile_it & 1;
-      const uint32_t acc_ph = (tile_it >> 1) & 1;
-      ptx::mbar_wait(&ctl->tmem_full[acc], acc_ph);
-      ptx::tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.N;
-      // the previous tile's TMA stores must have finished reading the staging buffer
-      if (et == 0) ptx::tma_store_wait_read();
-      ptx::named_bar_sync(1, 128);
-      for (int c0 = 0; c0 < p.N; c0 += 16) {
-        uint32_t r[16];
-        ptx::tmem_ld_32x32b_x16(taddr + c0, r);
-        ptx::tmem_ld_wait();
-        if (c0 + 16 >= p.N) {
-          // accumulator fully read: hand it back to the issuer before the math / stores
-          ptx::tc_fence_before_sync();
-          ptx::mbar_arrive(&ctl->tmem_empty[acc]);
-        }
-        uint8_t* blk = c_stage + (size_t)(c0 >> 5) * A_TILE_BYTES + (size_t)r_in_tile * 128;
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          float o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = c0 + v * 4 + e;
-            float val = __uint_as_float(r[v * 4 + e]);
-            if (p.bias != nullptr) val += __ldg(p.bias + (c % p.bias_mod));
-            o[e] = act_apply(val, p.act);
-          }
-          const int chunk = (((c0 & 31) >> 2) + v) ^ (r_in_tile & 7);  // 16-byte chunk, 128B swizzle
-          *reinterpret_cast<float4*>(blk + chunk * 16) = make_float4(o[0], o[1], o[2], o[3]);
-        }
-      }
-      ptx::fence_proxy_async_smem();
-      ptx::named_bar_sync(1, 128);
-      if (et == 0) {
-        for (int cb = 0; cb < (p.N + 31) / 32; ++cb)
-          ptx::tma_store_2d(&map_c, c_stage + (size_t)cb * A_TILE_BYTES, cb * 32, (int32_t)(tile * BM));
-        ptx::tma_store_commit();
-      }
+    // instantiated per activation: one inlined 6-way switch per output value made the epilogue ~43 KB of
+    // SASS and instruction-fetch bound (ncu r1e: stall_no_instruction 5.0 per issue)
+    switch (p.act) {
+      case DS_ACT_RELU: epilogue_loop<DS_ACT_RELU>(p, ctl, c_stage, &map_c, tmem_base, n_tiles); break;
+      case DS_ACT_ELU: epilogue_loop<DS_ACT_ELU>(p, ctl, c_stage, &map_c, tmem_base, n_tiles); break;
+      case DS_ACT_SIGMOID: epilogue_loop<DS_ACT_SIGMOID>(p, ctl, c_stage, &map_c, tmem_base, n_tiles); break;
+      case DS_ACT_TANH: epilogue_loop<DS_ACT_TANH>(p, ctl, c_stage, &map_c, tmem_base, n_tiles); break;
+      case DS_ACT_SOFTPLUS: epilogue_loop<DS_ACT_SOFTPLUS>(p, ctl, c_stage, &map_c, tmem_base, n_tiles); break;
+      default: epilogue_loop<DS_ACT_LINEAR>(p, ctl, c_stage, &map_c, tmem_base, n_tiles); break;
     }
-    if (et == 0) ptx::tma_store_wait_all();
   } else if (p.three_pass) {
     // ===================== 3xTF32 operand splitter (4 warps) =====================
     const int t = threadIdx.x - 6 * 32;  // 0..127
@@ -364,7 +384,7 @@ int launch_umma_gemm(int64_t R, int64_t N, int64_t Kc, int nseg, const float* A0
   int dev = 0, max_smem = 0;
   DS_CUDA(cudaGetDevice(&dev));
   DS_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const int ctl_bytes = (int)sizeof(SmemLayout) + 1024 /* alignment slack */ + (int)((N + 31) / 32) * A_TILE_BYTES;
+  const int ctl_bytes = (int)sizeof(SmemLayout) + 1024 /* alignment slack */ + (int)std::min<int64_t>((N + 31) / 32, 2) * A_TILE_BYTES;
   int stages = (max_smem - ctl_bytes) / (int)p.stage_bytes;
   stages = std::min(stages, std::min(MAX_STAGES, three ? 4 : 6));
   DS_CHECK(stages >= 2, "umma gemm: tile does not fit shared memory (stage %u bytes)", p.stage_bytes);
