@@ -45,8 +45,8 @@ int check_common(const ds_plan_t* plan, int32_t recursion, int32_t K, int64_t B,
 
 // T_1..T_{K-1} into basis ([K-1, B, M, Fin]); T_0 = x
 int compute_basis(const ds_plan* plan, int32_t recursion, int32_t K, int64_t B, int64_t Fin, const float* x,
-                  float* basis, cudaStream_t st) {
-  const SparseDev& S = plan->fwd;
+                  float* basis, cudaStream_t st, bool transpose = false) {
+  const SparseDev& S = transpose ? plan->bwd : plan->fwd;  // the lattice path requires L~ symmetric
   const int64_t A = B * S.M * Fin;
   if (lattice_usable(plan, K, B, Fin)) {
     // all K-1 hops fused on chip (ds_lattice.cu); every hop's own-tile result goes to its basis slot
@@ -110,7 +110,7 @@ int64_t ds_graph_conv_backward_workspace_elems(int64_t M, int64_t B, int64_t Fin
   int64_t n = 0;
   if (act != DS_ACT_LINEAR) n += R * Fout;                  // dz
   if (!have_basis && K > 1) n += (int64_t)(K - 1) * A;      // recomputed basis
-  n += (int64_t)std::max(4, K) * A;                         // G_k + three Clenshaw buffers, or all K G_k (fused path)
+  if (K > 1) n += (int64_t)(K - 1) * R * Fout;              // T_1..T_{K-1} of L~^T applied to dz
   n += std::max(gemm_tn_workspace_elems(R, Fin, K, Fout),   // dkernel split partials (fp32 / tensor-core kernel)
                 umma_tn_workspace_elems(R, Fout, Fin, K));
   n += colsum_workspace_elems(Fout);                        // dbias partials
@@ -144,9 +144,7 @@ int ds_graph_conv_backward(const ds_plan_t* plan, int32_t recursion, int32_t K, 
     DS_TRY(compute_basis(plan, recursion, K, B, Fin, x, tb, st));
     T = tb;
   }
-  float* Gall = take((int64_t)std::max(4, K) * A);
-  float* G = Gall;
-  float* buf[3] = {Gall + A, Gall + 2 * A, Gall + 3 * A};
+  float* U = K > 1 ? take((int64_t)(K - 1) * R * Fout) : nullptr;
   float* tn_partial = take(std::max(gemm_tn_workspace_elems(R, Fin, K, Fout), umma_tn_workspace_elems(R, Fout, Fin, K)));
   float* cs_partial = take(colsum_workspace_elems(Fout));
 
@@ -160,49 +158,15 @@ int ds_graph_conv_backward(const ds_plan_t* plan, int32_t recursion, int32_t K, 
   }
   if (dx == nullptr) return 0;
 
-  // 5. dx = sum_k T_k(L~^T) G_k,  G_k[b,m,f] = sum_o dz[b,m,o] kernel[f*K + k, o]   (Clenshaw / Horner)
-  const bool tc_G = mode != DS_MODE_FP32 && umma_supported(Fout, 1, Fin) == 0;
-  auto make_G = [&](int k, float* out) {
-    if (tc_G)  // G_k = dz * W_k^T on the tensor cores: B(kc = o, n = f) = kernel[(f*K + k)*Fout + o]
-      return launch_umma_gemm(R, Fin, Fout, 1, dz, dz, R, kernel + (int64_t)k * Fout, 1, 0, (int64_t)K * Fout, nullptr,
-                              1, DS_ACT_LINEAR, out, Fin, mode, st);
-    return launch_gemm_nt(R, Fin, Fout, 1, dz, Fout, kernel + (int64_t)k * Fout, Fout, K, 0, nullptr, 1,
-                          DS_ACT_LINEAR, out, Fin, 0, st);
-  };
-  const SparseDev& St = plan->bwd;
-  if (K == 1) return make_G(0, dx);
-  const bool cheb = recursion == DS_RECURSION_CHEBYSHEV;
-  if (lattice_usable(plan, K, B, Fin)) {
-    // fused Clenshaw / Horner: all G_k first, then one lattice launch: cur = G_{K-1}; step s handles k = K-1-s
-    for (int k = 0; k < K; ++k) DS_TRY(make_G(k, Gall + (int64_t)k * A));
-    const float* add[16] = {};
-    float* out[16] = {};
-    float al[16], be[16], ga[16];
-    for (int s = 1; s < K; ++s) {
-      const int k = K - 1 - s;
-      add[s - 1] = Gall + (int64_t)k * A;
-      al[s - 1] = (cheb && k > 0) ? 2.f : 1.f;
-      be[s - 1] = (cheb && s > 1) ? -1.f : 0.f;
-      ga[s - 1] = 1.f;
-    }
-    out[K - 2] = dx;
-    return lattice_recursion(plan, B, (int)Fin, K - 1, Gall + (int64_t)(K - 1) * A, add, out, al, be, ga, st);
-  }
-  int cur = 0, old = -1, nxt = 1;
-  DS_TRY(make_G(K - 1, buf[cur]));  // b_{K-1} = G_{K-1}
-  for (int k = K - 2; k >= 1; --k) {
-    DS_TRY(make_G(k, G));
-    // Chebyshev: b_k = G_k + 2 L^T b_{k+1} - b_{k+2};   Monomial: h_k = G_k + L^T h_{k+1}
-    DS_TRY(launch_spmm(St, B, Fin, buf[cur], cheb ? 2.f : 1.f, (cheb && old >= 0) ? buf[old] : nullptr, -1.f, G, 1.f,
-                       buf[nxt], st));
-    const int freed = old >= 0 ? old : 3 - cur - nxt;
-    old = cur;
-    cur = nxt;
-    nxt = freed;
-  }
-  DS_TRY(make_G(0, G));
-  // Chebyshev: dx = G_0 + L^T b_1 - b_2;   Monomial: dx = G_0 + L^T h_1
-  return launch_spmm(St, B, Fin, buf[cur], 1.f, (cheb && old >= 0) ? buf[old] : nullptr, -1.f, G, 1.f, dx, st);
+  // 5. dx = sum_k T_k(L~^T)(dz) W_k^T.  L~ acts on the pixel axis and W_k on the channel axis, so they
+  //    commute: the data gradient is the FORWARD pipeline applied to dz - the same (fused) recursion with
+  //    L~^T on Fout channels, then one segmented contraction with B(k, o, f) = kernel[(f*K + k), o].
+  //    (Equivalent to the Clenshaw adjoint sum of SURVEY a18, with K-1 hops and a single GEMM.)
+  DS_TRY(compute_basis(plan, recursion, K, B, Fout, dz, U, st, /*transpose=*/true));
+  if (mode != DS_MODE_FP32 && umma_supported(Fout, K, Fin) == 0)
+    return launch_umma_gemm(R, Fin, Fout, K, dz, U, R, kernel, /*b_k_stride=*/1, /*b_seg_stride=*/Fout,
+                            /*b_n_stride=*/(int64_t)K * Fout, nullptr, 1, DS_ACT_LINEAR, dx, Fin, mode, st);
+  return launch_gemm_nt_seg(R, Fin, Fout, K, dz, U, R * Fout, Fout, kernel, Fout, K, 1, dx, Fin, st);
 }
 
 int ds_bias_act_forward(int64_t R, int64_t F, const float* z, const float* bias, int32_t act, float* y, void* stream);

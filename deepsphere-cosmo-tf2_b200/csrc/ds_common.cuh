@@ -125,6 +125,10 @@ int launch_gemm_nn(int64_t R, int64_t N, int64_t Kc, int nseg, const float* A0, 
 int launch_gemm_nt(int64_t R, int64_t Nc, int64_t Kd, int nseg, const float* A, int64_t lda, const float* Bm,
                    int64_t ldb, int64_t b_nc_stride, int64_t b_seg_stride, const float* bias, int64_t bias_mod,
                    int act, float* C, int64_t ldc, int64_t c_seg_stride, cudaStream_t st);
+// C[R,Nc] = sum_seg A_seg[R,Kd] * Bm[nc*b_nc_stride + seg*b_seg_stride, :Kd]^T
+int launch_gemm_nt_seg(int64_t R, int64_t Nc, int64_t Kd, int nseg, const float* A0, const float* Arest,
+                       int64_t a_seg_stride, int64_t lda, const float* Bm, int64_t ldb, int64_t b_nc_stride,
+                       int64_t b_seg_stride, float* C, int64_t ldc, cudaStream_t st);
 // C[kc*c_kc_stride + seg*c_seg_stride, :N] = sum_r A_seg[r,kc] * D[r,:N]     (reduction over R rows)
 //   partial: workspace of gemm_tn_workspace_elems floats
 int64_t gemm_tn_workspace_elems(int64_t R, int64_t Kc, int nseg, int64_t N);

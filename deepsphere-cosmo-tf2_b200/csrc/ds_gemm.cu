@@ -120,6 +120,46 @@ __global__ void __launch_bounds__(256) gemm_nt_kernel(int64_t R, int64_t Nc, int
   }
 }
 
+// C[R,Nc] = sum_seg A_seg[R,Kd] * Bm[nc*bns + seg*bss, :Kd]^T   (segmented A, one output)
+__global__ void __launch_bounds__(256) gemm_nt_seg_kernel(int64_t R, int64_t Nc, int64_t Kd, int nseg,
+                                                          const float* __restrict__ A0, const float* __restrict__ Arest,
+                                                          int64_t a_seg_stride, int64_t lda,
+                                                          const float* __restrict__ Bm, int64_t ldb, int64_t bns,
+                                                          int64_t bss, float* __restrict__ C, int64_t ldc) {
+  __shared__ __align__(16) float As[BK][BM + PAD];
+  __shared__ __align__(16) float Bs[BK][BN + PAD];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int64_t r0 = (int64_t)blockIdx.x * BM, n0 = (int64_t)blockIdx.y * BN;
+  float acc[4][4] = {};
+  for (int seg = 0; seg < nseg; ++seg) {
+    const float* A = seg == 0 ? A0 : Arest + (int64_t)(seg - 1) * a_seg_stride;
+    for (int64_t k0 = 0; k0 < Kd; k0 += BK) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = tid + i * 256;
+        const int row = e >> 4, kk = e & 15;
+        const int64_t r = r0 + row, k = k0 + kk;
+        As[kk][row] = (r < R && k < Kd) ? __ldg(A + r * lda + k) : 0.f;
+        const int64_t c = n0 + row;
+        Bs[kk][row] = (c < Nc && k < Kd) ? __ldg(Bm + (c * bns + seg * bss) * ldb + k) : 0.f;
+      }
+      __syncthreads();
+      tile_fma(As, Bs, ty, tx, acc);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = r0 + ty * 4 + i;
+    if (r >= R) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t c = n0 + tx * 4 + j;
+      if (c < Nc) C[r * ldc + c] = acc[i][j];
+    }
+  }
+}
+
 // partial[split][seg][kc, n] = sum_{r in split} A_seg[r,kc] * D[r,n]
 __global__ void __launch_bounds__(256) gemm_tn_kernel(int64_t R, int64_t N, int64_t Kc, int nseg, int kc_tiles,
                                                       const float* __restrict__ A0, const float* __restrict__ Arest,
@@ -251,6 +291,17 @@ int launch_gemm_nt(int64_t R, int64_t Nc, int64_t Kd, int nseg, const float* A, 
   DS_CHECK(cdiv(Nc, BN) < 65536 && nseg < 65536, "gemm_nt: N or nseg too large");
   gemm_nt_kernel<<<grid, 256, 0, st>>>(R, Nc, Kd, A, lda, Bm, ldb, b_nc_stride, b_seg_stride, bias,
                                        bias_mod > 0 ? bias_mod : 1, act, C, ldc, c_seg_stride);
+  DS_LAUNCHED();
+  return 0;
+}
+
+int launch_gemm_nt_seg(int64_t R, int64_t Nc, int64_t Kd, int nseg, const float* A0, const float* Arest,
+                       int64_t a_seg_stride, int64_t lda, const float* Bm, int64_t ldb, int64_t b_nc_stride,
+                       int64_t b_seg_stride, float* C, int64_t ldc, cudaStream_t st) {
+  dim3 grid((unsigned)cdiv(R, BM), (unsigned)cdiv(Nc, BN));
+  DS_CHECK(cdiv(Nc, BN) < 65536, "gemm_nt_seg: N too large");
+  gemm_nt_seg_kernel<<<grid, 256, 0, st>>>(R, Nc, Kd, nseg, A0, Arest, a_seg_stride, lda, Bm, ldb, b_nc_stride,
+                                           b_seg_stride, C, ldc);
   DS_LAUNCHED();
   return 0;
 }

@@ -286,7 +286,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
           h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
           h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
           h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-          hi[idx] = h;
+          // the tensor core truncates fp32 operands to TF32 itself (probed: tools/umma_probe.py), so the
+          // high part needs no write-back: only the residual tile is materialised
           lo[idx] = l;
         }
         ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the UMMA operand fetch

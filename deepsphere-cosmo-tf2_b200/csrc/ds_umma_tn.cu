@@ -182,7 +182,7 @@ umma_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
         h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
         h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
         h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-        hi[idx] = h;
+        // (high part: implicit hardware truncation, see ds_umma.cu)
         lo[idx] = l;
       }
       ptx::fence_proxy_async_smem();
