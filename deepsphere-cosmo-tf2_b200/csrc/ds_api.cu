@@ -83,6 +83,14 @@ int64_t ds_graph_conv_basis_elems(int64_t M, int64_t B, int64_t Fin, int32_t K) 
   return K > 1 ? (int64_t)(K - 1) * B * M * Fin : 0;
 }
 
+int ds_graph_conv_basis(const ds_plan_t* plan, int32_t recursion, int32_t K, int64_t B, int64_t F, const float* x,
+                        float* basis, int32_t transpose, void* stream) {
+  using namespace ds;
+  DS_TRY(check_common(plan, recursion, K, B, F, F, DS_ACT_LINEAR, DS_MODE_FP32, "ds_graph_conv_basis"));
+  DS_CHECK(x && (K == 1 || basis), "ds_graph_conv_basis: NULL tensor");
+  return compute_basis(plan, recursion, K, B, F, x, basis, (cudaStream_t)stream, transpose != 0);
+}
+
 int ds_graph_conv_forward(const ds_plan_t* plan, int32_t recursion, int32_t K, int64_t B, int64_t Fin, int64_t Fout,
                           const float* x, const float* kernel, const float* bias, int32_t act, float* y, float* basis,
                           int32_t mode, void* stream) {

@@ -241,3 +241,20 @@ def spmm(plan, x, alpha=1.0, prev=None, beta=0.0, add=None, gamma=0.0, transpose
             "ds_spmm",
         )
     return out
+
+
+def basis(plan, x, K, recursion=nat.RECURSION_CHEBYSHEV, transpose=False):
+    """T_1..T_{K-1} of the recursion (gnn_layers.py:135-143) as a [K-1, B, M, F] tensor (no autograd)."""
+    _need_cuda(x, "basis")
+    x = _f32c(x)
+    B, M, F = x.shape
+    out = torch.empty((max(K - 1, 1), B, M, F), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device.index):
+        nat.check(
+            nat.lib().ds_graph_conv_basis(
+                plan.handle(x.device.index), recursion, K, B, F, nat.ptr(x), nat.ptr(out), 1 if transpose else 0,
+                nat.current_stream(),
+            ),
+            "ds_graph_conv_basis",
+        )
+    return out[: K - 1]

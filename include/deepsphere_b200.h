@@ -113,6 +113,11 @@ int ds_spmm(const ds_plan_t* plan, int32_t transpose, int64_t B, int64_t F, cons
  * ([K-1, B, M, Fin]) and may be handed to ds_graph_conv_backward to skip recomputation.
  */
 int64_t ds_graph_conv_basis_elems(int64_t M, int64_t B, int64_t Fin, int32_t K);
+/* only the recursion of gnn_layers.py:135-143 / :287-290: basis[k-1] = T_k(L~) x for k = 1..K-1 (L~^T when
+ * transpose != 0).  On a HEALPix 8-neighbour graph with a lattice attachment all K-1 hops run fused in one
+ * kernel; otherwise one streaming hop kernel per k. */
+int ds_graph_conv_basis(const ds_plan_t* plan, int32_t recursion, int32_t K, int64_t B, int64_t F, const float* x,
+                        float* basis, int32_t transpose, void* stream);
 int ds_graph_conv_forward(const ds_plan_t* plan, int32_t recursion, int32_t K, int64_t B, int64_t Fin,
                           int64_t Fout, const float* x, const float* kernel, const float* bias, int32_t act,
                           float* y, float* basis, int32_t mode, void* stream);
