@@ -49,26 +49,11 @@ struct LoadEvent {
   bool valid;
 };
 
-// packed fp32 arithmetic (Blackwell FFMA2 / FMUL2): two IEEE fp32 FMAs per instruction, identical rounding to
-// two scalar fmaf; halves the issue slots of the stencil, which is issue-bound (ncu r1e)
-__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
-  return ((unsigned long long)__float_as_uint(hi) << 32) | (unsigned long long)__float_as_uint(lo);
-}
 __device__ __forceinline__ float4 f4_fma(float w, const float4& x, const float4& acc) {
-  unsigned long long r0, r1;
-  const unsigned long long ww = pk2(w, w);
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r0) : "l"(ww), "l"(pk2(x.x, x.y)), "l"(pk2(acc.x, acc.y)));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r1) : "l"(ww), "l"(pk2(x.z, x.w)), "l"(pk2(acc.z, acc.w)));
-  return make_float4(__uint_as_float((unsigned)r0), __uint_as_float((unsigned)(r0 >> 32)),
-                     __uint_as_float((unsigned)r1), __uint_as_float((unsigned)(r1 >> 32)));
+  return make_float4(fmaf(w, x.x, acc.x), fmaf(w, x.y, acc.y), fmaf(w, x.z, acc.z), fmaf(w, x.w, acc.w));
 }
 __device__ __forceinline__ float4 f4_scale(float w, const float4& x) {
-  unsigned long long r0, r1;
-  const unsigned long long ww = pk2(w, w);
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r0) : "l"(ww), "l"(pk2(x.x, x.y)));
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r1) : "l"(ww), "l"(pk2(x.z, x.w)));
-  return make_float4(__uint_as_float((unsigned)r0), __uint_as_float((unsigned)(r0 >> 32)),
-                     __uint_as_float((unsigned)r1), __uint_as_float((unsigned)(r1 >> 32)));
+  return make_float4(w * x.x, w * x.y, w * x.z, w * x.w);
 }
 
 template <int H, int FC, int S>
