@@ -182,11 +182,17 @@ __global__ void __launch_bounds__(lat_threads(LAT_T + 2 * H, FC, S), 1) lattice_
           const bool use_old = be != 0.f;
           const float4* cp = cur + strip_off;
           float4* op = oth + strip_off;
+          // explicit software pipeline: the window row needed by iteration jj + 1 and the `old` value of
+          // iteration jj + 1 are requested one iteration ahead, so ~40 FMAs cover each shared-memory round trip
           float4 a0 = cp[-LW - 1], a1 = cp[-LW], a2 = cp[-LW + 1];
           float4 b0 = cp[-1], b1 = cp[0], b2 = cp[1];
+          float4 c0 = cp[LW - 1], c1 = cp[LW], c2 = cp[LW + 1];
+          float4 oldv = use_old ? op[0] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int jj = 0; jj < S; ++jj) {
-            const float4 c0 = cp[(jj + 1) * LW - 1], c1 = cp[(jj + 1) * LW], c2 = cp[(jj + 1) * LW + 1];
+            const float4 d0 = cp[(jj + 2) * LW - 1], d1 = cp[(jj + 2) * LW], d2 = cp[(jj + 2) * LW + 1];
+            float4 oldn = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (use_old && jj + 1 < S) oldn = op[(jj + 1) * LW];
             float4 acc = f4_scale(w[jj][8], b1);
             acc = f4_fma(w[jj][0], b0, acc);  // SW (-1, 0)
             acc = f4_fma(w[jj][1], c0, acc);  // W  (-1,+1)
@@ -197,11 +203,13 @@ __global__ void __launch_bounds__(lat_threads(LAT_T + 2 * H, FC, S), 1) lattice_
             acc = f4_fma(w[jj][6], a1, acc);  // SE ( 0,-1)
             acc = f4_fma(w[jj][7], a0, acc);  // S  (-1,-1)
             float4 r = f4_scale(al, acc);
-            if (use_old) r = f4_fma(be, op[jj * LW], r);
+            if (use_old) r = f4_fma(be, oldv, r);
             const int j = j0 + jj;
             if (j >= lo && j <= hi) op[jj * LW] = r;
             a0 = b0; a1 = b1; a2 = b2;
             b0 = c0; b1 = c1; b2 = c2;
+            c0 = d0; c1 = d1; c2 = d2;
+            oldv = oldn;
           }
         }
         __syncthreads();
@@ -260,7 +268,7 @@ int lattice_configure(const LatticeDev& L, int64_t B, int64_t M, int F, LatticeA
 
 int launch_lattice(const LatticeDev& L, LatticeArgs& a, int threads, int smem, cudaStream_t st) {
   (void)L; (void)threads; (void)smem;
-  static const bool strip4 = [] { const char* e = getenv("DEEPSPHERE_LATTICE_STRIP"); return !(e && atoi(e) == 8); }();
+  static const bool strip4 = [] { const char* e = getenv("DEEPSPHERE_LATTICE_STRIP"); return e && atoi(e) == 4; }();
 #define DS_LAT_CASE(HH)                                                        \
   case HH:                                                                     \
     return a.FC == 16 ? (strip4 ? launch_instance<HH, 16, 4>(a, st) : launch_instance<HH, 16, 8>(a, st)) \
