@@ -193,17 +193,15 @@ __global__ void __launch_bounds__(lat_threads(LAT_T + 2 * H, FC, S), 1) lattice_
             const float4 d0 = cp[(jj + 2) * LW - 1], d1 = cp[(jj + 2) * LW], d2 = cp[(jj + 2) * LW + 1];
             float4 oldn = make_float4(0.f, 0.f, 0.f, 0.f);
             if (use_old && jj + 1 < S) oldn = op[(jj + 1) * LW];
-            // two partial sums per channel: halves the dependent-FMA chain (fixed-latency stalls, ncu r1h)
             float4 acc = f4_scale(w[jj][8], b1);
-            float4 acc2 = f4_scale(w[jj][0], b0);     // SW (-1, 0)
-            acc = f4_fma(w[jj][1], c0, acc);          // W  (-1,+1)
-            acc2 = f4_fma(w[jj][2], c1, acc2);        // NW ( 0,+1)
-            acc = f4_fma(w[jj][3], c2, acc);          // N  (+1,+1)
-            acc2 = f4_fma(w[jj][4], b2, acc2);        // NE (+1, 0)
-            acc = f4_fma(w[jj][5], a2, acc);          // E  (+1,-1)
-            acc2 = f4_fma(w[jj][6], a1, acc2);        // SE ( 0,-1)
-            acc = f4_fma(w[jj][7], a0, acc);          // S  (-1,-1)
-            acc = make_float4(acc.x + acc2.x, acc.y + acc2.y, acc.z + acc2.z, acc.w + acc2.w);
+            acc = f4_fma(w[jj][0], b0, acc);  // SW (-1, 0)
+            acc = f4_fma(w[jj][1], c0, acc);  // W  (-1,+1)
+            acc = f4_fma(w[jj][2], c1, acc);  // NW ( 0,+1)
+            acc = f4_fma(w[jj][3], c2, acc);  // N  (+1,+1)
+            acc = f4_fma(w[jj][4], b2, acc);  // NE (+1, 0)
+            acc = f4_fma(w[jj][5], a2, acc);  // E  (+1,-1)
+            acc = f4_fma(w[jj][6], a1, acc);  // SE ( 0,-1)
+            acc = f4_fma(w[jj][7], a0, acc);  // S  (-1,-1)
             float4 r = f4_scale(al, acc);
             if (use_old) r = f4_fma(be, oldv, r);
             const int j = j0 + jj;
