@@ -21,8 +21,12 @@ int launch_umma_gemm(int64_t R, int64_t N, int64_t Kc, int nseg, const float* A0
 int umma_tn_supported(int64_t R, int64_t N, int64_t Kc, int nseg);
 int64_t umma_tn_workspace_elems(int64_t R, int64_t N, int64_t Kc, int nseg);
 int launch_umma_gemm_tn(int64_t R, int64_t N, int64_t Kc, int nseg, const float* A0, const float* Arest, const float* D,
-                        float* C, int64_t ldc, int64_t c_kc_stride, int64_t c_seg_stride, float* partial, int mode,
-                        cudaStream_t st);
+                        float* C, int64_t s_kc, int64_t s_seg, int64_t s_n, float* partial, int mode, cudaStream_t st);
+// fully fused recursion + contraction on the lattice (ds_lattice_conv.cu / ds_lattice_api.cu)
+bool fused_conv_usable(const ds_plan* plan, int32_t K, int64_t B, int64_t F, int64_t N, int32_t mode);
+int fused_conv(const ds_plan* plan, int32_t recursion, int32_t K, int64_t B, int64_t F, int64_t N, const float* in0,
+               float* basis_out, const float* W, int64_t s_f, int64_t s_k, int64_t s_n, const float* bias, int act,
+               float* y, int mode, cudaStream_t st);
 
 bool lattice_usable(const ds_plan* plan, int32_t K, int64_t B, int64_t F);
 int lattice_recursion(const ds_plan* plan, int64_t B, int F, int nsteps, const float* in0, const float* const* add,
@@ -100,6 +104,12 @@ int ds_graph_conv_forward(const ds_plan_t* plan, int32_t recursion, int32_t K, i
   DS_CHECK(K == 1 || basis != nullptr, "ds_graph_conv_forward: basis workspace required for K > 1");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t M = plan->M, R = B * M, A = R * Fin;
+  if (fused_conv_usable(plan, K, B, Fin, Fout, mode)) {
+    // recursion + contraction in one kernel; the basis never leaves the chip (and `basis` is left untouched:
+    // the fused backward does not need it)
+    return fused_conv(plan, recursion, K, B, Fin, Fout, x, nullptr, kernel, (int64_t)K * Fout, Fout, 1, bias, act, y,
+                      mode, st);
+  }
   DS_TRY(compute_basis(plan, recursion, K, B, Fin, x, basis, st));
   if (mode == DS_MODE_FP32) {
     return launch_gemm_nn(R, Fout, Fin, K, x, basis, A, Fin, kernel, Fout, K, 1, bias, Fout, act, y, Fout, st);
@@ -119,6 +129,7 @@ int64_t ds_graph_conv_backward_workspace_elems(int64_t M, int64_t B, int64_t Fin
   if (act != DS_ACT_LINEAR) n += R * Fout;                  // dz
   if (!have_basis && K > 1) n += (int64_t)(K - 1) * A;      // recomputed basis
   if (K > 1) n += (int64_t)(K - 1) * R * Fout;              // T_1..T_{K-1} of L~^T applied to dz
+  n += umma_tn_workspace_elems(R, Fin, Fout, K);            // fused path: dkernel partials in the transposed form
   n += std::max(gemm_tn_workspace_elems(R, Fin, K, Fout),   // dkernel split partials (fp32 / tensor-core kernel)
                 umma_tn_workspace_elems(R, Fout, Fin, K));
   n += colsum_workspace_elems(Fout);                        // dbias partials
@@ -145,6 +156,19 @@ int ds_graph_conv_backward(const ds_plan_t* plan, int32_t recursion, int32_t K, 
     DS_TRY(launch_act_backward(R, Fout, Fout, y, dy, act, dzb, st));
     dz = dzb;
   }
+  // fused path: dx = fused conv on dz (also emits U_k = T_k(L~^T) dz), dkernel = [dz|U_1..]^T-contracted with x
+  if (dx != nullptr && K > 1 && plan->symmetric && fused_conv_usable(plan, K, B, Fout, Fin, mode) &&
+      umma_tn_supported(R, Fin, Fout, K) == 0) {
+    float* U = take((int64_t)(K - 1) * R * Fout);
+    float* tn_partial = take(umma_tn_workspace_elems(R, Fin, Fout, K));
+    float* cs_partial = take(colsum_workspace_elems(Fout));
+    if (dbias != nullptr) DS_TRY(launch_colsum(R, Fout, Fout, dz, dbias, cs_partial, st));
+    // B_k(o, f) = kernel[(f*K + k)*Fout + o]
+    DS_TRY(fused_conv(plan, recursion, K, B, Fout, Fin, dz, U, kernel, 1, Fout, (int64_t)K * Fout, nullptr,
+                      DS_ACT_LINEAR, dx, mode, st));
+    // dkernel[(f*K + k)*Fout + o] = sum_r U_k[r, o] x[r, f]   (adjoint identity: sum_m T_k(L~)x . dz = sum_m x . T_k(L~^T)dz)
+    return launch_umma_gemm_tn(R, Fin, Fout, K, dz, U, x, dkernel, 1, Fout, (int64_t)K * Fout, tn_partial, mode, st);
+  }
   // 2. basis (saved by the forward or recomputed)
   const float* T = basis;
   if (T == nullptr && K > 1) {
@@ -160,7 +184,7 @@ int ds_graph_conv_backward(const ds_plan_t* plan, int32_t recursion, int32_t K, 
   if (dbias != nullptr) DS_TRY(launch_colsum(R, Fout, Fout, dz, dbias, cs_partial, st));
   // 4. dkernel[f*K + k, o] = sum_{b,m} T_k[b,m,f] dz[b,m,o]
   if (mode != DS_MODE_FP32 && umma_tn_supported(R, Fout, Fin, K) == 0) {
-    DS_TRY(launch_umma_gemm_tn(R, Fout, Fin, K, x, T, dz, dkernel, Fout, K, 1, tn_partial, mode, st));
+    DS_TRY(launch_umma_gemm_tn(R, Fout, Fin, K, x, T, dz, dkernel, (int64_t)K * Fout, Fout, 1, tn_partial, mode, st));
   } else {
     DS_TRY(launch_gemm_tn(R, Fout, Fin, K, x, T, A, Fin, dz, Fout, dkernel, Fout, K, 1, tn_partial, st));
   }

@@ -131,6 +131,75 @@ int lattice_recursion(const ds_plan* plan, int64_t B, int F, int nsteps, const f
   return sub_problem_recursion(plan, B, F, nsteps, in0, add, out, alpha, beta, gamma, st);
 }
 
+bool lattice_conv_usable(const LatticeDev& L, int F, int N, int mode);
+int launch_lattice_conv(const LatticeDev& L, int64_t B, int64_t M, int F, int N, int recursion, const float* in0,
+                        float* const* out, const float* W, int64_t s_f, int64_t s_k, int64_t s_n, const float* bias,
+                        int act, float* y, int mode, cudaStream_t st);
+int umma_supported(int64_t Kc, int nseg, int64_t N);
+int launch_umma_gemm(int64_t R, int64_t N, int64_t Kc, int nseg, const float* A0, const float* Arest,
+                     int64_t a_seg_stride_rows, const float* Bm, int64_t b_k_stride, int64_t b_seg_stride,
+                     int64_t b_n_stride, const float* bias, int64_t bias_mod, int act, float* C, int64_t ldc, int mode,
+                     cudaStream_t st);
+
+bool fused_conv_usable(const ds_plan* plan, int32_t K, int64_t B, int64_t F, int64_t N, int32_t mode) {
+  (void)B;
+  if (!plan->lattice || !plan->symmetric || K < 2) return false;
+  const LatticeAttachment* L = plan->lattice;
+  if (K - 1 != L->H) return false;
+  if (umma_supported(F, K, N) != 0) return false;  // the irregular tiles go through the tensor-core GEMM
+  return lattice_conv_usable(L->dev, (int)F, (int)N, mode);
+}
+
+// y = act( sum_k T_k(L~)(in0) B_k + bias ),  B_k(f, n) = W[f*s_f + k*s_k + n*s_n];  basis_out (optional):
+// [K-1, B, M, F] receives T_1..T_{K-1}(in0).  Regular tiles: one fused kernel; irregular tiles: generic hops +
+// tensor-core GEMM on the gathered closure, own rows scattered back.
+int fused_conv(const ds_plan* plan, int32_t recursion, int32_t K, int64_t B, int64_t F, int64_t N, const float* in0,
+               float* basis_out, const float* W, int64_t s_f, int64_t s_k, int64_t s_n, const float* bias, int act,
+               float* y, int mode, cudaStream_t st) {
+  const LatticeAttachment* L = plan->lattice;
+  DS_CHECK(L != nullptr, "fused_conv: no lattice attachment");
+  const int64_t M = plan->M, A = B * M * F;
+  float* out[LAT_MAX_STEPS] = {};
+  if (basis_out != nullptr)
+    for (int s = 1; s < K; ++s) out[s - 1] = basis_out + (int64_t)(s - 1) * A;
+  DS_TRY(launch_lattice_conv(L->dev, B, M, (int)F, (int)N, recursion, in0, basis_out ? out : nullptr, W, s_f, s_k, s_n,
+                             bias, act, y, mode, st));
+  if (L->n_own == 0) return 0;
+  // ---- irregular tiles ----
+  const int FV = (int)(F / 4), NV = (int)(N / 4);
+  const int64_t n = L->n_closure, As = B * n * F;
+  float* ws = nullptr;  // [K][B, n, F] basis on the closure, then [B, n, N] result
+  DS_CUDA(cudaMallocAsync((void**)&ws, sizeof(float) * ((int64_t)K * As + B * n * N), st));
+  float* ys = ws + (int64_t)K * As;
+  gather_rows_kernel<<<grid_for(B * n * FV), 256, 0, st>>>(B, M, n, FV, L->closure_rows,
+                                                          reinterpret_cast<const float4*>(in0),
+                                                          reinterpret_cast<float4*>(ws));
+  g_launches.fetch_add(1);
+  int rc = 0;
+  for (int k = 1; k < K && rc == 0; ++k) {
+    const bool cheb2 = recursion == DS_RECURSION_CHEBYSHEV && k >= 2;
+    rc = launch_spmm(L->sub_plan->fwd, B, F, ws + (int64_t)(k - 1) * As, cheb2 ? 2.f : 1.f,
+                     cheb2 ? ws + (int64_t)(k - 2) * As : nullptr, -1.f, nullptr, 0.f, ws + (int64_t)k * As, st);
+    if (rc == 0 && basis_out != nullptr) {
+      scatter_rows_kernel<<<grid_for(B * L->n_own * FV), 256, 0, st>>>(
+          B, M, n, L->n_own, FV, L->closure_rows, L->own_sub, reinterpret_cast<const float4*>(ws + (int64_t)k * As),
+          reinterpret_cast<float4*>(out[k - 1]));
+      g_launches.fetch_add(1);
+    }
+  }
+  if (rc == 0)
+    rc = launch_umma_gemm(B * n, N, F, K, ws, ws + As, B * n, W, s_f, s_k, s_n, bias, N, act, ys, N, mode, st);
+  if (rc == 0) {
+    scatter_rows_kernel<<<grid_for(B * L->n_own * NV), 256, 0, st>>>(B, M, n, L->n_own, NV, L->closure_rows, L->own_sub,
+                                                                     reinterpret_cast<const float4*>(ys),
+                                                                     reinterpret_cast<float4*>(y));
+    g_launches.fetch_add(1);
+  }
+  cudaFreeAsync(ws, st);
+  if (rc == 0) DS_CUDA(cudaGetLastError());
+  return rc;
+}
+
 }  // namespace ds
 
 extern "C" int ds_plan_attach_lattice(ds_plan_t* plan, int32_t n_tiles, int32_t LW, int32_t H, int32_t T,

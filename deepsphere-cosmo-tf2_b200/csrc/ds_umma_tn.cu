@@ -197,9 +197,9 @@ umma_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
   }
 }
 
-// C[(kc*cks + seg*css), n] = sum over CTAs of partial[cta][q*32 + i][n],  kc = (q % q_per_seg)*32 + i
+// C[kc*s_kc + seg*s_seg + n*s_n] = sum over CTAs of partial[cta][q*32 + i][n],  kc = (q % q_per_seg)*32 + i
 __global__ void umma_tn_reduce_kernel(int n_cta, int n_q, int q_per_seg, int N, int64_t Kc, const float* __restrict__ partial,
-                                      float* __restrict__ C, int64_t ldc, int64_t cks, int64_t css) {
+                                      float* __restrict__ C, int64_t s_kc, int64_t s_seg, int64_t s_n) {
   const int64_t total = (int64_t)n_q * BLK * N;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int n = (int)(e % N);
@@ -210,7 +210,7 @@ __global__ void umma_tn_reduce_kernel(int n_cta, int n_q, int q_per_seg, int N, 
     if (kc >= Kc) continue;
     float s = 0.f;
     for (int c = 0; c < n_cta; ++c) s += partial[(size_t)c * total + e];
-    C[(kc * cks + seg * css) * ldc + n] = s;
+    C[kc * s_kc + seg * s_seg + n * s_n] = s;
   }
 }
 
@@ -298,9 +298,9 @@ int64_t umma_tn_workspace_elems(int64_t R, int64_t N, int64_t Kc, int nseg) {
 }
 
 // A_seg: [R, Kc] contiguous (seg 0 = A0, others stacked in Arest with stride R rows); D: [R, N] contiguous
+//   output element (kc, seg, n) goes to C[kc*s_kc + seg*s_seg + n*s_n]
 int launch_umma_gemm_tn(int64_t R, int64_t N, int64_t Kc, int nseg, const float* A0, const float* Arest, const float* D,
-                        float* C, int64_t ldc, int64_t c_kc_stride, int64_t c_seg_stride, float* partial, int mode,
-                        cudaStream_t st) {
+                        float* C, int64_t s_kc, int64_t s_seg, int64_t s_n, float* partial, int mode, cudaStream_t st) {
   const int three = mode == DS_MODE_TF32X3 ? 1 : 0;
   TnGeometry g;
   DS_CHECK(tn_geometry(R, N, Kc, nseg, three, g) == 0, "umma tn: unsupported shape Kc=%lld N=%lld nseg=%d",
@@ -335,7 +335,7 @@ int launch_umma_gemm_tn(int64_t R, int64_t N, int64_t Kc, int nseg, const float*
   DS_LAUNCHED();
   const int64_t total = (int64_t)g.n_q * BLK * N;
   umma_tn_reduce_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 2048), 256, 0, st>>>(
-      g.n_cta, g.n_q, g.q_per_seg, (int)N, Kc, partial, C, ldc, c_kc_stride, c_seg_stride);
+      g.n_cta, g.n_q, g.q_per_seg, (int)N, Kc, partial, C, s_kc, s_seg, s_n);
   DS_LAUNCHED();
   return 0;
 }

@@ -75,3 +75,38 @@ def test_lattice_masked_sky():
     assert rel_err(y, orc.graph_conv_forward(x, Lt, w, 4, "chebyshev", dtype=np.float64)) <= 1e-5
     rdx, rdk, _ = orc.graph_conv_backward(x, Lt, w, 4, dy, "chebyshev")
     assert rel_err(dx, rdx) <= 1e-5 and rel_err(dk, rdk) <= 1e-5
+
+
+@pytest.mark.parametrize("mode,tol", [("tf32", 1e-3), ("tf32x3", 2e-5)])
+@pytest.mark.parametrize("cls", ["Chebyshev", "Monomial"])
+@pytest.mark.parametrize("nside,B,Fin,Fout,K", [(32, 2, 16, 16, 5), (64, 2, 64, 64, 5), (32, 3, 32, 16, 3),
+                                                (32, 2, 16, 64, 2), (32, 1, 48, 32, 4)])
+def test_fused_lattice_conv_matches_oracle(mode, tol, cls, nside, B, Fin, Fout, K):
+    """ds_lattice_conv.cu: recursion + tcgen05 contraction in one kernel (forward), and the same kernel on dz
+    plus the transposed weight-gradient contraction (backward), against the float64 oracle."""
+    g = SphereHealpix(nside, k=8)
+    M = g.L.shape[0]
+    torch.manual_seed(0)
+    layer = getattr(gnn_layers, cls)(L=g.L, K=K, Fout=Fout, use_bias=True, activation="elu", mode=mode)
+    rng = np.random.default_rng(K + Fin)
+    x = rng.standard_normal((B, M, Fin))
+    dy = rng.standard_normal((B, M, Fout))
+    xt = torch.tensor(x, dtype=torch.float32, device="cuda", requires_grad=True)
+    before = nat.launch_count()
+    y = layer(xt)
+    fwd_launches = nat.launch_count() - before
+    y.backward(torch.tensor(dy, dtype=torch.float32, device="cuda"))
+    assert layer._plan.info(0)["lattice"] == 1
+    # fused forward = weight-image prep + fused kernel + the irregular-tile sub-problem; no per-hop launches
+    assert fwd_launches <= 4 + 2 * K, fwd_launches
+    rec = cls.lower()
+    Lt, _ = orc.prepare_laplacian(g.L, 0.75 if rec == "chebyshev" else 1.0)
+    xr = torch.tensor(x, requires_grad=True)
+    wr = layer.kernel.detach().double().cpu().requires_grad_(True)
+    br = layer.bias.detach().double().cpu().requires_grad_(True)
+    yr = torch.nn.functional.elu(orc.torch_cpu_graph_conv(xr, Lt, wr, K, rec) + br)
+    yr.backward(torch.tensor(dy))
+    assert rel_err(y.detach().cpu().numpy(), yr.detach().numpy()) <= tol
+    assert rel_err(xt.grad.cpu().numpy(), xr.grad.numpy()) <= tol
+    assert rel_err(layer.kernel.grad.cpu().numpy(), wr.grad.numpy()) <= tol
+    assert rel_err(layer.bias.grad.cpu().numpy(), br.grad.numpy()) <= tol
