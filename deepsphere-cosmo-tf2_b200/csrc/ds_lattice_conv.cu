@@ -76,7 +76,7 @@ __device__ __forceinline__ float4 c4_residual(const float4& v) {
 }
 
 template <int H, bool THREE>
-__global__ void __maxnreg__(224) lattice_conv_kernel(const LatConvArgs a) {
+__global__ void __launch_bounds__(conv_threads(CT + 2 * H), 1) lattice_conv_kernel(const LatConvArgs a) {
   constexpr int T = CT, LW = T + 2 * H, P = LW * LW, S = CS;
   constexpr int PL = conv_plane(LW);
   constexpr int TASKS = conv_tasks(LW), NT = conv_threads(LW);
