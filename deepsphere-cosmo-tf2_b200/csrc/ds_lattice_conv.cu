@@ -48,8 +48,8 @@ constexpr int CFC = 16;  // channels per chunk
 constexpr int CVPP = 4;  // float4 planes per chunk
 constexpr int CS = 8;    // strip height
 
-__host__ __device__ constexpr int conv_plane(int LW) {  // float4 per plane, == 2 (mod 8); CS + 3 rows of slack
-  int v = (LW + 3 + CS) * LW;
+__host__ __device__ constexpr int conv_plane(int LW) {  // float4 per plane, == 2 (mod 8): one pad row above, the
+  int v = (((LW + CS - 1) / CS) * CS + 3) * LW;       // strips' rows, two rows of look-ahead for the software pipeline
   while (v % 8 != 2) ++v;
   return v;
 }
