@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(lat_threads(LAT_T + 2 * H, FC, S), 1) lattice_
       issue(next_event(it, 0));  // ... and immediately puts the next event in flight
       __syncthreads();
 #pragma unroll 1
-      for (int s = 1; s <= H; ++s) {
+      for (int s = 1; s <= H && s <= a.nsteps; ++s) {
         const float al = a.alpha[s - 1];
         float be = a.beta[s - 1];
         if (a.add[s - 1] != nullptr) {

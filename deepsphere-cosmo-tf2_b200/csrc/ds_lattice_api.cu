@@ -63,7 +63,7 @@ void lattice_free(LatticeAttachment* L) {
 bool lattice_usable(const ds_plan* plan, int32_t K, int64_t B, int64_t F) {
   if (!plan->lattice || !plan->symmetric) return false;
   const LatticeAttachment* L = plan->lattice;
-  if (K - 1 != L->H || K < 2 || F % 4 != 0) return false;
+  if (K - 1 > L->H || K < 2 || F % 4 != 0) return false;
   LatticeArgs a;
   int threads = 0, smem = 0;
   return lattice_configure(L->dev, B, plan->M, (int)F, a, &threads, &smem) == 0;
@@ -114,7 +114,7 @@ static int sub_problem_recursion(const ds_plan* plan, int64_t B, int F, int nste
 int lattice_recursion(const ds_plan* plan, int64_t B, int F, int nsteps, const float* in0, const float* const* add,
                       float* const* out, const float* alpha, const float* beta, const float* gamma, cudaStream_t st) {
   const LatticeAttachment* L = plan->lattice;
-  DS_CHECK(L != nullptr && nsteps == L->H && nsteps <= LAT_MAX_STEPS, "lattice_recursion: plan mismatch");
+  DS_CHECK(L != nullptr && nsteps >= 1 && nsteps <= L->H && nsteps <= LAT_MAX_STEPS, "lattice_recursion: plan mismatch");
   LatticeArgs a;
   int threads = 0, smem = 0;
   DS_CHECK(lattice_configure(L->dev, B, plan->M, F, a, &threads, &smem) == 0, "lattice_recursion: cannot configure");
@@ -141,12 +141,18 @@ int launch_umma_gemm(int64_t R, int64_t N, int64_t Kc, int nseg, const float* A0
                      int64_t b_n_stride, const float* bias, int64_t bias_mod, int act, float* C, int64_t ldc, int mode,
                      cudaStream_t st);
 
+bool lattice_conv2_usable(const LatticeDev& L, int nsteps, int F, int N, int mode);
+int launch_lattice_conv2(const LatticeDev& L, int nsteps, int64_t B, int64_t M, int F, int N, int recursion,
+                         const float* in0, float* const* out, const float* W, int64_t s_f, int64_t s_k, int64_t s_n,
+                         const float* bias, int act, float* y, cudaStream_t st);
+
 bool fused_conv_usable(const ds_plan* plan, int32_t K, int64_t B, int64_t F, int64_t N, int32_t mode) {
   (void)B;
   if (!plan->lattice || !plan->symmetric || K < 2) return false;
   const LatticeAttachment* L = plan->lattice;
-  if (K - 1 != L->H) return false;
   if (umma_supported(F, K, N) != 0) return false;  // the irregular tiles go through the tensor-core GEMM
+  if (lattice_conv2_usable(L->dev, K - 1, (int)F, (int)N, mode)) return true;  // register-resident kernel (ds_lattice_conv2.cu)
+  if (K - 1 != L->H) return false;
   return lattice_conv_usable(L->dev, (int)F, (int)N, mode);
 }
 
@@ -162,8 +168,13 @@ int fused_conv(const ds_plan* plan, int32_t recursion, int32_t K, int64_t B, int
   float* out[LAT_MAX_STEPS] = {};
   if (basis_out != nullptr)
     for (int s = 1; s < K; ++s) out[s - 1] = basis_out + (int64_t)(s - 1) * A;
-  DS_TRY(launch_lattice_conv(L->dev, B, M, (int)F, (int)N, recursion, in0, basis_out ? out : nullptr, W, s_f, s_k, s_n,
-                             bias, act, y, mode, st));
+  if (lattice_conv2_usable(L->dev, K - 1, (int)F, (int)N, mode)) {
+    DS_TRY(launch_lattice_conv2(L->dev, K - 1, B, M, (int)F, (int)N, recursion, in0, basis_out ? out : nullptr, W, s_f,
+                                s_k, s_n, bias, act, y, st));
+  } else {
+    DS_TRY(launch_lattice_conv(L->dev, B, M, (int)F, (int)N, recursion, in0, basis_out ? out : nullptr, W, s_f, s_k, s_n,
+                               bias, act, y, mode, st));
+  }
   if (L->n_own == 0) return 0;
   // ---- irregular tiles ----
   const int FV = (int)(F / 4), NV = (int)(N / 4);

@@ -434,8 +434,10 @@ bool conv_fits(int N, bool three) {
 bool lattice_conv_usable(const LatticeDev& L, int F, int N, int mode) {
   if (mode == DS_MODE_FP32 || L.n_tiles <= 0 || L.T != CT) return false;
   if (F % 16 != 0 || N % 16 != 0 || N < 16 || N > 128) return false;
-  static const bool disabled = [] { const char* e = getenv("DEEPSPHERE_FUSED_CONV"); return e && atoi(e) == 0; }();
-  if (disabled) return false;
+  // opt-in: this first fused kernel is shared-memory-bandwidth bound and slower than recursion + GEMM kernels;
+  // the register-resident ds_lattice_conv2.cu supersedes it
+  static const bool enabled = [] { const char* e = getenv("DEEPSPHERE_FUSED_CONV"); return e && atoi(e) == 1; }();
+  if (!enabled) return false;
   const bool three = mode == DS_MODE_TF32X3;
   switch (L.H) {
     case 1: return conv_fits<1>(N, three);

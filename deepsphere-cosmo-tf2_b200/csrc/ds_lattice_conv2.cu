@@ -1,0 +1,526 @@
+// Register-resident fused graph convolution on the HEALPix lattice (sm_100a), warp specialised.
+//
+//   y[b, m, :] = act( sum_k T_k(L~) x [b, m, :] * W_k + bias )            (gnn_layers.py:131-159)
+//
+// Work item = (16x16-pixel tile + 4-ring halo = 24x24 lattice, batch element b, 16-channel chunk c).
+// What differs from ds_lattice_conv.cu (whose recursion is shared-memory-bandwidth bound at ~5 accesses per
+// 36 FMAs): every compute thread OWNS a 3x3 pixel block x 4 channels for all hops of an item and keeps
+// T_{k-1} and T_{k-2} of that block in REGISTERS next to its 81 stencil weights.  Shared memory only carries
+// the neighbour exchange: per hop a thread stores its 9 new values and loads the 16 perimeter values
+// (2.8 accesses per 36 FMAs), and the very same exchange buffer is the K-major no-swizzle UMMA A operand, so
+// the contraction costs no extra shared-memory writes.
+//
+// Roles (384 threads, 1 CTA / SM, registers rebalanced with setmaxnreg):
+//   warps 0-7  compute: warp R owns lattice rows 3R..3R+2, lane = (channel quad q, column block cb); hops whose
+//              active region does not reach the warp's rows are skipped by the whole warp.  They also drain the
+//              TMEM accumulators (bias + activation + store of the own pixels), one (tile, b) behind the MMAs.
+//   warp  8    one lane: streams the weight slice of the next chunk (cp.async.bulk) and issues
+//              tcgen05.mma.kind::tf32 after every hop: A = T_k rows 4..19 of the lattice (384 positions = 3 M-tiles),
+//              B = 16-channel slice of W_k, accumulating over hops and chunks in TMEM (double buffered).
+//   warps 9-11 gather the next item's input rows into a staging buffer (cp.async, zero fill for holes).
+//
+// Exchange-buffer layout: 4 float4 planes (channel quads) of 26 x 24 positions; lattice (row j, column c) sits
+// at position (j + 1) * 24 + (c % 3) * 8 + c / 3, i.e. the three columns of a block are de-interleaved so that
+// the 8 lanes of a quarter-warp always touch 8 consecutive float4 (conflict-free LDS.128 / STS.128), and 8
+// consecutive positions are one UMMA core matrix (SBO = 128 B, LBO = plane stride).
+//
+// Chebyshev: the register-resident weights are 2 L~ (exact doubling), so T_k = (2L~) T_{k-1} - T_{k-2} costs exactly
+// 9 FMAs per output (the subtraction rides on the first FMA); hop 1 halves its result (T_1 = L~ T_0).
+// Monomial: plain T_k = L~ T_{k-1}.
+#include <algorithm>
+#include <cstdlib>
+#include <type_traits>
+
+#include "ds_lattice.cuh"
+#include "ds_ptx.cuh"
+
+namespace ds {
+
+namespace {
+
+constexpr int C2_LW = 24, C2_T = 16, C2_H = 4, C2_P = C2_LW * C2_LW;
+constexpr int C2_PL = 26 * C2_LW + 2;  // float4 per plane (+2: the 4 planes start on distinct bank groups)
+constexpr int C2_BUF = 4 * C2_PL;      // float4 per exchange buffer (16 channels)
+constexpr int C2_FC = 16;
+constexpr int C2_THREADS = 384, C2_NLOAD = 96;
+constexpr int C2_REG_COMPUTE = 224, C2_REG_IO = 56;
+
+struct Conv2Args {
+  int n_tiles;
+  const int32_t* pix;
+  const float* w;
+  int64_t B, M;
+  int F, N;
+  int b_split;
+  int nsteps;  // hops, 1..4
+  float wscale;
+  const float* in0;     // [B, M, F]
+  float* out[C2_H];     // optional basis of hop s (own pixels), [B, M, F]
+  const float* b_img;   // [F/16][nsteps+1][N*16] K-major no-swizzle images of the (scaled) weight slices
+  const float* bias;    // [N] or NULL
+  int act;
+  float* y;             // [B, M, N]
+};
+
+struct Conv2Ctl {
+  uint64_t in_full[2], in_empty[2], w_full[2], item_done[2], hop_full[2], mma_done[2], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float4 f4_fma(float w, const float4& x, const float4& acc) {
+  return make_float4(fmaf(w, x.x, acc.x), fmaf(w, x.y, acc.y), fmaf(w, x.z, acc.z), fmaf(w, x.w, acc.w));
+}
+__device__ __forceinline__ float4 f4_fms(float w, const float4& x, const float4& acc) {  // w*x - acc
+  return make_float4(fmaf(w, x.x, -acc.x), fmaf(w, x.y, -acc.y), fmaf(w, x.z, -acc.z), fmaf(w, x.w, -acc.w));
+}
+__device__ __forceinline__ float4 f4_scale(float w, const float4& x) {
+  return make_float4(w * x.x, w * x.y, w * x.z, w * x.w);
+}
+__device__ __noinline__ float4 act4(float4 v, int act) {
+  return make_float4(act_apply(v.x, act), act_apply(v.y, act), act_apply(v.z, act), act_apply(v.w, act));
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ptx::smem_u32(dst)), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// stencil direction index of the plan's weight table for (drow, dcol) (lattice.py: SW, W, NW, N, NE, E, SE, S, centre)
+__device__ __forceinline__ constexpr int dir_of(int dr, int dc) {
+  return dr == 0 ? (dc < 0 ? 0 : (dc > 0 ? 4 : 8)) : (dr > 0 ? (dc < 0 ? 1 : (dc == 0 ? 2 : 3)) : (dc > 0 ? 5 : (dc == 0 ? 6 : 7)));
+}
+
+// One hop on the thread's 3x3 block: acc <- (sum_d w_d * neighbour_d(in)) - (HAS_OLD ? acc : 0).
+// `src` points at the thread's own (r = 0, cc = 0) position of the buffer holding `in` of all threads.
+template <bool HAS_OLD, bool HALVE>
+__device__ __forceinline__ void hop_compute(const float4 (&in)[3][3], float4 (&acc)[3][3], const float (&w)[3][3][9],
+                                            const float4* __restrict__ src) {
+  // position offsets of columns -1, 0, 1, 2, 3 relative to the own column-0 position
+  constexpr int CO[5] = {15, 0, 8, 16, 1};
+  float4 top[5], bot[5], lft[3], rgt[3];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) top[k] = src[-C2_LW + CO[k]];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    lft[r] = src[r * C2_LW + 15];
+    rgt[r] = src[r * C2_LW + 1];
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) bot[k] = src[3 * C2_LW + CO[k]];
+  // centre taps (and the -T_{k-2} term), then the taps inside the block, then the perimeter
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc)
+      acc[r][cc] = HAS_OLD ? f4_fms(w[r][cc][8], in[r][cc], acc[r][cc]) : f4_scale(w[r][cc][8], in[r][cc]);
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+        for (int dr = -1; dr <= 1; ++dr)
+#pragma unroll
+          for (int dc = -1; dc <= 1; ++dc) {
+            if (dr == 0 && dc == 0) continue;
+            const int sr = r + dr, sc = cc + dc;
+            const bool inside = sr >= 0 && sr < 3 && sc >= 0 && sc < 3;
+            if (inside != (pass == 0)) continue;
+            const float wv = w[r][cc][dir_of(dr, dc)];
+            if (inside) acc[r][cc] = f4_fma(wv, in[sr][sc], acc[r][cc]);
+            else if (sr < 0) acc[r][cc] = f4_fma(wv, top[sc + 1], acc[r][cc]);
+            else if (sr > 2) acc[r][cc] = f4_fma(wv, bot[sc + 1], acc[r][cc]);
+            else if (sc < 0) acc[r][cc] = f4_fma(wv, lft[sr], acc[r][cc]);
+            else acc[r][cc] = f4_fma(wv, rgt[sr], acc[r][cc]);
+          }
+  if (HALVE) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) acc[r][cc] = f4_scale(0.5f, acc[r][cc]);
+  }
+}
+
+template <bool CHEB>
+__global__ void __launch_bounds__(C2_THREADS, 1) lattice_conv2_kernel(const Conv2Args a) {
+  extern __shared__ __align__(128) uint8_t c2_smem[];
+  float4* const bufs = reinterpret_cast<float4*>(c2_smem);  // S0, S1 (input staging), X0, X1 (hop results)
+  const int N = a.N, nsteps = a.nsteps;
+  const uint32_t img_bytes = (uint32_t)N * C2_FC * 4;                 // one (chunk, hop) weight image
+  const uint32_t wslice_bytes = (uint32_t)(nsteps + 1) * img_bytes;  // all hops of one chunk
+  uint8_t* const wbuf = c2_smem + (size_t)4 * C2_BUF * 16;
+  int32_t* const s_pix = reinterpret_cast<int32_t*>(wbuf + 2 * (size_t)wslice_bytes);
+  Conv2Ctl* const ctl = reinterpret_cast<Conv2Ctl*>(s_pix + C2_P);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_chunks = a.F / C2_FC;
+  const int64_t b_per = (a.B + a.b_split - 1) / a.b_split;
+  const int n_units = a.n_tiles * a.b_split;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&ctl->in_full[i], C2_NLOAD);
+      ptx::mbar_init(&ctl->in_empty[i], 1);
+      ptx::mbar_init(&ctl->w_full[i], 1);
+      ptx::mbar_init(&ctl->item_done[i], 1);
+      ptx::mbar_init(&ctl->hop_full[i], 8);
+      ptx::mbar_init(&ctl->mma_done[i], 1);
+      ptx::mbar_init(&ctl->acc_full[i], 1);
+      ptx::mbar_init(&ctl->acc_empty[i], 8);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) ptx::tmem_alloc(&ctl->tmem_base, 512);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp < 8) {
+    // ================================ compute warps ================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C2_REG_COMPUTE));
+    const int R = warp, q = lane >> 3, cb = lane & 7;
+    const int own0 = q * C2_PL + (3 * R + 1) * C2_LW + cb;  // float4 index of the own (0, 0) position
+    const int FV = a.F / 4, NV16 = N / 16;
+    const bool has_out = a.out[0] != nullptr || a.out[1] != nullptr || a.out[2] != nullptr || a.out[3] != nullptr;
+    float w[3][3][9];
+    float4 A[3][3], Bv[3][3];
+    uint32_t it = 0, g = 0;
+    uint32_t cnt_done[2] = {0, 0};
+    int erow[3] = {-1, -1, -1};
+    bool pend = false;
+    uint32_t pend_g = 0;
+    int64_t pend_b = 0;
+    int pend_rows[3] = {-1, -1, -1};
+
+    auto epilogue = [&]() {
+      const uint32_t set = pend_g & 1;
+      ptx::mbar_wait(&ctl->acc_full[set], (pend_g >> 1) & 1);
+      ptx::tc_fence_after_sync();
+      const int half = R >> 2, Q = R & 3;
+      const int c_lo = half == 0 ? 0 : (NV16 + 1) / 2, c_hi = half == 0 ? (NV16 + 1) / 2 : NV16;
+#pragma unroll 1
+      for (int mt = 0; mt < 3; ++mt) {
+        const int row = pend_rows[mt];
+        float* yrow = a.y + (pend_b * a.M + (row >= 0 ? row : 0)) * (int64_t)N;
+#pragma unroll 1
+        for (int cc = c_lo; cc < c_hi; ++cc) {
+          uint32_t r[16];
+          ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(Q * 32) << 16) + set * 3 * N + (uint32_t)(mt * N + cc * 16), r);
+          ptx::tmem_ld_wait();
+          if (row >= 0) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              float4 o = make_float4(__uint_as_float(r[v * 4]), __uint_as_float(r[v * 4 + 1]), __uint_as_float(r[v * 4 + 2]),
+                                     __uint_as_float(r[v * 4 + 3]));
+              if (a.bias != nullptr) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + cc * 16 + v * 4));
+                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+              }
+              if (a.act != DS_ACT_LINEAR) o = act4(o, a.act);
+              __stcs(reinterpret_cast<float4*>(yrow + cc * 16 + v * 4), o);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&ctl->acc_empty[set]);
+      pend = false;
+    };
+
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      const int tile = unit / a.b_split;
+      const int64_t b_begin = (int64_t)(unit % a.b_split) * b_per;
+      const int64_t b_end = min(a.B, b_begin + b_per);
+      if (b_begin >= b_end) continue;
+      const int32_t* tpix = a.pix + (size_t)tile * C2_P;
+      if (has_out) {  // own-pixel rows of this tile for the basis stores
+        ptx::named_bar_sync(1, 256);
+        for (int p = tid; p < C2_P; p += 256) {
+          const int j = p / C2_LW, c = p % C2_LW;
+          s_pix[p] = (j >= C2_H && j < C2_H + C2_T && c >= C2_H && c < C2_H + C2_T) ? __ldg(tpix + p) : -1;
+        }
+        ptx::named_bar_sync(1, 256);
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          const float* wp = a.w + ((size_t)tile * C2_P + (size_t)(3 * R + r) * C2_LW + 3 * cb + cc) * 9;
+#pragma unroll
+          for (int d = 0; d < 9; ++d) w[r][cc][d] = __ldg(wp + d) * a.wscale;
+        }
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt) {  // accumulator row (mt, TMEM lane) -> lattice position -> row of y
+        const int m = mt * 128 + (R & 3) * 32 + lane;
+        const int j = C2_H + m / C2_LW, p = m % C2_LW, c = 3 * (p & 7) + (p >> 3);
+        erow[mt] = (c >= C2_H && c < C2_H + C2_T) ? __ldg(tpix + j * C2_LW + c) : -1;
+      }
+
+      for (int64_t b = b_begin; b < b_end; ++b) {
+        for (int c = 0; c < n_chunks; ++c) {
+          const uint32_t st = it & 1;
+          const float4* S = bufs + (size_t)st * C2_BUF;
+          float4* X[2] = {bufs + 2 * (size_t)C2_BUF, bufs + 3 * (size_t)C2_BUF};
+          ptx::mbar_wait(&ctl->in_full[st], (it >> 1) & 1);
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) A[r][cc] = S[own0 + r * C2_LW + cc * 8];
+
+          // hop s: in -> acc (register arrays alternate), src buffer -> X[(s-1)&1]
+          auto hop = [&](auto s_tag, const float4(&in)[3][3], float4(&acc)[3][3], const float4* src) {
+            constexpr int s = decltype(s_tag)::value;
+            constexpr int p = (s - 1) & 1;
+            const bool active = (3 * R + 2 >= s) && (3 * R <= C2_LW - 1 - s);
+            if (active) {
+              hop_compute<(CHEB && s >= 2), (CHEB && s == 1)>(in, acc, w, src + own0);
+            }
+            if (cnt_done[p] > 0) ptx::mbar_wait(&ctl->mma_done[p], (cnt_done[p] - 1) & 1);  // UMMAs reading X[p] are done
+            if (active) {
+              float4* dst = X[p] + own0;
+#pragma unroll
+              for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) dst[r * C2_LW + cc * 8] = acc[r][cc];
+            }
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&ctl->hop_full[p]);
+            float* outp = a.out[s - 1];
+            if (outp != nullptr && active) {
+              float4* ob = reinterpret_cast<float4*>(outp + (b * a.M * a.F + c * C2_FC)) + q;
+#pragma unroll
+              for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) {
+                  const int row = s_pix[(3 * R + r) * C2_LW + 3 * cb + cc];
+                  if (row >= 0) __stcs(ob + (int64_t)row * FV, acc[r][cc]);
+                }
+            }
+            ptx::named_bar_sync(1, 256);
+            cnt_done[p]++;
+          };
+
+          hop(std::integral_constant<int, 1>{}, A, Bv, S);
+          if (pend) epilogue();
+          if (nsteps >= 2) hop(std::integral_constant<int, 2>{}, Bv, A, X[0]);
+          if (nsteps >= 3) hop(std::integral_constant<int, 3>{}, A, Bv, X[1]);
+          if (nsteps >= 4) hop(std::integral_constant<int, 4>{}, Bv, A, X[0]);
+
+          if (c == n_chunks - 1) {
+            pend = true;
+            pend_g = g;
+            pend_b = b;
+            pend_rows[0] = erow[0]; pend_rows[1] = erow[1]; pend_rows[2] = erow[2];
+            ++g;
+          }
+          ++it;
+        }
+      }
+    }
+    if (pend) epilogue();
+  } else if (warp == 8) {
+    // ================================ UMMA issuer / weight streamer ================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REG_IO));
+    if (lane == 0) {
+      uint32_t total_items = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int64_t b_begin = (int64_t)(unit % a.b_split) * b_per;
+        const int64_t b_end = min(a.B, b_begin + b_per);
+        if (b_end > b_begin) total_items += (uint32_t)((b_end - b_begin) * n_chunks);
+      }
+      const uint32_t idesc = ptx::make_idesc_tf32(128, N, 0, 0);
+      const uint32_t buf_u32 = ptx::smem_u32(bufs);
+      const uint32_t wbuf_u32 = ptx::smem_u32(wbuf);
+      auto load_w = [&](uint32_t item, int chunk) {
+        const uint32_t wb = item & 1;
+        ptx::mbar_arrive_expect_tx(&ctl->w_full[wb], wslice_bytes);
+        ptx::bulk_load_1d(wbuf + (size_t)wb * wslice_bytes,
+                          reinterpret_cast<const uint8_t*>(a.b_img) + (size_t)chunk * wslice_bytes, wslice_bytes,
+                          &ctl->w_full[wb]);
+      };
+      auto issue = [&](uint32_t a_buf_u32, uint32_t w_u32, int k, uint32_t set, bool first) {
+        const uint32_t a_base = a_buf_u32 + (uint32_t)((C2_H + 1) * C2_LW) * 16;  // plane 0, lattice row 4, position 0
+        const uint32_t b_base = w_u32 + (uint32_t)k * img_bytes;
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {  // K = 8 per UMMA = 2 planes
+            const uint64_t ad = ptx::make_smem_desc(a_base + (uint32_t)(ks * 2 * C2_PL + mt * 128) * 16, C2_PL * 16, 128,
+                                                    ptx::LAYOUT_SWIZZLE_NONE);
+            const uint64_t bd = ptx::make_smem_desc(b_base + (uint32_t)ks * 2 * N * 16, (uint32_t)N * 16, 128,
+                                                    ptx::LAYOUT_SWIZZLE_NONE);
+            ptx::umma_tf32(tmem_base + set * 3 * N + (uint32_t)(mt * N), ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
+          }
+      };
+      uint32_t it = 0, g = 0, ch[2] = {0, 0};
+      if (total_items > 0) load_w(0, 0);
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int64_t b_begin = (int64_t)(unit % a.b_split) * b_per;
+        const int64_t b_end = min(a.B, b_begin + b_per);
+        if (b_begin >= b_end) continue;
+        for (int64_t b = b_begin; b < b_end; ++b) {
+          for (int c = 0; c < n_chunks; ++c) {
+            const uint32_t st = it & 1, set = g & 1;
+            if (c == 0 && g >= 2) ptx::mbar_wait(&ctl->acc_empty[set], ((g >> 1) - 1) & 1);
+            ptx::mbar_wait(&ctl->w_full[st], (it >> 1) & 1);
+            ptx::mbar_wait(&ctl->in_full[st], (it >> 1) & 1);
+            ptx::tc_fence_after_sync();
+            const uint32_t w_u32 = wbuf_u32 + st * wslice_bytes;
+            issue(buf_u32 + st * (uint32_t)(C2_BUF * 16), w_u32, 0, set, c == 0);
+            if (it + 1 < total_items) {  // stream the next chunk's weight slice into the other buffer
+              if (it >= 1) ptx::mbar_wait(&ctl->item_done[(it + 1) & 1], ((it - 1) >> 1) & 1);
+              load_w(it + 1, (c + 1) % n_chunks);
+            }
+            for (int s = 1; s <= nsteps; ++s) {
+              const int p = (s - 1) & 1;
+              ptx::mbar_wait(&ctl->hop_full[p], ch[p] & 1);
+              ch[p]++;
+              ptx::tc_fence_after_sync();
+              issue(buf_u32 + (uint32_t)(2 + p) * (uint32_t)(C2_BUF * 16), w_u32, s, set, false);
+              ptx::umma_commit(&ctl->mma_done[p]);
+              if (s == 1) ptx::umma_commit(&ctl->in_empty[st]);
+            }
+            ptx::umma_commit(&ctl->item_done[st]);
+            if (c == n_chunks - 1) {
+              ptx::umma_commit(&ctl->acc_full[set]);
+              ++g;
+            }
+            ++it;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ input gather warps ================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REG_IO));
+    const int t = tid - 9 * 32;       // 0..95
+    const int g8 = t >> 2, q = t & 3; // in-row position, channel quad
+    const int col = 3 * (g8 & 7) + (g8 >> 3);
+    const int FV = a.F / 4;
+    uint32_t it = 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      const int tile = unit / a.b_split;
+      const int64_t b_begin = (int64_t)(unit % a.b_split) * b_per;
+      const int64_t b_end = min(a.B, b_begin + b_per);
+      if (b_begin >= b_end) continue;
+      int rows[C2_LW];
+#pragma unroll
+      for (int k = 0; k < C2_LW; ++k) rows[k] = __ldg(a.pix + (size_t)tile * C2_P + k * C2_LW + col);
+      for (int64_t b = b_begin; b < b_end; ++b) {
+        for (int c = 0; c < n_chunks; ++c) {
+          const uint32_t st = it & 1;
+          if (it >= 2) ptx::mbar_wait(&ctl->in_empty[st], ((it >> 1) - 1) & 1);
+          float4* dst = bufs + (size_t)st * C2_BUF + q * C2_PL + C2_LW + g8;
+          const float4* src = reinterpret_cast<const float4*>(a.in0 + (b * a.M * a.F + c * C2_FC)) + q;
+#pragma unroll
+          for (int k = 0; k < C2_LW; ++k) {
+            const int row = rows[k];
+            cp_async16(dst + k * C2_LW, row >= 0 ? (const void*)(src + (int64_t)row * FV) : (const void*)a.in0,
+                       row >= 0 ? 16u : 0u);
+          }
+          cp_async_wait_all();
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(&ctl->in_full[st]);
+          ++it;
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// weight images: chunk c, hop k: element (n, kk) at (kk / 4) * (N * 4) + n * 4 + kk % 4,
+// value = tf32_rn( Wsrc[(c*16 + kk) * s_f + k * s_k + n * s_n] )
+__global__ void conv2_prep_b_kernel(const float* __restrict__ W, int64_t s_f, int64_t s_k, int64_t s_n, int n_chunks,
+                                    int K, int N, float* __restrict__ img) {
+  const int64_t per = (int64_t)N * C2_FC;
+  const int64_t total = (int64_t)n_chunks * K * per;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(e % C2_FC);
+    const int n = (int)((e / C2_FC) % N);
+    const int k = (int)((e / per) % K);
+    const int c = (int)(e / (per * K));
+    const float v = W[(int64_t)(c * C2_FC + kk) * s_f + (int64_t)k * s_k + (int64_t)n * s_n];
+    uint32_t u = __float_as_uint(v);
+    uint32_t rr = (u + 0x00000FFFu + ((u >> 13) & 1u)) & 0xFFFFE000u;
+    float hi = __uint_as_float(rr);
+    if (!isfinite(hi)) hi = __uint_as_float(u & 0xFFFFE000u);
+    img[((int64_t)(c * K + k)) * per + (int64_t)(kk / 4) * (N * 4) + n * 4 + (kk % 4)] = hi;
+  }
+}
+
+size_t conv2_smem_bytes(int N, int nsteps) {
+  return (size_t)4 * C2_BUF * 16 + (size_t)2 * (nsteps + 1) * N * C2_FC * 4 + (size_t)C2_P * 4 + sizeof(Conv2Ctl) + 16;
+}
+
+}  // namespace
+
+// Is the register-resident fused kernel available for this call?
+bool lattice_conv2_usable(const LatticeDev& L, int nsteps, int F, int N, int mode) {
+  if (mode != DS_MODE_TF32 || L.n_tiles <= 0) return false;
+  if (L.T != C2_T || L.H != C2_H || L.LW != C2_LW) return false;
+  if (nsteps < 1 || nsteps > C2_H) return false;
+  if (F % 16 != 0 || N % 16 != 0 || N < 16 || N > 64) return false;
+  static const bool disabled = [] { const char* e = getenv("DEEPSPHERE_FUSED_CONV2"); return e && atoi(e) == 0; }();
+  if (disabled) return false;
+  int dev = 0, max_smem = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return false;
+  return (int)conv2_smem_bytes(N, nsteps) <= max_smem;
+}
+
+// y = act( sum_k T_k(L~)(in0) * B_k + bias ) on the regular tiles; out[s-1] (optional) receives T_s(in0) (own pixels).
+// Weights are addressed generically: B_k(f, n) = W[f*s_f + k*s_k + n*s_n].
+int launch_lattice_conv2(const LatticeDev& L, int nsteps, int64_t B, int64_t M, int F, int N, int recursion,
+                         const float* in0, float* const* out, const float* W, int64_t s_f, int64_t s_k, int64_t s_n,
+                         const float* bias, int act, float* y, cudaStream_t st) {
+  const bool cheb = recursion == DS_RECURSION_CHEBYSHEV;
+  const int K = nsteps + 1, n_chunks = F / C2_FC;
+  Conv2Args a;
+  a.n_tiles = L.n_tiles; a.pix = L.pix; a.w = L.w;
+  a.B = B; a.M = M; a.F = F; a.N = N; a.nsteps = nsteps;
+  int split = 1;
+  while ((int64_t)L.n_tiles * split < (int64_t)8 * num_sms() && split < B) split *= 2;
+  a.b_split = (int)std::min<int64_t>(split, B);
+  a.wscale = cheb ? 2.f : 1.f;
+  for (int s = 0; s < C2_H; ++s) a.out[s] = (out != nullptr && s < nsteps) ? out[s] : nullptr;
+  a.in0 = in0; a.bias = bias; a.act = act; a.y = y;
+  float* img = nullptr;
+  const size_t img_elems = (size_t)n_chunks * K * N * C2_FC;
+  DS_CUDA(cudaMallocAsync((void**)&img, img_elems * 4, st));
+  conv2_prep_b_kernel<<<(unsigned)std::min<size_t>((img_elems + 255) / 256, 1024), 256, 0, st>>>(
+      W, s_f, s_k, s_n, n_chunks, K, N, img);
+  g_launches.fetch_add(1);
+  a.b_img = img;
+  const size_t smem = conv2_smem_bytes(N, nsteps);
+  static bool attr_done = false;
+  if (!attr_done) {
+    int dev = 0, max_smem = 0;
+    DS_CUDA(cudaGetDevice(&dev));
+    DS_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    DS_CUDA(cudaFuncSetAttribute(lattice_conv2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    DS_CUDA(cudaFuncSetAttribute(lattice_conv2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    attr_done = true;
+  }
+  const int n_units = a.n_tiles * a.b_split;
+  const int grid = std::min(n_units, num_sms());
+  if (cheb) lattice_conv2_kernel<true><<<grid, C2_THREADS, smem, st>>>(a);
+  else lattice_conv2_kernel<false><<<grid, C2_THREADS, smem, st>>>(a);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(img, st);
+  g_launches.fetch_add(1);
+  if (e != cudaSuccess) return fail("lattice_conv2_kernel launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace ds

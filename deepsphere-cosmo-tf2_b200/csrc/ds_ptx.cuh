@@ -42,6 +42,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // bounded wait: ~seconds of polling, then trap (surfaces as a launch failure, never a hang)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
   for (uint32_t i = 0; i < (1u << 28); ++i)
     if (mbar_try_wait(bar, parity)) return;
   printf("deepsphere_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);

@@ -112,7 +112,9 @@ class _GraphConvBase(Model):
             return None
         Lt = sparse.csr_matrix((self._L_values, (self._L_indices[:, 0], self._L_indices[:, 1])), shape=(M, M))
         try:
-            return lattice.make_payload(Lt, nside, indices, self.K - 1)
+            # K <= 5: always a 4-ring halo (24 x 24 lattice) - the geometry of the register-resident fused kernel
+            # (ds_lattice_conv2.cu); the kernels run K - 1 <= 4 hops on it
+            return lattice.make_payload(Lt, nside, indices, max(self.K - 1, 4))
         except Exception as exc:  # never let the optional fast path break the layer
             logger.warning(f"lattice plan construction failed ({exc!r}); using the generic kernels")
             return None
