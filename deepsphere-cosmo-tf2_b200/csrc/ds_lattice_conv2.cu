@@ -39,11 +39,13 @@ namespace ds {
 namespace {
 
 constexpr int C2_LW = 24, C2_T = 16, C2_H = 4, C2_P = C2_LW * C2_LW;
-constexpr int C2_PL = 26 * C2_LW + 2;  // float4 per plane (+2: the 4 planes start on distinct bank groups)
-constexpr int C2_BUF = 4 * C2_PL;      // float4 per exchange buffer (16 channels)
-constexpr int C2_FC = 16;
-constexpr int C2_THREADS = 384, C2_NLOAD = 96;
-constexpr int C2_REG_COMPUTE = 224, C2_REG_IO = 56;
+constexpr int C2_FC = 8;               // channels per work item = one UMMA K step (tf32: K = 8)
+constexpr int C2_NQ = C2_FC / 4;       // float4 planes per buffer
+constexpr int C2_PL = 26 * C2_LW + 4;  // float4 per plane (+4: the two planes start on complementary bank groups)
+constexpr int C2_BUF = C2_NQ * C2_PL;  // float4 per exchange buffer
+constexpr int C2_THREADS = 256, C2_NCOMP = 128, C2_NLOAD = 96;
+constexpr int C2_REG_COMPUTE = 208, C2_REG_IO = 48;  // 128 * 208 + 128 * 48 = 256 * 128 registers per CTA
+constexpr int C2_TMEM_COLS = 256;
 
 struct Conv2Args {
   int n_tiles;
@@ -54,24 +56,69 @@ struct Conv2Args {
   int b_split;
   int nsteps;  // hops, 1..4
   float wscale;
+  long long* dbg;           // optional timeline probe [item < 16][hop 0..4][8 slots] of clock64 (block 0)
+  int sleep_mma, sleep_ld;  // ns of back-off between polls of the issuer / gather roles (0: plain spin)
   const float* in0;     // [B, M, F]
   float* out[C2_H];     // optional basis of hop s (own pixels), [B, M, F]
-  const float* b_img;   // [F/16][nsteps+1][N*16] K-major no-swizzle images of the (scaled) weight slices
+  const float* b_img;   // [F/8][nsteps+1][N*8] K-major no-swizzle images of the weight slices
   const float* bias;    // [N] or NULL
   int act;
   float* y;             // [B, M, N]
 };
 
 struct Conv2Ctl {
-  uint64_t in_full[2], in_empty[2], w_full[2], item_done[2], hop_full[2], mma_done[2], acc_full[2], acc_empty[2];
+  uint64_t in_full[2], in_empty[2], w_full[2], item_done[2], hop_full[2], mma_done[2], acc_full, acc_empty;
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ float4 f4_fma(float w, const float4& x, const float4& acc) {
-  return make_float4(fmaf(w, x.x, acc.x), fmaf(w, x.y, acc.y), fmaf(w, x.z, acc.z), fmaf(w, x.w, acc.w));
+// Register-bank-aware arithmetic.  A float4 that goes through LDS.128 / STS.128 sits in 4 consecutive, 4-aligned
+// registers, so member i of EVERY such vector has the same register parity; a scalar FFMA reading `in.x` and
+// `acc.x` takes two reads from one of the two register banks and issues at half rate (measured: 2.1 clk / FFMA,
+// and ptxas re-orders the taps so the weight rarely sits in the operand reuse cache).  The packed FFMA2 form reads
+// aligned register PAIRS (one register from each bank per operand), halves the issued instructions and cannot be
+// split by the scheduler; the weight is broadcast into a register pair.
+#ifndef C2_FFMA2
+#define C2_FFMA2 1
+#endif
+// ROT = 0: `x` natural channel order, `acc` rotated by one (x.x <-> acc.w, x.y <-> acc.x, ...); ROT = 1: `x` rotated,
+// `acc` natural; ROT = 2: both natural (used with FFMA2).
+__host__ __device__ constexpr int rot_of_hop(int s) { return C2_FFMA2 ? 2 : ((s - 1) & 1); }
+__host__ __device__ constexpr bool hop_is_rotated(int s) { return !C2_FFMA2 && (s & 1); }
+template <int ROT>
+__device__ __forceinline__ void f4_fma(float w, const float4& x, float4& acc) {
+  if (ROT == 2) {
+    const float2 ww = make_float2(w, w);
+    const float2 lo = __ffma2_rn(ww, make_float2(x.x, x.y), make_float2(acc.x, acc.y));
+    const float2 hi = __ffma2_rn(ww, make_float2(x.z, x.w), make_float2(acc.z, acc.w));
+    acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+  } else if (ROT == 0) {
+    acc.w = fmaf(w, x.x, acc.w); acc.x = fmaf(w, x.y, acc.x); acc.y = fmaf(w, x.z, acc.y); acc.z = fmaf(w, x.w, acc.z);
+  } else {
+    acc.y = fmaf(w, x.x, acc.y); acc.z = fmaf(w, x.y, acc.z); acc.w = fmaf(w, x.z, acc.w); acc.x = fmaf(w, x.w, acc.x);
+  }
 }
-__device__ __forceinline__ float4 f4_fms(float w, const float4& x, const float4& acc) {  // w*x - acc
-  return make_float4(fmaf(w, x.x, -acc.x), fmaf(w, x.y, -acc.y), fmaf(w, x.z, -acc.z), fmaf(w, x.w, -acc.w));
+template <int ROT>
+__device__ __forceinline__ void f4_fms(float w, const float4& x, float4& acc) {  // acc = w*x - acc
+  if (ROT == 2) {
+    const float2 ww = make_float2(w, w);
+    const float2 lo = __ffma2_rn(ww, make_float2(x.x, x.y), make_float2(-acc.x, -acc.y));
+    const float2 hi = __ffma2_rn(ww, make_float2(x.z, x.w), make_float2(-acc.z, -acc.w));
+    acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+  } else if (ROT == 0) {
+    acc.w = fmaf(w, x.x, -acc.w); acc.x = fmaf(w, x.y, -acc.x); acc.y = fmaf(w, x.z, -acc.y); acc.z = fmaf(w, x.w, -acc.z);
+  } else {
+    acc.y = fmaf(w, x.x, -acc.y); acc.z = fmaf(w, x.y, -acc.z); acc.w = fmaf(w, x.z, -acc.w); acc.x = fmaf(w, x.w, -acc.x);
+  }
+}
+template <int ROT>
+__device__ __forceinline__ void f4_mul(float w, const float4& x, float4& acc) {  // acc = w*x
+  if (ROT == 2) {
+    acc = make_float4(w * x.x, w * x.y, w * x.z, w * x.w);
+  } else if (ROT == 0) {
+    acc.w = w * x.x; acc.x = w * x.y; acc.y = w * x.z; acc.z = w * x.w;
+  } else {
+    acc.y = w * x.x; acc.z = w * x.y; acc.w = w * x.z; acc.x = w * x.w;
+  }
 }
 __device__ __forceinline__ float4 f4_scale(float w, const float4& x) {
   return make_float4(w * x.x, w * x.y, w * x.z, w * x.w);
@@ -90,9 +137,9 @@ __device__ __forceinline__ constexpr int dir_of(int dr, int dc) {
   return dr == 0 ? (dc < 0 ? 0 : (dc > 0 ? 4 : 8)) : (dr > 0 ? (dc < 0 ? 1 : (dc == 0 ? 2 : 3)) : (dc > 0 ? 5 : (dc == 0 ? 6 : 7)));
 }
 
-// One hop on the thread's 3x3 block: acc <- (sum_d w_d * neighbour_d(in)) - (HAS_OLD ? acc : 0).
+// One hop on the thread's 3x3 block: acc <- (sum_d w_d * neighbour_d(in)) - (HAS_OLD ? acc : 0), halved if HALVE.
 // `src` points at the thread's own (r = 0, cc = 0) position of the buffer holding `in` of all threads.
-template <bool HAS_OLD, bool HALVE>
+template <bool HAS_OLD, bool HALVE, int ROT>
 __device__ __forceinline__ void hop_compute(const float4 (&in)[3][3], float4 (&acc)[3][3], const float (&w)[3][3][9],
                                             const float4* __restrict__ src) {
   // position offsets of columns -1, 0, 1, 2, 3 relative to the own column-0 position
@@ -112,27 +159,30 @@ __device__ __forceinline__ void hop_compute(const float4 (&in)[3][3], float4 (&a
   for (int r = 0; r < 3; ++r)
 #pragma unroll
     for (int cc = 0; cc < 3; ++cc)
-      acc[r][cc] = HAS_OLD ? f4_fms(w[r][cc][8], in[r][cc], acc[r][cc]) : f4_scale(w[r][cc][8], in[r][cc]);
+      if (HAS_OLD) f4_fms<ROT>(w[r][cc][8], in[r][cc], acc[r][cc]);
+      else f4_mul<ROT>(w[r][cc][8], in[r][cc], acc[r][cc]);
+  // tap order: direction outer, pixel inner - consecutive 4-FFMA groups (one weight, 4 channels: the weight sits
+  // in the operand reuse cache for 3 of them) are independent, so the scheduler has no reason to split them
 #pragma unroll
   for (int pass = 0; pass < 2; ++pass)
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+    for (int dr = -1; dr <= 1; ++dr)
 #pragma unroll
-      for (int cc = 0; cc < 3; ++cc)
+      for (int dc = -1; dc <= 1; ++dc)
 #pragma unroll
-        for (int dr = -1; dr <= 1; ++dr)
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-          for (int dc = -1; dc <= 1; ++dc) {
+          for (int cc = 0; cc < 3; ++cc) {
             if (dr == 0 && dc == 0) continue;
             const int sr = r + dr, sc = cc + dc;
             const bool inside = sr >= 0 && sr < 3 && sc >= 0 && sc < 3;
             if (inside != (pass == 0)) continue;
             const float wv = w[r][cc][dir_of(dr, dc)];
-            if (inside) acc[r][cc] = f4_fma(wv, in[sr][sc], acc[r][cc]);
-            else if (sr < 0) acc[r][cc] = f4_fma(wv, top[sc + 1], acc[r][cc]);
-            else if (sr > 2) acc[r][cc] = f4_fma(wv, bot[sc + 1], acc[r][cc]);
-            else if (sc < 0) acc[r][cc] = f4_fma(wv, lft[sr], acc[r][cc]);
-            else acc[r][cc] = f4_fma(wv, rgt[sr], acc[r][cc]);
+            if (inside) f4_fma<ROT>(wv, in[sr][sc], acc[r][cc]);
+            else if (sr < 0) f4_fma<ROT>(wv, top[sc + 1], acc[r][cc]);
+            else if (sr > 2) f4_fma<ROT>(wv, bot[sc + 1], acc[r][cc]);
+            else if (sc < 0) f4_fma<ROT>(wv, lft[sr], acc[r][cc]);
+            else f4_fma<ROT>(wv, rgt[sr], acc[r][cc]);
           }
   if (HALVE) {
 #pragma unroll
@@ -143,7 +193,7 @@ __device__ __forceinline__ void hop_compute(const float4 (&in)[3][3], float4 (&a
 }
 
 template <bool CHEB>
-__global__ void __launch_bounds__(C2_THREADS, 1) lattice_conv2_kernel(const Conv2Args a) {
+__global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv2Args a) {
   extern __shared__ __align__(128) uint8_t c2_smem[];
   float4* const bufs = reinterpret_cast<float4*>(c2_smem);  // S0, S1 (input staging), X0, X1 (hop results)
   const int N = a.N, nsteps = a.nsteps;
@@ -164,23 +214,23 @@ __global__ void __launch_bounds__(C2_THREADS, 1) lattice_conv2_kernel(const Conv
       ptx::mbar_init(&ctl->in_empty[i], 1);
       ptx::mbar_init(&ctl->w_full[i], 1);
       ptx::mbar_init(&ctl->item_done[i], 1);
-      ptx::mbar_init(&ctl->hop_full[i], 8);
+      ptx::mbar_init(&ctl->hop_full[i], 4);
       ptx::mbar_init(&ctl->mma_done[i], 1);
-      ptx::mbar_init(&ctl->acc_full[i], 1);
-      ptx::mbar_init(&ctl->acc_empty[i], 8);
     }
+    ptx::mbar_init(&ctl->acc_full, 1);
+    ptx::mbar_init(&ctl->acc_empty, 4);
     ptx::fence_mbar_init();
   }
-  if (warp == 8) ptx::tmem_alloc(&ctl->tmem_base, 512);
+  if (warp == 4) ptx::tmem_alloc(&ctl->tmem_base, C2_TMEM_COLS);
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = ctl->tmem_base;
 
-  if (warp < 8) {
+  if (warp < 4) {
     // ================================ compute warps ================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C2_REG_COMPUTE));
-    const int R = warp, q = lane >> 3, cb = lane & 7;
+    const int R = 2 * warp + (lane >> 4), q = (lane >> 3) & 1, cb = lane & 7;
     const int own0 = q * C2_PL + (3 * R + 1) * C2_LW + cb;  // float4 index of the own (0, 0) position
     const int FV = a.F / 4, NV16 = N / 16;
     const bool has_out = a.out[0] != nullptr || a.out[1] != nullptr || a.out[2] != nullptr || a.out[3] != nullptr;
@@ -194,20 +244,18 @@ __global__ void __launch_bounds__(C2_THREADS, 1) lattice_conv2_kernel(const Conv
     int64_t pend_b = 0;
     int pend_rows[3] = {-1, -1, -1};
 
+    // drain the accumulators of group pend_g: TMEM -> bias/activation -> y (own pixels of the tile)
     auto epilogue = [&]() {
-      const uint32_t set = pend_g & 1;
-      ptx::mbar_wait(&ctl->acc_full[set], (pend_g >> 1) & 1);
+      ptx::mbar_wait(&ctl->acc_full, pend_g & 1);
       ptx::tc_fence_after_sync();
-      const int half = R >> 2, Q = R & 3;
-      const int c_lo = half == 0 ? 0 : (NV16 + 1) / 2, c_hi = half == 0 ? (NV16 + 1) / 2 : NV16;
 #pragma unroll 1
       for (int mt = 0; mt < 3; ++mt) {
         const int row = pend_rows[mt];
         float* yrow = a.y + (pend_b * a.M + (row >= 0 ? row : 0)) * (int64_t)N;
 #pragma unroll 1
-        for (int cc = c_lo; cc < c_hi; ++cc) {
+        for (int cc = 0; cc < NV16; ++cc) {
           uint32_t r[16];
-          ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(Q * 32) << 16) + set * 3 * N + (uint32_t)(mt * N + cc * 16), r);
+          ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * N + cc * 16), r);
           ptx::tmem_ld_wait();
           if (row >= 0) {
 #pragma unroll
@@ -226,7 +274,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) lattice_conv2_kernel(const Conv
       }
       ptx::tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&ctl->acc_empty[set]);
+      if (lane == 0) ptx::mbar_arrive(&ctl->acc_empty);
       pend = false;
     };
 
@@ -237,12 +285,12 @@ __global__ void __launch_bounds__(C2_THREADS, 1) lattice_conv2_kernel(const Conv
       if (b_begin >= b_end) continue;
       const int32_t* tpix = a.pix + (size_t)tile * C2_P;
       if (has_out) {  // own-pixel rows of this tile for the basis stores
-        ptx::named_bar_sync(1, 256);
-        for (int p = tid; p < C2_P; p += 256) {
+        ptx::named_bar_sync(1, C2_NCOMP);
+        for (int p = tid; p < C2_P; p += C2_NCOMP) {
           const int j = p / C2_LW, c = p % C2_LW;
           s_pix[p] = (j >= C2_H && j < C2_H + C2_T && c >= C2_H && c < C2_H + C2_T) ? __ldg(tpix + p) : -1;
         }
-        ptx::named_bar_sync(1, 256);
+        ptx::named_bar_sync(1, C2_NCOMP);
       }
 #pragma unroll
       for (int r = 0; r < 3; ++r)
@@ -250,11 +298,14 @@ __global__ void __launch_bounds__(C2_THREADS, 1) lattice_conv2_kernel(const Conv
         for (int cc = 0; cc < 3; ++cc) {
           const float* wp = a.w + ((size_t)tile * C2_P + (size_t)(3 * R + r) * C2_LW + 3 * cb + cc) * 9;
 #pragma unroll
-          for (int d = 0; d < 9; ++d) w[r][cc][d] = __ldg(wp + d) * a.wscale;
+          for (int d = 0; d < 9; ++d) {
+            // volatile: keeps the scaled weight in its register (ptxas otherwise re-multiplies at every use)
+            asm volatile("mul.rn.f32 %0, %1, %2;" : "=f"(w[r][cc][d]) : "f"(__ldg(wp + d)), "f"(a.wscale));
+          }
         }
 #pragma unroll
       for (int mt = 0; mt < 3; ++mt) {  // accumulator row (mt, TMEM lane) -> lattice position -> row of y
-        const int m = mt * 128 + (R & 3) * 32 + lane;
+        const int m = mt * 128 + warp * 32 + lane;
         const int j = C2_H + m / C2_LW, p = m % C2_LW, c = 3 * (p & 7) + (p >> 3);
         erow[mt] = (c >= C2_H && c < C2_H + C2_T) ? __ldg(tpix + j * C2_LW + c) : -1;
       }
@@ -264,43 +315,57 @@ __global__ void __launch_bounds__(C2_THREADS, 1) lattice_conv2_kernel(const Conv
           const uint32_t st = it & 1;
           const float4* S = bufs + (size_t)st * C2_BUF;
           float4* X[2] = {bufs + 2 * (size_t)C2_BUF, bufs + 3 * (size_t)C2_BUF};
+          if (a.dbg != nullptr && blockIdx.x == 0 && it < 16 && tid == 0) a.dbg[((size_t)(it & 15) * 5) * 8 + 0] = clock64();
           ptx::mbar_wait(&ctl->in_full[st], (it >> 1) & 1);
+          if (a.dbg != nullptr && blockIdx.x == 0 && it < 16 && tid == 0) a.dbg[((size_t)(it & 15) * 5) * 8 + 1] = clock64();
 #pragma unroll
           for (int r = 0; r < 3; ++r)
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc) A[r][cc] = S[own0 + r * C2_LW + cc * 8];
 
-          // hop s: in -> acc (register arrays alternate), src buffer -> X[(s-1)&1]
+          // hop s: in -> acc (the register arrays alternate), src buffer -> X[(s-1)&1].  Every thread computes its
+          // whole block on every hop: positions outside the shrinking valid region hold don't-care values that
+          // never reach a valid output (a valid output only reads valid inputs).
+          // hop s: in -> acc (the register arrays alternate), src buffer -> X[(s-1)&1].  Every thread computes its
+          // whole block on every hop: positions outside the shrinking valid region hold don't-care values that
+          // never reach a valid output (a valid output only reads valid inputs).
+          // (st.async + mbarrier complete_tx instead of STS + proxy fence + bar.sync was measured: the async-proxy
+          // store path sustains only ~20 B/clk, 3x slower than this.)
           auto hop = [&](auto s_tag, const float4(&in)[3][3], float4(&acc)[3][3], const float4* src) {
             constexpr int s = decltype(s_tag)::value;
             constexpr int p = (s - 1) & 1;
-            const bool active = (3 * R + 2 >= s) && (3 * R <= C2_LW - 1 - s);
-            if (active) {
-              hop_compute<(CHEB && s >= 2), (CHEB && s == 1)>(in, acc, w, src + own0);
-            }
-            if (cnt_done[p] > 0) ptx::mbar_wait(&ctl->mma_done[p], (cnt_done[p] - 1) & 1);  // UMMAs reading X[p] are done
-            if (active) {
-              float4* dst = X[p] + own0;
+            const bool probe = a.dbg != nullptr && blockIdx.x == 0 && it < 16 && tid == 0;
+            long long* pd = a.dbg + ((size_t)(it & 15) * 5 + s) * 8;
+            if (probe) pd[0] = clock64();
+            // the UMMAs that read X[p] two hops ago: probe now, consume after the arithmetic (hides the round trip)
+            const bool mma_ok = cnt_done[p] == 0 || ptx::mbar_test_wait(&ctl->mma_done[p], (cnt_done[p] - 1) & 1);
+            hop_compute<(CHEB && s >= 2), (CHEB && s == 1), rot_of_hop(s)>(in, acc, w, src + own0);
+            if (probe) pd[1] = clock64();
+            if (!mma_ok) ptx::mbar_wait(&ctl->mma_done[p], (cnt_done[p] - 1) & 1);
+            if (probe) pd[2] = clock64();
+            float4* dst = X[p] + own0;
 #pragma unroll
-              for (int r = 0; r < 3; ++r)
+            for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int cc = 0; cc < 3; ++cc) dst[r * C2_LW + cc * 8] = acc[r][cc];
-            }
+              for (int cc = 0; cc < 3; ++cc) dst[r * C2_LW + cc * 8] = acc[r][cc];
             ptx::fence_proxy_async_smem();
+            if (probe) pd[3] = clock64();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&ctl->hop_full[p]);
             float* outp = a.out[s - 1];
-            if (outp != nullptr && active) {
+            if (outp != nullptr) {
               float4* ob = reinterpret_cast<float4*>(outp + (b * a.M * a.F + c * C2_FC)) + q;
 #pragma unroll
               for (int r = 0; r < 3; ++r)
 #pragma unroll
                 for (int cc = 0; cc < 3; ++cc) {
                   const int row = s_pix[(3 * R + r) * C2_LW + 3 * cb + cc];
-                  if (row >= 0) __stcs(ob + (int64_t)row * FV, acc[r][cc]);
+                  const float4 v = hop_is_rotated(s) ? make_float4(acc[r][cc].w, acc[r][cc].x, acc[r][cc].y, acc[r][cc].z) : acc[r][cc];
+                  if (row >= 0) __stcs(ob + (int64_t)row * FV, v);
                 }
             }
-            ptx::named_bar_sync(1, 256);
+            ptx::named_bar_sync(1, C2_NCOMP);
+            if (probe) pd[4] = clock64();
             cnt_done[p]++;
           };
 
@@ -322,7 +387,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) lattice_conv2_kernel(const Conv
       }
     }
     if (pend) epilogue();
-  } else if (warp == 8) {
+  } else if (warp == 4) {
     // ================================ UMMA issuer / weight streamer ================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REG_IO));
     if (lane == 0) {
@@ -342,19 +407,17 @@ __global__ void __launch_bounds__(C2_THREADS, 1) lattice_conv2_kernel(const Conv
                           reinterpret_cast<const uint8_t*>(a.b_img) + (size_t)chunk * wslice_bytes, wslice_bytes,
                           &ctl->w_full[wb]);
       };
-      auto issue = [&](uint32_t a_buf_u32, uint32_t w_u32, int k, uint32_t set, bool first) {
+      // A = positions of lattice rows 4..19 (3 M-tiles of 128) x the item's 8 channels (one K step = 2 planes)
+      auto issue = [&](uint32_t a_buf_u32, uint32_t w_u32, int k, bool first) {
         const uint32_t a_base = a_buf_u32 + (uint32_t)((C2_H + 1) * C2_LW) * 16;  // plane 0, lattice row 4, position 0
-        const uint32_t b_base = w_u32 + (uint32_t)k * img_bytes;
+        const uint64_t bd = ptx::make_smem_desc(w_u32 + (uint32_t)k * img_bytes, (uint32_t)N * 16, 128,
+                                                ptx::LAYOUT_SWIZZLE_NONE);
 #pragma unroll
-        for (int mt = 0; mt < 3; ++mt)
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {  // K = 8 per UMMA = 2 planes
-            const uint64_t ad = ptx::make_smem_desc(a_base + (uint32_t)(ks * 2 * C2_PL + mt * 128) * 16, C2_PL * 16, 128,
-                                                    ptx::LAYOUT_SWIZZLE_NONE);
-            const uint64_t bd = ptx::make_smem_desc(b_base + (uint32_t)ks * 2 * N * 16, (uint32_t)N * 16, 128,
-                                                    ptx::LAYOUT_SWIZZLE_NONE);
-            ptx::umma_tf32(tmem_base + set * 3 * N + (uint32_t)(mt * N), ad, bd, idesc, (first && ks == 0) ? 0u : 1u);
-          }
+        for (int mt = 0; mt < 3; ++mt) {
+          const uint64_t ad = ptx::make_smem_desc(a_base + (uint32_t)(mt * 128) * 16, C2_PL * 16, 128,
+                                                  ptx::LAYOUT_SWIZZLE_NONE);
+          ptx::umma_tf32(tmem_base + (uint32_t)(mt * N), ad, bd, idesc, first ? 0u : 1u);
+        }
       };
       uint32_t it = 0, g = 0, ch[2] = {0, 0};
       if (total_items > 0) load_w(0, 0);
@@ -364,29 +427,37 @@ __global__ void __launch_bounds__(C2_THREADS, 1) lattice_conv2_kernel(const Conv
         if (b_begin >= b_end) continue;
         for (int64_t b = b_begin; b < b_end; ++b) {
           for (int c = 0; c < n_chunks; ++c) {
-            const uint32_t st = it & 1, set = g & 1;
-            if (c == 0 && g >= 2) ptx::mbar_wait(&ctl->acc_empty[set], ((g >> 1) - 1) & 1);
-            ptx::mbar_wait(&ctl->w_full[st], (it >> 1) & 1);
-            ptx::mbar_wait(&ctl->in_full[st], (it >> 1) & 1);
+            const uint32_t st = it & 1;
+            if (c == 0 && g >= 1) ptx::mbar_wait_backoff(&ctl->acc_empty, (g - 1) & 1, (uint32_t)a.sleep_mma);  // previous group drained
+            ptx::mbar_wait_backoff(&ctl->w_full[st], (it >> 1) & 1, (uint32_t)a.sleep_mma);
+            ptx::mbar_wait_backoff(&ctl->in_full[st], (it >> 1) & 1, (uint32_t)a.sleep_mma);
             ptx::tc_fence_after_sync();
             const uint32_t w_u32 = wbuf_u32 + st * wslice_bytes;
-            issue(buf_u32 + st * (uint32_t)(C2_BUF * 16), w_u32, 0, set, c == 0);
+            issue(buf_u32 + st * (uint32_t)(C2_BUF * 16), w_u32, 0, c == 0);
             if (it + 1 < total_items) {  // stream the next chunk's weight slice into the other buffer
-              if (it >= 1) ptx::mbar_wait(&ctl->item_done[(it + 1) & 1], ((it - 1) >> 1) & 1);
+              if (it >= 1) ptx::mbar_wait_backoff(&ctl->item_done[(it + 1) & 1], ((it - 1) >> 1) & 1, (uint32_t)a.sleep_mma);
               load_w(it + 1, (c + 1) % n_chunks);
             }
             for (int s = 1; s <= nsteps; ++s) {
               const int p = (s - 1) & 1;
-              ptx::mbar_wait(&ctl->hop_full[p], ch[p] & 1);
+              ptx::mbar_wait_backoff(&ctl->hop_full[p], ch[p] & 1, (uint32_t)a.sleep_mma);
+              const bool probe = a.dbg != nullptr && blockIdx.x == 0 && it < 16;
+              long long* pd = a.dbg + ((size_t)(it & 15) * 5 + s) * 8;
+              if (probe) pd[5] = clock64();
               ch[p]++;
               ptx::tc_fence_after_sync();
-              issue(buf_u32 + (uint32_t)(2 + p) * (uint32_t)(C2_BUF * 16), w_u32, s, set, false);
+              issue(buf_u32 + (uint32_t)(2 + p) * (uint32_t)(C2_BUF * 16), w_u32, s, false);
               ptx::umma_commit(&ctl->mma_done[p]);
+              if (probe) pd[6] = clock64();
+              if (probe && s == nsteps) {  // how long until this hop's UMMAs are complete
+                ptx::mbar_wait(&ctl->mma_done[p], (ch[p] - 1) & 1);
+                pd[7] = clock64();
+              }
               if (s == 1) ptx::umma_commit(&ctl->in_empty[st]);
             }
             ptx::umma_commit(&ctl->item_done[st]);
             if (c == n_chunks - 1) {
-              ptx::umma_commit(&ctl->acc_full[set]);
+              ptx::umma_commit(&ctl->acc_full);
               ++g;
             }
             ++it;
@@ -398,9 +469,10 @@ __global__ void __launch_bounds__(C2_THREADS, 1) lattice_conv2_kernel(const Conv
   } else {
     // ================================ input gather warps ================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REG_IO));
-    const int t = tid - 9 * 32;       // 0..95
-    const int g8 = t >> 2, q = t & 3; // in-row position, channel quad
-    const int col = 3 * (g8 & 7) + (g8 >> 3);
+    const int t = tid - 5 * 32;           // 0..95
+    const int q = t & 1, pl0 = t >> 1;    // channel quad; position within a pair of lattice rows (0..47)
+    const int inpos = pl0 % C2_LW, r0 = pl0 / C2_LW;
+    const int col = 3 * (inpos & 7) + (inpos >> 3);
     const int FV = a.F / 4;
     uint32_t it = 0;
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -408,19 +480,19 @@ __global__ void __launch_bounds__(C2_THREADS, 1) lattice_conv2_kernel(const Conv
       const int64_t b_begin = (int64_t)(unit % a.b_split) * b_per;
       const int64_t b_end = min(a.B, b_begin + b_per);
       if (b_begin >= b_end) continue;
-      int rows[C2_LW];
+      int rows[C2_LW / 2];
 #pragma unroll
-      for (int k = 0; k < C2_LW; ++k) rows[k] = __ldg(a.pix + (size_t)tile * C2_P + k * C2_LW + col);
+      for (int k = 0; k < C2_LW / 2; ++k) rows[k] = __ldg(a.pix + (size_t)tile * C2_P + (2 * k + r0) * C2_LW + col);
       for (int64_t b = b_begin; b < b_end; ++b) {
         for (int c = 0; c < n_chunks; ++c) {
           const uint32_t st = it & 1;
-          if (it >= 2) ptx::mbar_wait(&ctl->in_empty[st], ((it >> 1) - 1) & 1);
-          float4* dst = bufs + (size_t)st * C2_BUF + q * C2_PL + C2_LW + g8;
+          if (it >= 2) ptx::mbar_wait_backoff(&ctl->in_empty[st], ((it >> 1) - 1) & 1, (uint32_t)a.sleep_ld);
+          float4* dst = bufs + (size_t)st * C2_BUF + q * C2_PL + (r0 + 1) * C2_LW + inpos;
           const float4* src = reinterpret_cast<const float4*>(a.in0 + (b * a.M * a.F + c * C2_FC)) + q;
 #pragma unroll
-          for (int k = 0; k < C2_LW; ++k) {
+          for (int k = 0; k < C2_LW / 2; ++k) {
             const int row = rows[k];
-            cp_async16(dst + k * C2_LW, row >= 0 ? (const void*)(src + (int64_t)row * FV) : (const void*)a.in0,
+            cp_async16(dst + 2 * k * C2_LW, row >= 0 ? (const void*)(src + (int64_t)row * FV) : (const void*)a.in0,
                        row >= 0 ? 16u : 0u);
           }
           cp_async_wait_all();
@@ -433,9 +505,9 @@ __global__ void __launch_bounds__(C2_THREADS, 1) lattice_conv2_kernel(const Conv
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 4) {
     ptx::tc_fence_after_sync();
-    ptx::tmem_dealloc(tmem_base, 512);
+    ptx::tmem_dealloc(tmem_base, C2_TMEM_COLS);
   }
 }
 
@@ -450,7 +522,9 @@ __global__ void conv2_prep_b_kernel(const float* __restrict__ W, int64_t s_f, in
     const int n = (int)((e / C2_FC) % N);
     const int k = (int)((e / per) % K);
     const int c = (int)(e / (per * K));
-    const float v = W[(int64_t)(c * C2_FC + kk) * s_f + (int64_t)k * s_k + (int64_t)n * s_n];
+    // odd hops leave T_k in shared memory with each channel quad rotated by one (c1, c2, c3, c0)
+    const int ksrc = hop_is_rotated(k) ? ((kk & ~3) | ((kk + 1) & 3)) : kk;
+    const float v = W[(int64_t)(c * C2_FC + ksrc) * s_f + (int64_t)k * s_k + (int64_t)n * s_n];
     uint32_t u = __float_as_uint(v);
     uint32_t rr = (u + 0x00000FFFu + ((u >> 13) & 1u)) & 0xFFFFE000u;
     float hi = __uint_as_float(rr);
@@ -470,7 +544,7 @@ bool lattice_conv2_usable(const LatticeDev& L, int nsteps, int F, int N, int mod
   if (mode != DS_MODE_TF32 || L.n_tiles <= 0) return false;
   if (L.T != C2_T || L.H != C2_H || L.LW != C2_LW) return false;
   if (nsteps < 1 || nsteps > C2_H) return false;
-  if (F % 16 != 0 || N % 16 != 0 || N < 16 || N > 64) return false;
+  if (F % C2_FC != 0 || N % 16 != 0 || N < 16 || 3 * N > C2_TMEM_COLS) return false;
   static const bool disabled = [] { const char* e = getenv("DEEPSPHERE_FUSED_CONV2"); return e && atoi(e) == 0; }();
   if (disabled) return false;
   int dev = 0, max_smem = 0;
@@ -489,10 +563,19 @@ int launch_lattice_conv2(const LatticeDev& L, int nsteps, int64_t B, int64_t M, 
   Conv2Args a;
   a.n_tiles = L.n_tiles; a.pix = L.pix; a.w = L.w;
   a.B = B; a.M = M; a.F = F; a.N = N; a.nsteps = nsteps;
-  int split = 1;
-  while ((int64_t)L.n_tiles * split < (int64_t)8 * num_sms() && split < B) split *= 2;
+  int split = 1;  // persistent CTAs, 2 per SM: enough units for a balanced tail
+  while ((int64_t)L.n_tiles * split < (int64_t)32 * num_sms() && split < B) split *= 2;
   a.b_split = (int)std::min<int64_t>(split, B);
   a.wscale = cheb ? 2.f : 1.f;
+  static const int sleep_mma = [] { const char* e = getenv("DEEPSPHERE_CONV2_SLEEP_MMA"); return e ? atoi(e) : 0; }();
+  static const int sleep_ld = [] { const char* e = getenv("DEEPSPHERE_CONV2_SLEEP_LD"); return e ? atoi(e) : 128; }();
+  a.sleep_mma = sleep_mma; a.sleep_ld = sleep_ld;
+  static const bool dbg_on = [] { const char* e = getenv("DEEPSPHERE_CONV2_DEBUG"); return e && atoi(e) == 1; }();
+  a.dbg = nullptr;
+  if (dbg_on) {
+    DS_CUDA(cudaMalloc((void**)&a.dbg, 16 * 5 * 8 * sizeof(long long)));
+    DS_CUDA(cudaMemsetAsync(a.dbg, 0, 16 * 5 * 8 * sizeof(long long), st));
+  }
   for (int s = 0; s < C2_H; ++s) a.out[s] = (out != nullptr && s < nsteps) ? out[s] : nullptr;
   a.in0 = in0; a.bias = bias; a.act = act; a.y = y;
   float* img = nullptr;
@@ -510,13 +593,30 @@ int launch_lattice_conv2(const LatticeDev& L, int nsteps, int64_t B, int64_t M, 
     DS_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     DS_CUDA(cudaFuncSetAttribute(lattice_conv2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     DS_CUDA(cudaFuncSetAttribute(lattice_conv2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    DS_CUDA(cudaFuncSetAttribute(lattice_conv2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    DS_CUDA(cudaFuncSetAttribute(lattice_conv2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_done = true;
   }
   const int n_units = a.n_tiles * a.b_split;
-  const int grid = std::min(n_units, num_sms());
+  const int grid = std::min(n_units, 2 * num_sms());
   if (cheb) lattice_conv2_kernel<true><<<grid, C2_THREADS, smem, st>>>(a);
   else lattice_conv2_kernel<false><<<grid, C2_THREADS, smem, st>>>(a);
   cudaError_t e = cudaGetLastError();
+  if (a.dbg != nullptr) {
+    long long h[16 * 5 * 8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, a.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(a.dbg);
+    const long long t0 = h[0];
+    for (int it = 0; it < 16; ++it) {
+      fprintf(stderr, "item %2d: wait_in %lld..%lld\n", it, h[(it * 5) * 8] - t0, h[(it * 5) * 8 + 1] - t0);
+      for (int s2 = 1; s2 <= nsteps; ++s2) {
+        const long long* q = h + (it * 5 + s2) * 8;
+        fprintf(stderr, "   hop %d: start %lld fma+%lld mmawait+%lld stsfence+%lld bar+%lld | mma: seen %lld issued+%lld done+%lld\n", s2,
+                q[0] - t0, q[1] - q[0], q[2] - q[1], q[3] - q[2], q[4] - q[3], q[5] - t0, q[6] - q[5], q[7] ? q[7] - q[6] : 0);
+      }
+    }
+  }
   cudaFreeAsync(img, st);
   g_launches.fetch_add(1);
   if (e != cudaSuccess) return fail("lattice_conv2_kernel launch failed: %s", cudaGetErrorString(e));

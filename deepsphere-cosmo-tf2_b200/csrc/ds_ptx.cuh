@@ -40,11 +40,39 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe of a phase (result can be consumed much later: hides the ~150-cycle round trip)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\tmbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// 16-byte store through the ASYNC proxy that signals `bar` (complete_tx of 16 bytes) when it has landed: data
+// written this way is visible to UMMA / TMA reads ordered after the barrier phase without any proxy fence
+__device__ __forceinline__ void st_async_v4(void* dst, const float4& v, uint64_t* bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(smem_u32(dst)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(smem_u32(bar))
+               : "memory");
+}
 // bounded wait: ~seconds of polling, then trap (surfaces as a launch failure, never a hang)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #pragma unroll 1
   for (uint32_t i = 0; i < (1u << 28); ++i)
     if (mbar_try_wait(bar, parity)) return;
+  printf("deepsphere_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+  __trap();
+}
+
+// same, for the producer / issuer roles that must not steal issue slots from the math warps while they poll
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+#pragma unroll 1
+  for (uint32_t i = 0; i < (1u << 26); ++i) {
+    if (mbar_try_wait(bar, parity)) return;
+    if (ns) __nanosleep(ns);
+  }
   printf("deepsphere_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
   __trap();
 }
