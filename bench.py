@@ -28,6 +28,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = "HealpyChebyshev fwd+bwd algorithmic GB/s (nside 256, K 5, Fin=Fout=64, batch 32/GPU)"
+TRAFFIC_DEFAULT = None  # filled from the ncu capture of the default config (bytes per launch)
 
 
 def parse():
@@ -36,7 +37,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("DEEPSPHERE_MODE", "tf32x3"), choices=["fp32", "tf32", "tf32x3"])
+    # contraction arithmetic (the recursion is always fp32 FMA): north_star names "3xTF32 or TF32" with a stated
+    # <= 1e-3 for TF32; tf32 is the mode the register-resident fused kernel (ds_lattice_conv2.cu) serves
+    ap.add_argument("--mode", default=os.environ.get("DEEPSPHERE_MODE", "tf32"), choices=["fp32", "tf32", "tf32x3"])
+    ap.add_argument("--no-other-modes", action="store_true")
     ap.add_argument("--nside", type=int, default=256)
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--features", type=int, default=64)
@@ -241,38 +245,78 @@ def main():
         return a.elapsed_time(b) / n
 
     A_bytes = 4 * B * M * F
+    fused = layer._plan.info(local_rank)["lattice"] == 1
+    fused_conv = fused and mode == "tf32" and F % 8 == 0 and F <= 80 and K <= 5
     with torch.no_grad():
         xd = x.detach()
-        fused = layer._plan.info(local_rank)["lattice"] == 1
-        basis_ms = time_fn(lambda: _ops.basis(layer._plan, xd, K))       # the recursion: K-1 hops
         fwd_ms = time_fn(lambda: layer(xd))                              # recursion + contraction
         t1 = _ops.spmm(layer._plan, xd)
         hop_ms = time_fn(lambda: _ops.spmm(layer._plan, t1, 2.0, xd, -1.0))  # one generic streaming hop
-    contraction_ms = max(fwd_ms - basis_ms, 1e-6)
+        basis_ms = None if fused_conv else time_fn(lambda: _ops.basis(layer._plan, xd, K))
+        del t1
     gemm_flops = 2.0 * B * M * K * F * F
-    rec_name = ("lattice_recursion_kernel<%d,16,4> (all %d hops fused)" % (K - 1, K - 1)) if fused \
-        else "spmm_tile_kernel x %d" % (K - 1)
+    nnz_hops = 9.0 * (K - 1)
+    fma_flops = 2.0 * nnz_hops * B * M * F            # useful stencil FLOPs of one recursion pass
     kernels = {
-        # algorithmic bytes of each kernel in the present two-kernel split (DESIGN.md "Kernels"):
-        # recursion reads x and writes T_1..T_{K-1}; contraction reads x, T_1..T_{K-1} and writes y
-        "recursion": {"kernel": rec_name, "ms": basis_ms, "algorithmic_bytes": K * A_bytes,
-                      "GBps": K * A_bytes / basis_ms / 1e6},
-        "contraction": {"kernel": "umma_gemm_kernel" if mode != "fp32" else "gemm_nn_kernel", "ms": contraction_ms,
-                        "algorithmic_bytes": (K + 1) * A_bytes, "GBps": (K + 1) * A_bytes / contraction_ms / 1e6,
-                        "TFLOPs": gemm_flops / contraction_ms / 1e9},
         "generic_hop": {"kernel": "spmm_tile_kernel", "ms": hop_ms, "algorithmic_bytes": 3 * A_bytes,
                         "GBps": 3 * A_bytes / hop_ms / 1e6},
         "forward": {"ms": fwd_ms, "algorithmic_bytes": 2 * A_bytes, "GBps": 2 * A_bytes / fwd_ms / 1e6},
+        "backward": {"ms": ms - fwd_ms, "algorithmic_bytes": 3 * A_bytes, "GBps": 3 * A_bytes / max(ms - fwd_ms, 1e-6) / 1e6,
+                     "note": "step minus forward: dz recursion + dx contraction (+ basis U_k to HBM) and the dW kernel"},
     }
-    # dominant kernel of the step: the recursion runs twice (on x and on dy), the contraction twice + dW
-    dom = kernels["recursion"] if 2 * basis_ms >= 2.5 * contraction_ms else kernels["contraction"]
+    if fused_conv:
+        # one launch = recursion (fp32 FFMA2, register resident) + tcgen05 contraction + bias/activation epilogue;
+        # HBM sees x (+ halo, from L2) and y only: algorithmic bytes per launch = 2 A
+        dom = {"kernel": "lattice_conv2_kernel<Chebyshev> (all %d hops + contraction fused)" % (K - 1), "ms": fwd_ms,
+               "algorithmic_bytes": 2 * A_bytes, "GBps": 2 * A_bytes / fwd_ms / 1e6,
+               "stencil_TFLOPs_fp32": fma_flops / fwd_ms / 1e9, "contraction_TFLOPs_tf32": gemm_flops / fwd_ms / 1e9}
+        kernels["fused_forward"] = dom
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture of the default
+        # config (profiles/r1j_prof_conv2_raw.csv); only quoted for that config
+        traffic = TRAFFIC_DEFAULT if (args.nside, B, F, K) == (256, 32, 64, 5) else None
+    else:
+        contraction_ms = max(fwd_ms - basis_ms, 1e-6)
+        rec_name = ("lattice_recursion_kernel<%d,16,8> (all %d hops fused)" % (max(K - 1, 4), K - 1)) if fused \
+            else "spmm_tile_kernel x %d" % (K - 1)
+        kernels["recursion"] = {"kernel": rec_name, "ms": basis_ms, "algorithmic_bytes": K * A_bytes,
+                                "GBps": K * A_bytes / basis_ms / 1e6}
+        kernels["contraction"] = {"kernel": "umma_gemm_kernel" if mode != "fp32" else "gemm_nn_kernel",
+                                  "ms": contraction_ms, "algorithmic_bytes": (K + 1) * A_bytes,
+                                  "GBps": (K + 1) * A_bytes / contraction_ms / 1e6,
+                                  "TFLOPs": gemm_flops / contraction_ms / 1e9}
+        dom = kernels["recursion"] if 2 * basis_ms >= 2.5 * contraction_ms else kernels["contraction"]
+        traffic = None
     roofline = {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["GBps"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": dom["GBps"] / hbm_peak, "traffic": None, "peak_source": peak_kind,
-                "note": "algorithmic bytes of this kernel / its CUDA-event duration; see DESIGN.md for the on-chip "
-                        "(shared-memory / FMA) bound that actually limits the fused recursion"}
+                "frac": dom["GBps"] / hbm_peak, "traffic": traffic, "peak_source": peak_kind,
+                "note": "algorithmic bytes of one launch / its CUDA-event duration; DESIGN.md section 3 explains why the "
+                        "fused kernel is bound on chip (shared-memory exchange + fp32 FMA issue), not by HBM"}
     layer_roofline = {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                       "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak,
                       "note": "whole layer fwd+bwd, algorithmic bytes / step time, per GPU"}
+
+    # ---- the same step in the other contraction modes (short runs, reported next to the headline) ------
+    other_modes = {}
+    if not args.no_other_modes and rank == 0 and world == 1:
+        for om in ("tf32x3", "tf32", "fp32"):
+            if om == mode:
+                continue
+            try:
+                layer.mode = om
+                step()
+                torch.cuda.synchronize()
+                a0, b0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(2):
+                    step()
+                b0.record()
+                torch.cuda.synchronize()
+                oms = a0.elapsed_time(b0) / 2
+                other_modes[om] = {"ms_per_step": oms, "GBps": nbytes / (oms * 1e-3) / 1e9}
+            except Exception as exc:  # e.g. out of memory for the unfused fp32 workspace
+                other_modes[om] = {"error": str(exc)[:120]}
+            finally:
+                layer.mode = mode
+                torch.cuda.empty_cache()
 
     # ---- e2e: public layer API, pinned host buffers, H2D + D2H inside the timed region ------------
     e2e = None
@@ -335,13 +379,13 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"fp32": "fp32", "tf32": "tf32 contraction / fp32 recursion",
+            "vs_baseline": None, "dtype": {"fp32": "fp32", "tf32": "fp32 recursion (FFMA2) + TF32 tensor-core contraction, fp32 accumulate (rel err <= 1e-3, measured 5e-4)",
                                            "tf32x3": "fp32 (recursion fp32 FMA; contraction 3xTF32 error-compensated on tcgen05, rel err <= 2e-5)"}[mode],
             "data": "synthetic",
             "config": {"workload": f"HealpyChebyshev layer nside {args.nside} (M={M}) K {K} Fin=Fout={F} "
                                    f"batch {B}/GPU fwd+bwd, 8-neighbour HEALPix graph",
                        "mode": mode, "parallelism": f"batch-sharded x{world}", "l2": "inputs (6.4 GB/tensor) >> L2"},
-            "roofline": roofline, "layer_roofline": layer_roofline, "kernels": kernels,
+            "roofline": roofline, "layer_roofline": layer_roofline, "kernels": kernels, "other_modes": other_modes,
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
         }
         print(json.dumps(line))

@@ -57,6 +57,7 @@ struct Conv2Args {
   int nsteps;  // hops, 1..4
   float wscale;
   long long* dbg;           // optional timeline probe [item < 16][hop 0..4][8 slots] of clock64 (block 0)
+  int flags;                // bit 0: skip the outer block-row pair on hops 3, 4
   int sleep_mma, sleep_ld;  // ns of back-off between polls of the issuer / gather roles (0: plain spin)
   const float* in0;     // [B, M, F]
   float* out[C2_H];     // optional basis of hop s (own pixels), [B, M, F]
@@ -137,11 +138,37 @@ __device__ __forceinline__ constexpr int dir_of(int dr, int dc) {
   return dr == 0 ? (dc < 0 ? 0 : (dc > 0 ? 4 : 8)) : (dr > 0 ? (dc < 0 ? 1 : (dc == 0 ? 2 : 3)) : (dc > 0 ? 5 : (dc == 0 ? 6 : 7)));
 }
 
-// One hop on the thread's 3x3 block: acc <- (sum_d w_d * neighbour_d(in)) - (HAS_OLD ? acc : 0), halved if HALVE.
-// `src` points at the thread's own (r = 0, cc = 0) position of the buffer holding `in` of all threads.
-template <bool HAS_OLD, bool HALVE, int ROT>
-__device__ __forceinline__ void hop_compute(const float4 (&in)[3][3], float4 (&acc)[3][3], const float (&w)[3][3][9],
-                                            const float4* __restrict__ src) {
+// One hop on the thread's 3x3 block, in two parts so that the part that needs no other thread's data overlaps the
+// wait for the neighbours:
+//   hop_inside:    acc <- w_c * in - (HAS_OLD ? acc : 0) + taps whose source pixel lies inside the block (49 of 81)
+//   hop_perimeter: acc += taps whose source is one of the 16 perimeter pixels (loaded from `src`, which points at the
+//                  thread's own (r = 0, cc = 0) position of the buffer holding `in` of all threads); halved if HALVE
+template <bool HAS_OLD, int ROT>
+__device__ __forceinline__ void hop_inside(const float4 (&in)[3][3], float4 (&acc)[3][3], const float (&w)[3][3][9]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      if (HAS_OLD) f4_fms<ROT>(w[r][cc][8], in[r][cc], acc[r][cc]);
+      else f4_mul<ROT>(w[r][cc][8], in[r][cc], acc[r][cc]);
+    }
+#pragma unroll
+  for (int dr = -1; dr <= 1; ++dr)
+#pragma unroll
+    for (int dc = -1; dc <= 1; ++dc)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          if (dr == 0 && dc == 0) continue;
+          const int sr = r + dr, sc = cc + dc;
+          if (!(sr >= 0 && sr < 3 && sc >= 0 && sc < 3)) continue;
+          f4_fma<ROT>(w[r][cc][dir_of(dr, dc)], in[sr][sc], acc[r][cc]);
+        }
+}
+template <bool HALVE, int ROT>
+__device__ __forceinline__ void hop_perimeter(float4 (&acc)[3][3], const float (&w)[3][3][9],
+                                              const float4* __restrict__ src) {
   // position offsets of columns -1, 0, 1, 2, 3 relative to the own column-0 position
   constexpr int CO[5] = {15, 0, 8, 16, 1};
   float4 top[5], bot[5], lft[3], rgt[3];
@@ -154,36 +181,23 @@ __device__ __forceinline__ void hop_compute(const float4 (&in)[3][3], float4 (&a
   }
 #pragma unroll
   for (int k = 0; k < 5; ++k) bot[k] = src[3 * C2_LW + CO[k]];
-  // centre taps (and the -T_{k-2} term), then the taps inside the block, then the perimeter
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
+  for (int dr = -1; dr <= 1; ++dr)
 #pragma unroll
-    for (int cc = 0; cc < 3; ++cc)
-      if (HAS_OLD) f4_fms<ROT>(w[r][cc][8], in[r][cc], acc[r][cc]);
-      else f4_mul<ROT>(w[r][cc][8], in[r][cc], acc[r][cc]);
-  // tap order: direction outer, pixel inner - consecutive 4-FFMA groups (one weight, 4 channels: the weight sits
-  // in the operand reuse cache for 3 of them) are independent, so the scheduler has no reason to split them
+    for (int dc = -1; dc <= 1; ++dc)
 #pragma unroll
-  for (int pass = 0; pass < 2; ++pass)
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int dr = -1; dr <= 1; ++dr)
-#pragma unroll
-      for (int dc = -1; dc <= 1; ++dc)
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int cc = 0; cc < 3; ++cc) {
-            if (dr == 0 && dc == 0) continue;
-            const int sr = r + dr, sc = cc + dc;
-            const bool inside = sr >= 0 && sr < 3 && sc >= 0 && sc < 3;
-            if (inside != (pass == 0)) continue;
-            const float wv = w[r][cc][dir_of(dr, dc)];
-            if (inside) f4_fma<ROT>(wv, in[sr][sc], acc[r][cc]);
-            else if (sr < 0) f4_fma<ROT>(wv, top[sc + 1], acc[r][cc]);
-            else if (sr > 2) f4_fma<ROT>(wv, bot[sc + 1], acc[r][cc]);
-            else if (sc < 0) f4_fma<ROT>(wv, lft[sr], acc[r][cc]);
-            else f4_fma<ROT>(wv, rgt[sr], acc[r][cc]);
-          }
+        for (int cc = 0; cc < 3; ++cc) {
+          if (dr == 0 && dc == 0) continue;
+          const int sr = r + dr, sc = cc + dc;
+          if (sr >= 0 && sr < 3 && sc >= 0 && sc < 3) continue;
+          const float wv = w[r][cc][dir_of(dr, dc)];
+          if (sr < 0) f4_fma<ROT>(wv, top[sc + 1], acc[r][cc]);
+          else if (sr > 2) f4_fma<ROT>(wv, bot[sc + 1], acc[r][cc]);
+          else if (sc < 0) f4_fma<ROT>(wv, lft[sr], acc[r][cc]);
+          else f4_fma<ROT>(wv, rgt[sr], acc[r][cc]);
+        }
   if (HALVE) {
 #pragma unroll
     for (int r = 0; r < 3; ++r)
@@ -214,7 +228,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
       ptx::mbar_init(&ctl->in_empty[i], 1);
       ptx::mbar_init(&ctl->w_full[i], 1);
       ptx::mbar_init(&ctl->item_done[i], 1);
-      ptx::mbar_init(&ctl->hop_full[i], 4);
+      ptx::mbar_init(&ctl->hop_full[i], C2_NCOMP);
       ptx::mbar_init(&ctl->mma_done[i], 1);
     }
     ptx::mbar_init(&ctl->acc_full, 1);
@@ -230,14 +244,20 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
   if (warp < 4) {
     // ================================ compute warps ================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C2_REG_COMPUTE));
-    const int R = 2 * warp + (lane >> 4), q = (lane >> 3) & 1, cb = lane & 7;
+    // block rows are paired symmetrically (rp, 7 - rp) inside a warp: the outermost pair lies entirely outside the
+    // valid region of hops 3 and 4 and is skipped by its whole warp; co-resident CTAs rotate the pairing so that
+    // the light warp lands on different SM sub-partitions
+    const int rp = (warp + 2 * (int)(blockIdx.x & 1)) & 3;
+    const int R = (lane >> 4) ? 7 - rp : rp, q = (lane >> 3) & 1, cb = lane & 7;
     const int own0 = q * C2_PL + (3 * R + 1) * C2_LW + cb;  // float4 index of the own (0, 0) position
     const int FV = a.F / 4, NV16 = N / 16;
     const bool has_out = a.out[0] != nullptr || a.out[1] != nullptr || a.out[2] != nullptr || a.out[3] != nullptr;
     float w[3][3][9];
     float4 A[3][3], Bv[3][3];
     uint32_t it = 0, g = 0;
-    uint32_t cnt_done[2] = {0, 0};
+    uint32_t cnt_done[2] = {0, 0}, par[2] = {0, 0};
+    int last_bar = -1;
+    uint32_t last_par = 0;
     int erow[3] = {-1, -1, -1};
     bool pend = false;
     uint32_t pend_g = 0;
@@ -323,15 +343,14 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc) A[r][cc] = S[own0 + r * C2_LW + cc * 8];
 
-          // hop s: in -> acc (the register arrays alternate), src buffer -> X[(s-1)&1].  Every thread computes its
-          // whole block on every hop: positions outside the shrinking valid region hold don't-care values that
-          // never reach a valid output (a valid output only reads valid inputs).
-          // hop s: in -> acc (the register arrays alternate), src buffer -> X[(s-1)&1].  Every thread computes its
-          // whole block on every hop: positions outside the shrinking valid region hold don't-care values that
-          // never reach a valid output (a valid output only reads valid inputs).
-          // (st.async + mbarrier complete_tx instead of STS + proxy fence + bar.sync was measured: the async-proxy
-          // store path sustains only ~20 B/clk, 3x slower than this.)
-          auto hop = [&](auto s_tag, const float4(&in)[3][3], float4(&acc)[3][3], const float4* src) {
+          // Hop s: `in` (T_{s-1}) -> `acc` (T_{s-2} -> T_s), the register arrays alternate; results are published in
+          // X[(s-1)&1].  There is no __syncthreads: every thread arrives on hop_full[p] (count 128) after its stores
+          // and proxy fence, starts the inside part of the NEXT hop (own registers only, 60 % of the taps) and only
+          // then waits for the phase before it loads its perimeter.  Every thread computes its whole block on every
+          // hop: positions outside the shrinking valid region hold don't-care values that never reach a valid
+          // output (a valid output only reads valid inputs).
+          // (st.async + complete_tx instead of STS + proxy fence was measured: ~20 B/clk, 3x slower.)
+          auto finish_hop = [&](auto s_tag, float4(&acc)[3][3], const float4* src) {
             constexpr int s = decltype(s_tag)::value;
             constexpr int p = (s - 1) & 1;
             const bool probe = a.dbg != nullptr && blockIdx.x == 0 && it < 16 && tid == 0;
@@ -339,9 +358,13 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
             if (probe) pd[0] = clock64();
             // the UMMAs that read X[p] two hops ago: probe now, consume after the arithmetic (hides the round trip)
             const bool mma_ok = cnt_done[p] == 0 || ptx::mbar_test_wait(&ctl->mma_done[p], (cnt_done[p] - 1) & 1);
-            hop_compute<(CHEB && s >= 2), (CHEB && s == 1), rot_of_hop(s)>(in, acc, w, src + own0);
+            hop_perimeter<(CHEB && s == 1), rot_of_hop(s)>(acc, w, src + own0);
             if (probe) pd[1] = clock64();
             if (!mma_ok) ptx::mbar_wait(&ctl->mma_done[p], (cnt_done[p] - 1) & 1);
+            if (s == 1 && last_bar >= 0) {  // previous item's last phase: everybody has finished reading X[0]
+              ptx::mbar_wait(&ctl->hop_full[last_bar], last_par);
+              last_bar = -1;
+            }
             if (probe) pd[2] = clock64();
             float4* dst = X[p] + own0;
 #pragma unroll
@@ -349,9 +372,8 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
 #pragma unroll
               for (int cc = 0; cc < 3; ++cc) dst[r * C2_LW + cc * 8] = acc[r][cc];
             ptx::fence_proxy_async_smem();
+            ptx::mbar_arrive(&ctl->hop_full[p]);
             if (probe) pd[3] = clock64();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&ctl->hop_full[p]);
             float* outp = a.out[s - 1];
             if (outp != nullptr) {
               float4* ob = reinterpret_cast<float4*>(outp + (b * a.M * a.F + c * C2_FC)) + q;
@@ -364,16 +386,37 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
                   if (row >= 0) __stcs(ob + (int64_t)row * FV, v);
                 }
             }
-            ptx::named_bar_sync(1, C2_NCOMP);
-            if (probe) pd[4] = clock64();
+            par[p] = cnt_done[p] & 1;  // parity of the phase this arrival belongs to
             cnt_done[p]++;
+            if (probe) pd[4] = clock64();
           };
+          // wait until hop s has been published by everybody (its phase on hop_full[(s-1)&1])
+          auto wait_hop = [&](int pp) { ptx::mbar_wait(&ctl->hop_full[pp], par[pp]); };
 
-          hop(std::integral_constant<int, 1>{}, A, Bv, S);
+          hop_inside<false, rot_of_hop(1)>(A, Bv, w);
+          finish_hop(std::integral_constant<int, 1>{}, Bv, S);
           if (pend) epilogue();
-          if (nsteps >= 2) hop(std::integral_constant<int, 2>{}, Bv, A, X[0]);
-          if (nsteps >= 3) hop(std::integral_constant<int, 3>{}, A, Bv, X[1]);
-          if (nsteps >= 4) hop(std::integral_constant<int, 4>{}, Bv, A, X[0]);
+          int last = 0;
+          if (nsteps >= 2) {
+            hop_inside<CHEB, rot_of_hop(2)>(Bv, A, w);
+            wait_hop(0);
+            finish_hop(std::integral_constant<int, 2>{}, A, X[0]);
+            last = 1;
+          }
+          if (nsteps >= 3) {
+            hop_inside<CHEB, rot_of_hop(3)>(A, Bv, w);
+            wait_hop(1);
+            finish_hop(std::integral_constant<int, 3>{}, Bv, X[1]);
+            last = 0;
+          }
+          if (nsteps >= 4) {
+            hop_inside<CHEB, rot_of_hop(4)>(Bv, A, w);
+            wait_hop(0);
+            finish_hop(std::integral_constant<int, 4>{}, A, X[0]);
+            last = 1;
+          }
+          last_bar = last;
+          last_par = par[last];
 
           if (c == n_chunks - 1) {
             pend = true;
@@ -570,6 +613,8 @@ int launch_lattice_conv2(const LatticeDev& L, int nsteps, int64_t B, int64_t M, 
   static const int sleep_mma = [] { const char* e = getenv("DEEPSPHERE_CONV2_SLEEP_MMA"); return e ? atoi(e) : 0; }();
   static const int sleep_ld = [] { const char* e = getenv("DEEPSPHERE_CONV2_SLEEP_LD"); return e ? atoi(e) : 128; }();
   a.sleep_mma = sleep_mma; a.sleep_ld = sleep_ld;
+  static const int flags = [] { const char* e = getenv("DEEPSPHERE_CONV2_FLAGS"); return e ? atoi(e) : 1; }();
+  a.flags = flags;
   static const bool dbg_on = [] { const char* e = getenv("DEEPSPHERE_CONV2_DEBUG"); return e && atoi(e) == 1; }();
   a.dbg = nullptr;
   if (dbg_on) {

@@ -12,6 +12,7 @@
 // row is read from HBM exactly once; per-CTA partials are then summed by a small second kernel
 // (deterministic, no atomics).  HBM-bound: (nseg*Kc + N)*4 bytes per row.
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "ds_common.cuh"
@@ -38,6 +39,12 @@ struct TnParams {
   uint32_t tmem_cols;
   int64_t rblocks_per_cta;
   float* partial;   // [gridDim.x][n_q * 32][N]
+  // raw operand pointers for the cp.async producers
+  const float* A0;     // segment 0, [R, Kc]
+  const float* Arest;  // segments 1.., [nseg-1, R, Kc]
+  const float* D;      // [R, N]
+  int64_t Kc;
+  int use_cp_async;
 };
 
 struct TnCtl {
@@ -66,7 +73,7 @@ umma_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      ptx::mbar_init(&ctl->full[s], 1);
+      ptx::mbar_init(&ctl->full[s], p.use_cp_async ? 128 : 1);
       ptx::mbar_init(&ctl->empty[s], 1);
       ptx::mbar_init(&ctl->split_done[s], 128);
     }
@@ -85,7 +92,7 @@ umma_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
   const uint32_t tmem_base = ctl->tmem_base;
 
   if (warp == 0) {
-    if (ptx::elect_one()) {
+    if (!p.use_cp_async && ptx::elect_one()) {
       for (int64_t it = 0; it < n_it; ++it) {
         const int s = (int)(it % p.stages);
         const uint32_t ph = (uint32_t)(it / p.stages) & 1;
@@ -139,6 +146,61 @@ umma_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
       __syncwarp();
     }
   } else if (warp < 6) {
+    if (p.use_cp_async) {
+      // Operand producers (the epilogue warps are idle during the main loop).  The TMA box in 32-byte-atom swizzle
+      // mode sustains only ~10 B/clk/SM (ncu: 2.6 TB/s chip-wide, nothing saturated); 128 threads issuing 16-byte
+      // cp.async straight into the same layout (row r of a 16 x 32 block at r*128 B, 32-byte chunk index XOR r % 4)
+      // reach the HBM rate.  One 16-byte chunk per thread per block; out-of-range rows / channels are zero-filled.
+      const int t = threadIdx.x - 64;
+      const int r = t >> 3, j = t & 7;
+      const uint32_t dst_off = (uint32_t)(r * 128 + (((j >> 1) ^ (r & 3)) * 32) + (j & 1) * 16);
+      constexpr int LAG = 3;      // stages whose copies may still be in flight per thread
+      constexpr int MAXB = 16;    // blocks per stage handled by this path (launcher checks n_q + nb <= MAXB)
+      // per-block source column pointer / row pitch / validity do not depend on the stage: hoist them
+      const float* bptr[MAXB];
+      uint32_t bok = 0;
+      const int nblk = p.n_q + p.nb_blocks;
+#pragma unroll
+      for (int k = 0; k < MAXB; ++k) {
+        bptr[k] = p.A0;
+        if (k < p.n_q) {
+          const int seg = k / p.q_per_seg, cb = k % p.q_per_seg;
+          const int col = cb * BLK + 4 * j;
+          const float* base = seg == 0 ? p.A0 : p.Arest + (int64_t)(seg - 1) * p.R * p.Kc;
+          if (col < p.Kc) { bptr[k] = base + col; bok |= 1u << k; }
+        } else if (k < nblk) {
+          const int col = (k - p.n_q) * BLK + 4 * j;
+          if (col < p.N) { bptr[k] = p.D + col; bok |= 1u << k; }
+        }
+      }
+      for (int64_t it = 0; it < n_it + LAG; ++it) {
+        if (it < n_it) {
+          const int s = (int)(it % p.stages);
+          const uint32_t ph = (uint32_t)(it / p.stages) & 1;
+          ptx::mbar_wait(&ctl->empty[s], ph ^ 1);
+          const uint32_t st = ptx::smem_u32(stage_base + (size_t)s * p.stage_bytes) + dst_off;
+          const int64_t row = (rb0 + it) * BKR + r;
+          const bool row_ok = row < p.R;
+          const int64_t offA = row_ok ? row * p.Kc : 0, offD = row_ok ? row * (int64_t)p.N : 0;
+#pragma unroll
+          for (int k = 0; k < MAXB; ++k) {
+            if (k < nblk) {
+              const bool ok = row_ok && ((bok >> k) & 1u);
+              const float* src = bptr[k] + (k < p.n_q ? offA : offD);
+              // the D blocks follow the A blocks in the stage (off_d = n_q * BLK_BYTES)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(st + (uint32_t)k * BLK_BYTES), "l"(src),
+                           "r"(ok ? 16u : 0u) : "memory");
+            }
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (it >= LAG) {
+          asm volatile("cp.async.wait_group %0;" ::"n"(LAG) : "memory");
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(&ctl->full[(int)((it - LAG) % p.stages)]);
+        }
+      }
+    }
     // epilogue: once, after the whole row range has been reduced
     const int qd = warp & 3;
     float* part = p.partial + (size_t)blockIdx.x * p.n_q * BLK * p.N;
@@ -318,6 +380,9 @@ int launch_umma_gemm_tn(int64_t R, int64_t N, int64_t Kc, int nseg, const float*
   p.tmem_cols = g.tmem_cols;
   p.rblocks_per_cta = g.rblocks_per_cta;
   p.partial = partial;
+  p.A0 = A0; p.Arest = Arest != nullptr ? Arest : A0; p.D = D; p.Kc = Kc;
+  static const int use_tma = [] { const char* e = getenv("DEEPSPHERE_TN_TMA"); return e && atoi(e) == 1; }();
+  p.use_cp_async = (!use_tma && g.stages >= 5 && g.n_q + g.nb_blocks <= 16) ? 1 : 0;
   CUtensorMap m0, m1, md;
   DS_TRY(make_rows_map(&m0, A0, 1, R, Kc));
   DS_TRY(nseg > 1 ? make_rows_map(&m1, Arest, nseg - 1, R, Kc) : make_rows_map(&m1, A0, 1, R, Kc));

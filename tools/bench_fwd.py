@@ -22,9 +22,14 @@ def step():
         y.backward(dy)
 for _ in range(2): step()
 torch.cuda.synchronize()
-a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-a.record()
-n = 5
-for _ in range(n): step()
-b.record(); torch.cuda.synchronize()
-print("RESULT", mode, B, "bwd" if bwd else "fwd", "ms", a.elapsed_time(b) / n, "env", {k: v for k, v in os.environ.items() if k.startswith("DEEPSPHERE")})
+n = int(os.environ.get("ITERS", "8"))
+evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+evs[0].record()
+for i in range(n):
+    step()
+    evs[i + 1].record()
+torch.cuda.synchronize()
+ts = [evs[i].elapsed_time(evs[i + 1]) for i in range(n)]
+import subprocess
+clk = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.mem,power.draw,temperature.gpu,clocks_throttle_reasons.active", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip()
+print("RESULT", mode, B, "bwd" if bwd else "fwd", "ms", " ".join(f"{t:.2f}" for t in ts), "| clk", clk, "env", {k: v for k, v in os.environ.items() if k.startswith("DEEPSPHERE")})
