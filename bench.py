@@ -28,7 +28,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = "HealpyChebyshev fwd+bwd algorithmic GB/s (nside 256, K 5, Fin=Fout=64, batch 32/GPU)"
-TRAFFIC_DEFAULT = None  # filled from the ncu capture of the default config (bytes per launch)
+TRAFFIC_DEFAULT = 14552909000  # dram read 8.168 GB + write 6.385 GB per launch, profiles/r1k_prof_lattice_conv2_raw.csv
 
 
 def parse():
@@ -272,7 +272,7 @@ def main():
                "stencil_TFLOPs_fp32": fma_flops / fwd_ms / 1e9, "contraction_TFLOPs_tf32": gemm_flops / fwd_ms / 1e9}
         kernels["fused_forward"] = dom
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture of the default
-        # config (profiles/r1j_prof_conv2_raw.csv); only quoted for that config
+        # config (profiles/r1k_prof_lattice_conv2_raw.csv); only quoted for that config
         traffic = TRAFFIC_DEFAULT if (args.nside, B, F, K) == (256, 32, 64, 5) else None
     else:
         contraction_ms = max(fwd_ms - basis_ms, 1e-6)
@@ -339,15 +339,47 @@ def main():
         del x, dy
         torch.cuda.empty_cache()
 
+        # The reference-facing call with HOST buffers: batch chunks are pipelined over three streams (H2D of chunk
+        # i+1, layer fwd+bwd of chunk i, D2H of chunk i-1), all through the public layer API; the kernel gradient
+        # accumulates over the chunks exactly like a gradient-accumulation step.
+        n_chunks = max(1, min(8, Be))
+        while Be % n_chunks:
+            n_chunks -= 1
+        Bc = Be // n_chunks
+        s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+        x_d = [torch.empty((Bc, M, F), device=device) for _ in range(2)]
+        dy_d = [torch.empty((Bc, M, F), device=device) for _ in range(2)]
+
         def e2e_step():
-            xd_ = xh.to(device, non_blocking=True).requires_grad_(True)
-            dyd = dyh.to(device, non_blocking=True)
             layer.kernel.grad = None
-            y = layer(xd_)
-            y.backward(dyd)
-            dsd.allreduce_gradients([layer.kernel])
-            dxh.copy_(xd_.grad, non_blocking=True)
-            dkh.copy_(layer.kernel.grad, non_blocking=True)
+            cur = torch.cuda.current_stream()
+            for st_ in (s_in, s_cmp, s_out):
+                st_.wait_stream(cur)
+            ev_in, ev_cmp, ev_out = [], [], []
+            for i in range(n_chunks):
+                sl = slice(i * Bc, (i + 1) * Bc)
+                with torch.cuda.stream(s_in):
+                    if i >= 2:
+                        s_in.wait_event(ev_cmp[i - 2])  # the device buffers of chunk i-2 are free again
+                    x_d[i & 1].copy_(xh[sl], non_blocking=True)
+                    dy_d[i & 1].copy_(dyh[sl], non_blocking=True)
+                    ev_in.append(torch.cuda.Event()); ev_in[-1].record(s_in)
+                with torch.cuda.stream(s_cmp):
+                    s_cmp.wait_event(ev_in[i])
+                    xg = x_d[i & 1].detach().requires_grad_(True)
+                    y = layer(xg)
+                    y.backward(dy_d[i & 1])
+                    gx = xg.grad
+                    ev_cmp.append(torch.cuda.Event()); ev_cmp[-1].record(s_cmp)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_cmp[i])
+                    gx.record_stream(s_out)
+                    dxh[sl].copy_(gx, non_blocking=True)
+            with torch.cuda.stream(s_cmp):
+                dsd.allreduce_gradients([layer.kernel])
+                dkh.copy_(layer.kernel.grad, non_blocking=True)
+            for st_ in (s_in, s_cmp, s_out):
+                cur.wait_stream(st_)
 
         e2e_step()
         sync_all()
@@ -361,7 +393,8 @@ def main():
         e2e_ms = dsd.allreduce_max(a.elapsed_time(b) / n_e2e, device)
         e2e = {"value": world * algorithmic_bytes(Be, M, F, F) / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s",
                "h2d_bytes_per_step": 2 * 4 * Be * M * F, "d2h_bytes_per_step": 4 * Be * M * F + 4 * K * F * F,
-               "ms_per_step": e2e_ms, "batch": Be, "steps": n_e2e}
+               "ms_per_step": e2e_ms, "batch": Be, "steps": n_e2e,
+               "pipeline": f"{n_chunks} batch chunks over 3 streams (H2D | fwd+bwd | D2H), pinned host buffers"}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample -------------------
     cpu_baseline = None

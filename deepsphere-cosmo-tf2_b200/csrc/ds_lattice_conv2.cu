@@ -2,24 +2,27 @@
 //
 //   y[b, m, :] = act( sum_k T_k(L~) x [b, m, :] * W_k + bias )            (gnn_layers.py:131-159)
 //
-// Work item = (16x16-pixel tile + 4-ring halo = 24x24 lattice, batch element b, 16-channel chunk c).
+// Work item = (16x16-pixel tile + 4-ring halo = 24x24 lattice, batch element b, 8-channel chunk c).
 // What differs from ds_lattice_conv.cu (whose recursion is shared-memory-bandwidth bound at ~5 accesses per
 // 36 FMAs): every compute thread OWNS a 3x3 pixel block x 4 channels for all hops of an item and keeps
 // T_{k-1} and T_{k-2} of that block in REGISTERS next to its 81 stencil weights.  Shared memory only carries
 // the neighbour exchange: per hop a thread stores its 9 new values and loads the 16 perimeter values
-// (2.8 accesses per 36 FMAs), and the very same exchange buffer is the K-major no-swizzle UMMA A operand, so
-// the contraction costs no extra shared-memory writes.
+// (2.8 accesses per 36 FMAs), and the very same exchange buffer is the K-major no-swizzle UMMA A operand
+// (8 channels = one tf32 K step), so the contraction costs no extra shared-memory writes.
 //
-// Roles (384 threads, 1 CTA / SM, registers rebalanced with setmaxnreg):
-//   warps 0-7  compute: warp R owns lattice rows 3R..3R+2, lane = (channel quad q, column block cb); hops whose
-//              active region does not reach the warp's rows are skipped by the whole warp.  They also drain the
-//              TMEM accumulators (bias + activation + store of the own pixels), one (tile, b) behind the MMAs.
-//   warp  8    one lane: streams the weight slice of the next chunk (cp.async.bulk) and issues
+// Roles (256 threads, 2 CTAs / SM so that one CTA's synchronisation phases overlap the other's arithmetic;
+// registers rebalanced with setmaxnreg, see C2_REG_*):
+//   warps 0-3  compute: 64 blocks x 2 channel quads; lane = (block-row half, quad q, column block cb).  The arithmetic
+//              is packed FFMA2 with the weight as broadcast scalar operand.  Hops are synchronised with an mbarrier
+//              (every thread arrives after its stores + proxy fence) instead of __syncthreads, and the taps that
+//              only need the thread's own registers (49 of 81) run BEFORE the wait for the neighbours.  These warps
+//              also drain the TMEM accumulator (bias + activation + store of the own pixels) of the previous (tile, b).
+//   warp  4    one lane: streams the weight slice of the next chunk (cp.async.bulk) and issues
 //              tcgen05.mma.kind::tf32 after every hop: A = T_k rows 4..19 of the lattice (384 positions = 3 M-tiles),
-//              B = 16-channel slice of W_k, accumulating over hops and chunks in TMEM (double buffered).
-//   warps 9-11 gather the next item's input rows into a staging buffer (cp.async, zero fill for holes).
+//              B = 8-channel slice of W_k, accumulating over hops and chunks in TMEM.
+//   warps 5-7  gather the next item's input rows into a staging buffer (cp.async, zero fill for holes).
 //
-// Exchange-buffer layout: 4 float4 planes (channel quads) of 26 x 24 positions; lattice (row j, column c) sits
+// Exchange-buffer layout: 2 float4 planes (channel quads) of 26 x 24 positions; lattice (row j, column c) sits
 // at position (j + 1) * 24 + (c % 3) * 8 + c / 3, i.e. the three columns of a block are de-interleaved so that
 // the 8 lanes of a quarter-warp always touch 8 consecutive float4 (conflict-free LDS.128 / STS.128), and 8
 // consecutive positions are one UMMA core matrix (SBO = 128 B, LBO = plane stride).
@@ -57,7 +60,6 @@ struct Conv2Args {
   int nsteps;  // hops, 1..4
   float wscale;
   long long* dbg;           // optional timeline probe [item < 16][hop 0..4][8 slots] of clock64 (block 0)
-  int flags;                // bit 0: skip the outer block-row pair on hops 3, 4
   int sleep_mma, sleep_ld;  // ns of back-off between polls of the issuer / gather roles (0: plain spin)
   const float* in0;     // [B, M, F]
   float* out[C2_H];     // optional basis of hop s (own pixels), [B, M, F]
@@ -244,11 +246,9 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
   if (warp < 4) {
     // ================================ compute warps ================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C2_REG_COMPUTE));
-    // block rows are paired symmetrically (rp, 7 - rp) inside a warp: the outermost pair lies entirely outside the
-    // valid region of hops 3 and 4 and is skipped by its whole warp; co-resident CTAs rotate the pairing so that
-    // the light warp lands on different SM sub-partitions
-    const int rp = (warp + 2 * (int)(blockIdx.x & 1)) & 3;
-    const int R = (lane >> 4) ? 7 - rp : rp, q = (lane >> 3) & 1, cb = lane & 7;
+    // (skipping the block rows that lie outside the valid region of hops 3, 4 was measured: no gain, the kernel is
+    // bound by the per-hop dependency chain, not by issue slots)
+    const int R = 2 * warp + (lane >> 4), q = (lane >> 3) & 1, cb = lane & 7;
     const int own0 = q * C2_PL + (3 * R + 1) * C2_LW + cb;  // float4 index of the own (0, 0) position
     const int FV = a.F / 4, NV16 = N / 16;
     const bool has_out = a.out[0] != nullptr || a.out[1] != nullptr || a.out[2] != nullptr || a.out[3] != nullptr;
@@ -613,8 +613,6 @@ int launch_lattice_conv2(const LatticeDev& L, int nsteps, int64_t B, int64_t M, 
   static const int sleep_mma = [] { const char* e = getenv("DEEPSPHERE_CONV2_SLEEP_MMA"); return e ? atoi(e) : 0; }();
   static const int sleep_ld = [] { const char* e = getenv("DEEPSPHERE_CONV2_SLEEP_LD"); return e ? atoi(e) : 128; }();
   a.sleep_mma = sleep_mma; a.sleep_ld = sleep_ld;
-  static const int flags = [] { const char* e = getenv("DEEPSPHERE_CONV2_FLAGS"); return e ? atoi(e) : 1; }();
-  a.flags = flags;
   static const bool dbg_on = [] { const char* e = getenv("DEEPSPHERE_CONV2_DEBUG"); return e && atoi(e) == 1; }();
   a.dbg = nullptr;
   if (dbg_on) {

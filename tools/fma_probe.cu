@@ -12,6 +12,9 @@ __global__ void probe(float* out, int iters, long long* cycles) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) w[i] = 1.0f + 1e-6f * (threadIdx.x + i);
   float2 x = make_float2(0.999f, 1.001f);
+  float2 xs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) xs[i] = make_float2(0.999f + 1e-4f * i + 1e-6f * threadIdx.x, 1.001f - 1e-4f * i);
   __syncthreads();
   long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
@@ -25,6 +28,13 @@ __global__ void probe(float* out, int iters, long long* cycles) {
         } else if (MODE == 1) {  // FFMA2, broadcast pair built once per j (hoisted)
           float2 ww = make_float2(w[j], w[j]);
           acc[i] = __ffma2_rn(ww, x, acc[i]);
+        } else if (MODE == 3) {  // FFMA2, scalar weight reused across i, data pair distinct per instruction
+          acc[i] = __ffma2_rn(make_float2(w[j], w[j]), xs[(i + j) & 7], acc[i]);
+        } else if (MODE == 4) {  // FFMA2, weight AND data distinct per instruction
+          acc[i] = __ffma2_rn(make_float2(w[(i + j) & 7], w[(i + j) & 7]), xs[(i + 3 * j) & 7], acc[i]);
+        } else if (MODE == 5) {  // scalar FFMA, weight and data distinct per instruction
+          acc[i].x = fmaf(w[(i + j) & 7], xs[(i + 3 * j) & 7].x, acc[i].x);
+          acc[i].y = fmaf(w[(i + j) & 7], xs[(i + 3 * j) & 7].y, acc[i].y);
         } else {  // FFMA2 with a fresh pair per 2 FFMA2 (forces a MOV per pair of FFMA2)
           float wv = w[j] + (float)(i >> 1) * 1e-9f * (float)it;
           float2 ww = make_float2(wv, wv);
@@ -60,10 +70,13 @@ void run(const char* name, int warps_per_sm) {
 }
 
 int main() {
-  for (int w : {4, 8, 16, 32}) {
+  for (int w : {4, 8, 16}) {
     run<0>("FFMA scalar", w);
     run<1>("FFMA2 (pair hoisted)", w);
     run<2>("FFMA2 + op per pair", w);
+    run<3>("FFMA2 w reused, x distinct", w);
+    run<4>("FFMA2 w, x distinct", w);
+    run<5>("FFMA w, x distinct", w);
   }
   return 0;
 }
