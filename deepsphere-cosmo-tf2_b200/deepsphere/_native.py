@@ -14,7 +14,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PKG_ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libdeepsphere_b200.so")
+# DEEPSPHERE_LIB: alternative build of the same C-ABI (A/B measurements of kernel variants on one GPU box)
+LIB_PATH = os.environ.get("DEEPSPHERE_LIB") or os.path.join(_PKG_ROOT, "lib", "libdeepsphere_b200.so")
 
 MODE_FP32, MODE_TF32, MODE_TF32X3 = 0, 1, 2
 MODES = {"fp32": MODE_FP32, "tf32": MODE_TF32, "tf32x3": MODE_TF32X3}
