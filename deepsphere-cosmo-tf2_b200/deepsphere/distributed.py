@@ -76,3 +76,46 @@ def allreduce_max(value, device):
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+class _AllReduceSum(torch.autograd.Function):
+    """Differentiable sum over ranks: d(sum_r x_r)/dx_r = 1 on every rank, so the backward pass is the same
+    all-reduce applied to the incoming gradients."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        y = x.clone()
+        dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        return g, None
+
+
+def allreduce_sum_autograd(x, group=None):
+    """Sum of `x` over all ranks, differentiable (identity for a single process)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return x
+    return _AllReduceSum.apply(x, group)
+
+
+def batch_statistics(x, dims, group=None):
+    """Per-channel mean and (biased) variance of `x` over `dims` AND over all ranks: with the batch
+    sharded over GPUs, BatchNormalization (gnn_layers.py:53, 152-153) must see the statistics of the global batch
+    to reproduce the single-device reference.  One all-reduce of [count, sum, sum of squares] (2F + 1 floats)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return x.mean(dim=dims), x.var(dim=dims, unbiased=False)
+    n = 1
+    for d in dims:
+        n *= x.shape[d]
+    stats = torch.cat([x.sum(dim=dims), (x * x).sum(dim=dims), x.new_full((1,), float(n))])
+    stats = allreduce_sum_autograd(stats, group)
+    F = x.shape[-1]
+    total = stats[2 * F]
+    mean = stats[:F] / total
+    var = (stats[F : 2 * F] / total - mean * mean).clamp_min(0.0)
+    return mean, var

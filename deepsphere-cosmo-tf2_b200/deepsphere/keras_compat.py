@@ -378,8 +378,10 @@ class BatchNormalization(Model):
     def call(self, x, training=False):
         dims = tuple(range(x.dim() - 1))
         if training:
-            mean = x.mean(dim=dims)
-            var = x.var(dim=dims, unbiased=False)
+            # batch sharded over ranks: statistics of the GLOBAL batch (one small all-reduce), see distributed.py
+            from .distributed import batch_statistics
+
+            mean, var = batch_statistics(x, dims)
             with torch.no_grad():
                 self.moving_mean.mul_(self.momentum).add_(mean.detach() * (1 - self.momentum))
                 self.moving_variance.mul_(self.momentum).add_(var.detach() * (1 - self.momentum))

@@ -110,3 +110,47 @@ def test_fused_lattice_conv_matches_oracle(mode, tol, cls, nside, B, Fin, Fout, 
     assert rel_err(xt.grad.cpu().numpy(), xr.grad.numpy()) <= tol
     assert rel_err(layer.kernel.grad.cpu().numpy(), wr.grad.numpy()) <= tol
     assert rel_err(layer.bias.grad.cpu().numpy(), br.grad.numpy()) <= tol
+
+
+def test_fused_conv2_masked_sky_tf32():
+    """ds_lattice_conv2.cu on a partial sky: tiles with holes (zero-filled lattice positions, zero weights), padded
+    index set, K = 4 on the 24 x 24 lattice plan (3 of the 4 halo rings used), bias + relu epilogue."""
+    ext = utils.extend_indices(hpx.query_disc(64, [1, 0, 0], 1.2), 64, 8)
+    g = SphereHealpix(64, indexes=ext, k=8)
+    M = len(ext)
+    torch.manual_seed(1)
+    layer = gnn_layers.Chebyshev(L=g.L, K=4, Fout=24, healpix=(64, ext), use_bias=True, activation="relu", mode="tf32")
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((3, M, 16))
+    dy = rng.standard_normal((3, M, 24))
+    xt = torch.tensor(x, dtype=torch.float32, device="cuda", requires_grad=True)
+    y = layer(xt)
+    y.backward(torch.tensor(dy, dtype=torch.float32, device="cuda"))
+    assert layer._plan.info(0)["lattice"] == 1
+    Lt, _ = orc.prepare_laplacian(g.L, 0.75)
+    xr = torch.tensor(x, requires_grad=True)
+    wr = layer.kernel.detach().double().cpu().requires_grad_(True)
+    br = layer.bias.detach().double().cpu().requires_grad_(True)
+    yr = torch.relu(orc.torch_cpu_graph_conv(xr, Lt, wr, 4, "chebyshev") + br)
+    yr.backward(torch.tensor(dy))
+    assert rel_err(y.detach().cpu().numpy(), yr.detach().numpy()) <= 1e-3
+    assert rel_err(xt.grad.cpu().numpy(), xr.grad.numpy()) <= 1e-3
+    assert rel_err(layer.kernel.grad.cpu().numpy(), wr.grad.numpy()) <= 1e-3
+
+
+def test_fused_conv2_linearity_and_batch_independence():
+    """Size-independent properties of the fused tf32 kernel at a larger shape: the layer is linear in x, and a
+    sample's output does not depend on what else is in the batch (work items are (tile, sample, chunk))."""
+    g = SphereHealpix(64, k=8)
+    M = g.L.shape[0]
+    torch.manual_seed(2)
+    layer = gnn_layers.Chebyshev(L=g.L, K=5, Fout=32, mode="tf32")
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    x1 = torch.randn(4, M, 32, device="cuda", generator=gen)
+    x2 = torch.randn(4, M, 32, device="cuda", generator=gen)
+    with torch.no_grad():
+        y1, y2, y12 = layer(x1), layer(x2), layer(x1 + 2.0 * x2)
+        scale = float(y12.abs().max())
+        assert float((y12 - (y1 + 2.0 * y2)).abs().max()) <= 2e-3 * scale  # TF32 operand truncation is not linear
+        ya = layer(x1[1:2])
+        assert torch.equal(ya[0], y1[1])  # bit-identical: same item, same arithmetic
