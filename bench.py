@@ -41,6 +41,9 @@ def parse():
     # <= 1e-3 for TF32; tf32 is the mode the register-resident fused kernel (ds_lattice_conv2.cu) serves
     ap.add_argument("--mode", default=os.environ.get("DEEPSPHERE_MODE", "tf32"), choices=["fp32", "tf32", "tf32x3"])
     ap.add_argument("--no-other-modes", action="store_true")
+    ap.add_argument("--no-model", action="store_true")
+    ap.add_argument("--model-nside", type=int, default=256)
+    ap.add_argument("--model-batch", type=int, default=16)
     ap.add_argument("--nside", type=int, default=256)
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--features", type=int, default=64)
@@ -150,6 +153,65 @@ def cpu_reference_time(L, args, batch, steps, warmup, Lt=None):
         if i >= warmup:
             times.append(t1 - t0)
     return float(np.mean(times)), algorithmic_bytes(batch, M, F, F)
+
+
+def model_train_bench(args, mode, device, world):
+    """Second half of BASELINE.json's metric: HealpyGCNN training throughput (maps/s).  The regression network of
+    SURVEY 8d config C5 (PseudoConv p=1 F16 -> [Chebyshev K5 F32 + MAX pool] x 3 -> Chebyshev K5 F64 -> pool ->
+    mean over pixels -> Dense(2)) on synthetic full-sphere maps, batch sharded over the ranks, MSE loss, Adam,
+    one flat gradient all-reduce per step.  nside 256 here (C5's nside 1024 needs the sphere-partitioned path that
+    is not built yet)."""
+    import deepsphere
+    from deepsphere import distributed as dsd
+    from deepsphere import healpy_layers as hl, keras_compat as kc
+
+    nside, Bm = args.model_nside, args.model_batch
+    npix = 12 * nside * nside
+    kw = dict(use_bias=True, activation="relu", mode=mode)
+    layers = [hl.HealpyPseudoConv(p=1, Fout=16, activation="relu")]
+    for _ in range(3):
+        layers += [hl.HealpyChebyshev(K=5, Fout=32, **kw), hl.HealpyPool(p=1, pool_type="MAX")]
+    layers += [hl.HealpyChebyshev(K=5, Fout=64, **kw), hl.HealpyPool(p=1, pool_type="AVG"),
+               kc.Lambda(lambda t: t.mean(dim=1)), kc.Dense(2)]
+    torch.manual_seed(11)
+    model = deepsphere.HealpyGCNN(nside=nside, indices=np.arange(npix), layers=layers)
+    model.build(input_shape=(None, npix, 1))
+    dsd.broadcast_parameters(model)
+    params = model.trainable_variables
+    opt = torch.optim.Adam(params, lr=1e-3)
+    gen = torch.Generator(device=device).manual_seed(11 + int(os.environ.get("RANK", "0")))
+    x = torch.randn(Bm, npix, 1, device=device, generator=gen)
+    t = torch.randn(Bm, 2, device=device, generator=gen)
+
+    def train_step():
+        opt.zero_grad(set_to_none=True)
+        loss = ((model(x, training=True) - t) ** 2).mean()
+        loss.backward()
+        dsd.allreduce_gradients(params)
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        train_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+    n = 10
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        loss = train_step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = dsd.allreduce_max(a.elapsed_time(b) / n, device)
+    n_params = int(sum(p.numel() for p in params))
+    del model, opt, x, t
+    torch.cuda.empty_cache()
+    return {"metric": "HealpyGCNN train maps/s", "value": world * Bm / (ms * 1e-3), "unit": "maps/s",
+            "ms_per_step": ms, "batch_per_gpu": Bm, "n_gpus": world, "parameters": n_params, "final_loss": float(loss),
+            "config": f"nside {nside} full sphere ({npix} px): PseudoConv p1 F16 -> [Chebyshev K5 F32 + MAX pool] x3 -> "
+                      f"Chebyshev K5 F64 -> AVG pool -> mean -> Dense(2); MSE, Adam, fwd+bwd+all-reduce+step, mode {mode}"}
 
 
 def main():
@@ -318,6 +380,14 @@ def main():
                 layer.mode = mode
                 torch.cuda.empty_cache()
 
+    # ---- HealpyGCNN training throughput (the second half of the metric) ------------------------------
+    model_train = None
+    if not args.no_model:
+        try:
+            model_train = model_train_bench(args, mode, device, world)
+        except Exception as exc:
+            model_train = {"error": str(exc)[:200]}
+
     # ---- e2e: public layer API, pinned host buffers, H2D + D2H inside the timed region ------------
     e2e = None
     if not args.no_e2e:
@@ -418,7 +488,7 @@ def main():
             "config": {"workload": f"HealpyChebyshev layer nside {args.nside} (M={M}) K {K} Fin=Fout={F} "
                                    f"batch {B}/GPU fwd+bwd, 8-neighbour HEALPix graph",
                        "mode": mode, "parallelism": f"batch-sharded x{world}", "l2": "inputs (6.4 GB/tensor) >> L2"},
-            "roofline": roofline, "layer_roofline": layer_roofline, "kernels": kernels, "other_modes": other_modes,
+            "roofline": roofline, "layer_roofline": layer_roofline, "kernels": kernels, "other_modes": other_modes, "model_train": model_train,
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
         }
         print(json.dumps(line))
