@@ -250,14 +250,25 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(int64_t R, int64_t 
   }
 }
 
-__global__ void colsum_final_kernel(int64_t Ncols, int64_t F, int nblk, const float* __restrict__ partial,
-                                    float* __restrict__ out) {
-  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= F) return;
+// out[f] = sum over blocks and folded columns (c = f, f + F, ...) of partial[b][c]; 32 outputs per CTA, 8 thread
+// groups split the blocks (fixed order: deterministic), combined through shared memory
+__global__ void __launch_bounds__(256) colsum_final_kernel(int64_t Ncols, int64_t F, int nblk,
+                                                            const float* __restrict__ partial, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int64_t f = (int64_t)blockIdx.x * 32 + cl;
   float s = 0.f;
-  for (int b = 0; b < nblk; ++b)
-    for (int64_t c = f; c < Ncols; c += F) s += partial[(int64_t)b * Ncols + c];
-  out[f] = s;
+  if (f < F)
+    for (int b = g; b < nblk; b += 8)
+      for (int64_t c = f; c < Ncols; c += F) s += __ldg(partial + (int64_t)b * Ncols + c);
+  red[g][cl] = s;
+  __syncthreads();
+  if (g == 0 && f < F) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][cl];
+    out[f] = t;
+  }
 }
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -344,7 +355,7 @@ int launch_colsum(int64_t R, int64_t Ncols, int64_t F, const float* Z, float* ou
   const int nblk = (int)std::max<int64_t>(1, std::min<int64_t>(COLSUM_BLOCKS, cdiv(R, 64)));
   colsum_partial_kernel<<<nblk, 256, 0, st>>>(R, Ncols, Z, workspace);
   DS_LAUNCHED();
-  colsum_final_kernel<<<(unsigned)cdiv(F, 128), 128, 0, st>>>(Ncols, F, nblk, workspace, out);
+  colsum_final_kernel<<<(unsigned)cdiv(F, 32), 256, 0, st>>>(Ncols, F, nblk, workspace, out);
   DS_LAUNCHED();
   return 0;
 }
