@@ -87,6 +87,13 @@ int64_t ds_graph_conv_basis_elems(int64_t M, int64_t B, int64_t Fin, int32_t K) 
   return K > 1 ? (int64_t)(K - 1) * B * M * Fin : 0;
 }
 
+int32_t ds_graph_conv_forward_writes_basis(const ds_plan_t* plan, int32_t K, int64_t B, int64_t Fin, int64_t Fout,
+                                           int32_t mode) {
+  using namespace ds;
+  if (plan == nullptr || K <= 1) return 0;
+  return fused_conv_usable(plan, K, B, Fin, Fout, mode) ? 0 : 1;
+}
+
 int ds_graph_conv_basis(const ds_plan_t* plan, int32_t recursion, int32_t K, int64_t B, int64_t F, const float* x,
                         float* basis, int32_t transpose, void* stream) {
   using namespace ds;
@@ -101,10 +108,12 @@ int ds_graph_conv_forward(const ds_plan_t* plan, int32_t recursion, int32_t K, i
   using namespace ds;
   DS_TRY(check_common(plan, recursion, K, B, Fin, Fout, act, mode, "ds_graph_conv_forward"));
   DS_CHECK(x && kernel && y, "ds_graph_conv_forward: NULL tensor");
-  DS_CHECK(K == 1 || basis != nullptr, "ds_graph_conv_forward: basis workspace required for K > 1");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t M = plan->M, R = B * M, A = R * Fin;
-  if (fused_conv_usable(plan, K, B, Fin, Fout, mode)) {
+  const bool fused_fwd = fused_conv_usable(plan, K, B, Fin, Fout, mode);
+  DS_CHECK(K == 1 || fused_fwd || basis != nullptr,
+           "ds_graph_conv_forward: basis workspace required for K > 1 (see ds_graph_conv_forward_writes_basis)");
+  if (fused_fwd) {
     // recursion + contraction in one kernel; the basis never leaves the chip (and `basis` is left untouched:
     // the fused backward does not need it)
     return fused_conv(plan, recursion, K, B, Fin, Fout, x, nullptr, kernel, (int64_t)K * Fout, Fout, 1, bias, act, y,

@@ -39,6 +39,7 @@ SIGNATURES = {
     ),
     "ds_spmm": (ctypes.c_int, [_ptr, _i32, _i64, _i64, _ptr, _f32, _ptr, _f32, _ptr, _f32, _ptr, _ptr]),
     "ds_graph_conv_basis_elems": (_i64, [_i64, _i64, _i64, _i32]),
+    "ds_graph_conv_forward_writes_basis": (_i32, [_ptr, _i32, _i64, _i64, _i64, _i32]),
     "ds_graph_conv_basis": (ctypes.c_int, [_ptr, _i32, _i32, _i64, _i64, _ptr, _ptr, _i32, _ptr]),
     "ds_graph_conv_forward": (
         ctypes.c_int,

@@ -39,8 +39,10 @@ class _GraphConv(torch.autograd.Function):
         dev = x.device.index
         h = plan.handle(dev)
         y = torch.empty((B, M, Fout), device=x.device, dtype=torch.float32)
-        n_basis = nat.lib().ds_graph_conv_basis_elems(M, B, Fin, K)
-        basis = torch.empty(max(n_basis, 1), device=x.device, dtype=torch.float32)
+        # the fused lattice kernel keeps the basis on chip: nothing to allocate, and the backward gets basis = NULL
+        writes = nat.lib().ds_graph_conv_forward_writes_basis(h, K, B, Fin, Fout, mode)
+        n_basis = nat.lib().ds_graph_conv_basis_elems(M, B, Fin, K) if writes else 0
+        basis = torch.empty(n_basis, device=x.device, dtype=torch.float32) if n_basis > 0 else None
         with torch.cuda.device(dev):
             nat.check(
                 nat.lib().ds_graph_conv_forward(

@@ -113,6 +113,11 @@ int ds_spmm(const ds_plan_t* plan, int32_t transpose, int64_t B, int64_t F, cons
  * ([K-1, B, M, Fin]) and may be handed to ds_graph_conv_backward to skip recomputation.
  */
 int64_t ds_graph_conv_basis_elems(int64_t M, int64_t B, int64_t Fin, int32_t K);
+/* 1 if ds_graph_conv_forward with these arguments writes `basis` (recursion and contraction are separate
+ * kernels), 0 if it runs the fused lattice kernel, which keeps the basis on chip: `basis` may then be NULL and
+ * ds_graph_conv_backward must be called with basis = NULL (it recomputes what it needs). */
+int32_t ds_graph_conv_forward_writes_basis(const ds_plan_t* plan, int32_t K, int64_t B, int64_t Fin, int64_t Fout,
+                                           int32_t mode);
 /* only the recursion of gnn_layers.py:135-143 / :287-290: basis[k-1] = T_k(L~) x for k = 1..K-1 (L~^T when
  * transpose != 0).  On a HEALPix 8-neighbour graph with a lattice attachment all K-1 hops run fused in one
  * kernel; otherwise one streaming hop kernel per k. */

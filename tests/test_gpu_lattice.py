@@ -80,7 +80,7 @@ def test_lattice_masked_sky():
 @pytest.mark.parametrize("mode,tol", [("tf32", 1e-3), ("tf32x3", 2e-5)])
 @pytest.mark.parametrize("cls", ["Chebyshev", "Monomial"])
 @pytest.mark.parametrize("nside,B,Fin,Fout,K", [(32, 2, 16, 16, 5), (64, 2, 64, 64, 5), (32, 3, 32, 16, 3),
-                                                (32, 2, 16, 64, 2), (32, 1, 48, 32, 4)])
+                                                (32, 2, 16, 64, 2), (32, 1, 48, 32, 4), (32, 2, 24, 80, 5)])
 def test_fused_lattice_conv_matches_oracle(mode, tol, cls, nside, B, Fin, Fout, K):
     """ds_lattice_conv.cu: recursion + tcgen05 contraction in one kernel (forward), and the same kernel on dz
     plus the transposed weight-gradient contraction (backward), against the float64 oracle."""
@@ -155,3 +155,29 @@ def test_fused_conv2_linearity_and_batch_independence():
         assert float((y12 - (y1 + 2.0 * y2)).abs().max()) <= 2e-3 * scale  # TF32 operand truncation is not linear
         ya = layer(x1[1:2])
         assert float((ya[0] - y1[1]).abs().max()) <= 1e-6 * scale  # same items, same arithmetic
+
+
+def test_fused_forward_without_input_gradient():
+    """First layer of a network: x does not require a gradient, so the backward takes the non-fused weight-gradient
+    path and must recompute the basis the fused forward never wrote (ds_graph_conv_forward_writes_basis == 0)."""
+    g = SphereHealpix(32, k=8)
+    M = g.L.shape[0]
+    torch.manual_seed(4)
+    layer = gnn_layers.Chebyshev(L=g.L, K=5, Fout=32, use_bias=True, mode="tf32")
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((2, M, 16))
+    dy = rng.standard_normal((2, M, 32))
+    xt = torch.tensor(x, dtype=torch.float32, device="cuda")  # requires_grad = False
+    y = layer(xt)
+    y.backward(torch.tensor(dy, dtype=torch.float32, device="cuda"))
+    h = layer._plan.handle(0)
+    assert nat.lib().ds_graph_conv_forward_writes_basis(h, 5, 2, 16, 32, nat.MODES["tf32"]) == 0
+    assert nat.lib().ds_graph_conv_forward_writes_basis(h, 5, 2, 16, 32, nat.MODES["fp32"]) == 1
+    Lt, _ = orc.prepare_laplacian(g.L, 0.75)
+    wr = layer.kernel.detach().double().cpu().requires_grad_(True)
+    br = layer.bias.detach().double().cpu().requires_grad_(True)
+    yr = orc.torch_cpu_graph_conv(torch.tensor(x), Lt, wr, 5, "chebyshev") + br
+    yr.backward(torch.tensor(dy))
+    assert rel_err(y.detach().cpu().numpy(), yr.detach().numpy()) <= 1e-3
+    assert rel_err(layer.kernel.grad.cpu().numpy(), wr.grad.numpy()) <= 1e-3
+    assert rel_err(layer.bias.grad.cpu().numpy(), br.grad.numpy()) <= 1e-3
