@@ -73,11 +73,15 @@ class _GraphConvBase(Model):
         # optional HEALPix geometry (nside, NESTED pixel ids of the rows of L): enables the fused lattice
         # kernel; HealpyGCNN provides it, and a full-sphere Laplacian is recognised automatically
         self._healpix = kwargs.pop("healpix", None)
+        # largest eigenvalue of L supplied by the caller (skips ARPACK): the sphere-partitioned layer passes the
+        # GLOBAL value so that every rank's restricted Laplacian is the restriction of the same L~
+        lmax_given = kwargs.pop("lmax", None)
         self.kwargs = kwargs
 
         # gnn_layers.py:64-72: rescale the Laplacian and keep it as COO (indices, values, shape)
         Lc = _to_csr(L)
-        lmax = 1.02 * eigsh(Lc, k=1, which="LM", return_eigenvectors=False)[0]
+        lmax = float(lmax_given) if lmax_given is not None else \
+            1.02 * eigsh(Lc, k=1, which="LM", return_eigenvectors=False)[0]
         self.lmax = float(lmax)
         Lc = utils.rescale_L(Lc, lmax=lmax, scale=self._scale)
         L_coo = Lc.tocoo()

@@ -1,0 +1,178 @@
+"""Sphere partition with halo exchange: one sphere spread over the ranks of a process group.
+
+The reference is single-device.  Here rank r owns a contiguous range of the rows of L (for a NESTED full sphere:
+whole base-pixel blocks, so pooling / pseudo-convolutions with 4^p | block stay local) and, per graph-convolution
+layer, needs the (K-1)-hop neighbourhood of its rows.  Schedule (i) of SURVEY 8e.2 is implemented: ONE exchange of
+the (K-1)-ring halo per layer, then the unchanged single-GPU layer (fused lattice kernel included: the extended row
+set is just a masked sky) on own + halo rows; results are exact on the own rows and the redundant halo rows are
+dropped.  The halo set is derived from the sparsity of L by K-1 rounds of neighbour expansion on the host - never
+from a ring count - so k = 20/40/60 graphs and masked skies work the same way.
+
+Backward: the exchange is a torch.autograd.Function whose backward is the transposed exchange (gradients of halo
+rows travel back to their owners and are added).  Weight gradients are partial sums over the own rows (the loss
+only sees own rows, so dy is zero on the halo): sum them over the group (`distributed.allreduce_gradients(...,
+average=False)`).
+
+Collectives: all_to_all_single with per-peer row counts (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+"""
+
+import numpy as np
+import torch
+import torch.distributed as dist
+from scipy import sparse
+
+from .distributed import shard_range
+
+
+def _closure(pattern, rows, n_hops):
+    """Rows within n_hops of `rows` in the graph of the (structurally symmetric) sparse `pattern`."""
+    M = pattern.shape[0]
+    mask = np.zeros(M, dtype=bool)
+    mask[rows] = True
+    frontier = mask.copy()
+    for _ in range(int(n_hops)):
+        reach = (pattern @ frontier.astype(np.float32)) > 0
+        frontier = reach & ~mask
+        if not frontier.any():
+            break
+        mask |= frontier
+    return np.flatnonzero(mask)
+
+
+class HaloPlan:
+    """Who owns what and who sends which rows to whom, for `n_hops` hops over the sparsity of L.
+
+    Every rank computes the full plan from the (replicated, host-side) Laplacian, so no negotiation is needed.
+    own[r]     = [begin, end) of rank r (multiples of `align`)
+    ext        = sorted global rows this rank computes on (own + halo)
+    own_pos    = positions of the own rows inside ext
+    send_rows[q] = LOCAL (own-relative) rows sent to rank q;  recv_pos[q] = positions in ext filled by rank q
+    """
+
+    def __init__(self, L, n_hops, rank, world, align=1):
+        L = sparse.csr_matrix(L)
+        M = L.shape[0]
+        if M % align:
+            raise ValueError(f"{M} rows are not a multiple of align={align}")
+        pattern = sparse.csr_matrix((np.ones(L.nnz, dtype=np.float32), L.indices, L.indptr), shape=L.shape)
+        pattern = pattern + pattern.T  # expansion must be symmetric: row i needs j  <=>  L[i, j] != 0
+        units = M // align
+        self.rank, self.world, self.M, self.n_hops = int(rank), int(world), M, int(n_hops)
+        self.own = [tuple(align * v for v in shard_range(units, r, world)) for r in range(world)]
+        owner_of = np.empty(M, dtype=np.int32)
+        for r, (b, e) in enumerate(self.own):
+            owner_of[b:e] = r
+        exts = [_closure(pattern, np.arange(b, e), n_hops) for (b, e) in self.own]
+        b0, e0 = self.own[rank]
+        self.ext = exts[rank]
+        self.own_pos = np.searchsorted(self.ext, np.arange(b0, e0))
+        self.send_rows, self.recv_pos = [], []
+        for q in range(world):
+            if q == rank:
+                self.send_rows.append(np.zeros(0, dtype=np.int64))
+                self.recv_pos.append(np.zeros(0, dtype=np.int64))
+                continue
+            need_q = exts[q][owner_of[exts[q]] == rank]          # rows of mine in q's extended set
+            self.send_rows.append((need_q - b0).astype(np.int64))
+            mine_from_q = self.ext[owner_of[self.ext] == q]      # rows of q in my extended set
+            self.recv_pos.append(np.searchsorted(self.ext, mine_from_q).astype(np.int64))
+        self.n_own, self.n_ext = e0 - b0, len(self.ext)
+        self.halo_rows = self.n_ext - self.n_own
+
+    def restrict(self, L):
+        """L restricted to the extended row set (rows and columns), CSR."""
+        L = sparse.csr_matrix(L)
+        return L[self.ext][:, self.ext].tocsr()
+
+
+class _HaloExchange(torch.autograd.Function):
+    """x_own [B, n_own, F] -> x_ext [B, n_ext, F]; backward = transposed exchange (halo gradients are returned to
+    their owners and added)."""
+
+    @staticmethod
+    def forward(ctx, x_own, plan, group):
+        ctx.plan, ctx.group = plan, group
+        return _exchange(x_own, plan, group)
+
+    @staticmethod
+    def backward(ctx, g_ext):
+        plan, group = ctx.plan, ctx.group
+        g_ext = g_ext.contiguous()
+        dev = g_ext.device
+        B, _, F = g_ext.shape
+        g_own = g_ext[:, torch.as_tensor(plan.own_pos, device=dev), :].clone()
+        # send back what I received (halo positions), receive what I sent (own rows) and accumulate
+        send = [g_ext[:, torch.as_tensor(plan.recv_pos[q], device=dev), :].permute(1, 0, 2).reshape(-1)
+                for q in range(plan.world)]
+        counts_out = [len(plan.recv_pos[q]) * B * F for q in range(plan.world)]
+        counts_in = [len(plan.send_rows[q]) * B * F for q in range(plan.world)]
+        recv = _all_to_all(torch.cat(send) if send else g_ext.new_zeros(0), counts_out, counts_in, group)
+        off = 0
+        for q in range(plan.world):
+            n = len(plan.send_rows[q])
+            if n:
+                blk = recv[off: off + n * B * F].reshape(n, B, F).permute(1, 0, 2)
+                g_own.index_add_(1, torch.as_tensor(plan.send_rows[q], device=dev), blk)
+            off += n * B * F
+        return g_own, None, None
+
+
+def _all_to_all(flat, counts_out, counts_in, group):
+    out = flat.new_empty(int(sum(counts_in)))
+    dist.all_to_all_single(out, flat.contiguous(), output_split_sizes=[int(c) for c in counts_in],
+                           input_split_sizes=[int(c) for c in counts_out], group=group)
+    return out
+
+
+def _exchange(x_own, plan, group):
+    x_own = x_own.contiguous()
+    dev = x_own.device
+    B, n_own, F = x_own.shape
+    if n_own != plan.n_own:
+        raise ValueError(f"rank {plan.rank} owns {plan.n_own} rows, got a tensor with {n_own}")
+    x_ext = x_own.new_empty((B, plan.n_ext, F))
+    x_ext[:, torch.as_tensor(plan.own_pos, device=dev), :] = x_own
+    # rows go out row-major ([row, b, f]) so that a peer's block is contiguous
+    send = [x_own[:, torch.as_tensor(plan.send_rows[q], device=dev), :].permute(1, 0, 2).reshape(-1)
+            for q in range(plan.world)]
+    counts_out = [len(plan.send_rows[q]) * B * F for q in range(plan.world)]
+    counts_in = [len(plan.recv_pos[q]) * B * F for q in range(plan.world)]
+    recv = _all_to_all(torch.cat(send), counts_out, counts_in, group)
+    off = 0
+    for q in range(plan.world):
+        n = len(plan.recv_pos[q])
+        if n:
+            x_ext[:, torch.as_tensor(plan.recv_pos[q], device=dev), :] = recv[off: off + n * B * F].reshape(n, B, F).permute(1, 0, 2)
+        off += n * B * F
+    return x_ext
+
+
+def halo_exchange(x_own, plan, group=None):
+    """Differentiable gather of the halo rows: [B, n_own, F] -> [B, n_ext, F] (rows ordered like plan.ext)."""
+    return _HaloExchange.apply(x_own, plan, group)
+
+
+class PartitionedGraphConv(torch.nn.Module):
+    """A graph convolution on a row-partitioned sphere: y_own = conv_ext(halo_exchange(x_own))[own rows].
+
+    `make_layer(L_ext, ext_rows)` builds the single-device layer on the restricted Laplacian (e.g.
+    `lambda L, rows: Chebyshev(L=L, K=5, Fout=64, lmax=lmax_global, healpix=(nside, pix[rows]))`); its weights must
+    be identical on all ranks (broadcast them) and their gradients summed over the group after backward."""
+
+    def __init__(self, L, n_hops, make_layer, rank=None, world=None, group=None, align=1):
+        super().__init__()
+        if rank is None:
+            rank = dist.get_rank(group)
+        if world is None:
+            world = dist.get_world_size(group)
+        self.group = group
+        self.plan = HaloPlan(L, n_hops, rank, world, align)
+        self.layer = make_layer(self.plan.restrict(L), self.plan.ext)
+        self._own_pos = None
+
+    def forward(self, x_own, *args, **kwargs):
+        x_ext = halo_exchange(x_own, self.plan, self.group)
+        y_ext = self.layer(x_ext, *args, **kwargs)
+        if self._own_pos is None or self._own_pos.device != y_ext.device:
+            self._own_pos = torch.as_tensor(self.plan.own_pos, device=y_ext.device)
+        return y_ext.index_select(1, self._own_pos)

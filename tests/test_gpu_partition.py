@@ -1,0 +1,83 @@
+"""Sphere partition with halo exchange on 2 GPUs (NCCL): the CUDA Chebyshev layer on each rank's own + halo rows
+reproduces the single-GPU layer on the whole sphere - forward, input gradient, weight gradient.  Needs >= 2 GPUs."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+NSIDE, K, F_IN, F_OUT, B = 32, 5, 16, 16, 2
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, mode, tol, out_dir):
+    import torch.distributed as dist
+    from scipy.sparse.linalg import eigsh
+
+    from deepsphere import distributed as dsd
+    from deepsphere import gnn_layers, partition
+    from deepsphere.graph import SphereHealpix
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dsd.init_from_env(backend="nccl")
+    dev = torch.device("cuda", rank)
+    g = SphereHealpix(NSIDE, k=8)
+    M = g.L.shape[0]
+    lmax = 1.02 * eigsh(g.L.astype(np.float64), k=1, which="LM", return_eigenvectors=False)[0]
+    pix = np.arange(M)
+
+    def make(L_ext, rows):
+        torch.manual_seed(0)
+        layer = gnn_layers.Chebyshev(L=L_ext, K=K, Fout=F_OUT, lmax=lmax, healpix=(NSIDE, pix[rows]), mode=mode)
+        layer.build_from_shape((B, len(rows), F_IN))
+        return layer
+
+    conv = partition.PartitionedGraphConv(g.L, K - 1, make, align=256)
+    dsd.broadcast_parameters(conv.layer)
+    torch.manual_seed(0)
+    whole = gnn_layers.Chebyshev(L=g.L, K=K, Fout=F_OUT, lmax=lmax, mode=mode)
+    whole.build_from_shape((B, M, F_IN))
+    with torch.no_grad():
+        whole.kernel.copy_(conv.layer.kernel)
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(B, M, F_IN, generator=gen).to(dev)
+    dy = torch.randn(B, M, F_OUT, generator=gen).to(dev)
+    b, e = conv.plan.own[rank]
+    x_own = x[:, b:e].clone().requires_grad_(True)
+    y_own = conv(x_own)
+    y_own.backward(dy[:, b:e].contiguous())
+    dsd.allreduce_gradients([conv.layer.kernel], average=False)
+    xg = x.clone().requires_grad_(True)
+    y = whole(xg)
+    y.backward(dy)
+    torch.cuda.synchronize()
+
+    def rel(a, ref):
+        return float((a - ref).abs().max() / ref.abs().max())
+
+    errs = (rel(y_own.detach(), y.detach()[:, b:e]), rel(x_own.grad, xg.grad[:, b:e]),
+            rel(conv.layer.kernel.grad, whole.kernel.grad))
+    np.save(os.path.join(out_dir, f"err{rank}.npy"), np.array(errs + (conv.plan.n_own, conv.plan.n_ext,
+                                                                    conv.layer._plan.info(rank)["lattice"])))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-5), ("tf32", 2e-3)])
+def test_partitioned_chebyshev_two_gpus(tmp_path, mode, tol):
+    import torch.multiprocessing as mp
+
+    mp.spawn(_worker, args=(2, _free_port(), mode, tol, str(tmp_path)), nprocs=2, join=True)
+    for r in (0, 1):
+        ey, edx, edw, n_own, n_ext, lattice = np.load(tmp_path / f"err{r}.npy")
+        assert n_ext > n_own
+        assert ey <= tol and edx <= tol and edw <= tol, (mode, r, ey, edx, edw)
