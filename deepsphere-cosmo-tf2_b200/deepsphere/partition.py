@@ -78,6 +78,18 @@ class HaloPlan:
             self.recv_pos.append(np.searchsorted(self.ext, mine_from_q).astype(np.int64))
         self.n_own, self.n_ext = e0 - b0, len(self.ext)
         self.halo_rows = self.n_ext - self.n_own
+        # the own rows are one interval of the sorted extended set: the exchange copies them as a slice
+        self.own_start = int(self.own_pos[0]) if self.n_own else 0
+        assert self.n_own == 0 or np.array_equal(self.own_pos, self.own_start + np.arange(self.n_own))
+        self._dev = {}
+
+    def on(self, device):
+        """Index tensors of the exchange, resident on `device` (uploaded once)."""
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = ([torch.as_tensor(v, device=device) for v in self.send_rows],
+                              [torch.as_tensor(v, device=device) for v in self.recv_pos])
+        return self._dev[key]
 
     def restrict(self, L):
         """L restricted to the extended row set (rows and columns), CSR."""
@@ -98,12 +110,11 @@ class _HaloExchange(torch.autograd.Function):
     def backward(ctx, g_ext):
         plan, group = ctx.plan, ctx.group
         g_ext = g_ext.contiguous()
-        dev = g_ext.device
         B, _, F = g_ext.shape
-        g_own = g_ext[:, torch.as_tensor(plan.own_pos, device=dev), :].clone()
+        send_idx, recv_idx = plan.on(g_ext.device)
+        g_own = g_ext[:, plan.own_start: plan.own_start + plan.n_own, :].clone()
         # send back what I received (halo positions), receive what I sent (own rows) and accumulate
-        send = [g_ext[:, torch.as_tensor(plan.recv_pos[q], device=dev), :].permute(1, 0, 2).reshape(-1)
-                for q in range(plan.world)]
+        send = [g_ext.index_select(1, recv_idx[q]).permute(1, 0, 2).reshape(-1) for q in range(plan.world)]
         counts_out = [len(plan.recv_pos[q]) * B * F for q in range(plan.world)]
         counts_in = [len(plan.send_rows[q]) * B * F for q in range(plan.world)]
         recv = _all_to_all(torch.cat(send) if send else g_ext.new_zeros(0), counts_out, counts_in, group)
@@ -112,13 +123,15 @@ class _HaloExchange(torch.autograd.Function):
             n = len(plan.send_rows[q])
             if n:
                 blk = recv[off: off + n * B * F].reshape(n, B, F).permute(1, 0, 2)
-                g_own.index_add_(1, torch.as_tensor(plan.send_rows[q], device=dev), blk)
+                g_own.index_add_(1, send_idx[q], blk)
             off += n * B * F
         return g_own, None, None
 
 
 def _all_to_all(flat, counts_out, counts_in, group):
     out = flat.new_empty(int(sum(counts_in)))
+    if not dist.is_initialized():  # single process: nothing to exchange
+        return out
     dist.all_to_all_single(out, flat.contiguous(), output_split_sizes=[int(c) for c in counts_in],
                            input_split_sizes=[int(c) for c in counts_out], group=group)
     return out
@@ -126,15 +139,14 @@ def _all_to_all(flat, counts_out, counts_in, group):
 
 def _exchange(x_own, plan, group):
     x_own = x_own.contiguous()
-    dev = x_own.device
     B, n_own, F = x_own.shape
     if n_own != plan.n_own:
         raise ValueError(f"rank {plan.rank} owns {plan.n_own} rows, got a tensor with {n_own}")
+    send_idx, recv_idx = plan.on(x_own.device)
     x_ext = x_own.new_empty((B, plan.n_ext, F))
-    x_ext[:, torch.as_tensor(plan.own_pos, device=dev), :] = x_own
+    x_ext[:, plan.own_start: plan.own_start + n_own, :] = x_own
     # rows go out row-major ([row, b, f]) so that a peer's block is contiguous
-    send = [x_own[:, torch.as_tensor(plan.send_rows[q], device=dev), :].permute(1, 0, 2).reshape(-1)
-            for q in range(plan.world)]
+    send = [x_own.index_select(1, send_idx[q]).permute(1, 0, 2).reshape(-1) for q in range(plan.world)]
     counts_out = [len(plan.send_rows[q]) * B * F for q in range(plan.world)]
     counts_in = [len(plan.recv_pos[q]) * B * F for q in range(plan.world)]
     recv = _all_to_all(torch.cat(send), counts_out, counts_in, group)
@@ -142,7 +154,7 @@ def _exchange(x_own, plan, group):
     for q in range(plan.world):
         n = len(plan.recv_pos[q])
         if n:
-            x_ext[:, torch.as_tensor(plan.recv_pos[q], device=dev), :] = recv[off: off + n * B * F].reshape(n, B, F).permute(1, 0, 2)
+            x_ext.index_copy_(1, recv_idx[q], recv[off: off + n * B * F].reshape(n, B, F).permute(1, 0, 2))
         off += n * B * F
     return x_ext
 
@@ -162,17 +174,14 @@ class PartitionedGraphConv(torch.nn.Module):
     def __init__(self, L, n_hops, make_layer, rank=None, world=None, group=None, align=1):
         super().__init__()
         if rank is None:
-            rank = dist.get_rank(group)
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
         if world is None:
-            world = dist.get_world_size(group)
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.group = group
         self.plan = HaloPlan(L, n_hops, rank, world, align)
         self.layer = make_layer(self.plan.restrict(L), self.plan.ext)
-        self._own_pos = None
 
     def forward(self, x_own, *args, **kwargs):
         x_ext = halo_exchange(x_own, self.plan, self.group)
         y_ext = self.layer(x_ext, *args, **kwargs)
-        if self._own_pos is None or self._own_pos.device != y_ext.device:
-            self._own_pos = torch.as_tensor(self.plan.own_pos, device=y_ext.device)
-        return y_ext.index_select(1, self._own_pos)
+        return y_ext[:, self.plan.own_start: self.plan.own_start + self.plan.n_own, :]
