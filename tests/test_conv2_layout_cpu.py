@@ -1,0 +1,89 @@
+"""Index arithmetic of the register-resident fused kernel (csrc/ds_lattice_conv2.cu), restated in numpy: the
+de-interleaved exchange layout, the perimeter offsets of a 3x3 block, the UMMA operand rows <-> lattice positions of the
+epilogue, the gather mapping of the loader warps and the stencil direction table.  CPU only - guards the constants
+the kernel hard-codes."""
+import re
+import os
+
+import numpy as np
+
+from deepsphere import healpix as hpx
+
+LW, H, T = 24, 4, 16
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = open(os.path.join(ROOT, "deepsphere-cosmo-tf2_b200", "csrc", "ds_lattice_conv2.cu")).read()
+
+
+def pos(j, c):
+    """float4 index inside a plane of lattice (row j, column c): one pad row above, columns de-interleaved mod 3."""
+    return (j + 1) * LW + (c % 3) * 8 + c // 3
+
+
+def test_layout_is_a_bijection_and_quarter_warps_are_contiguous():
+    p = np.array([[pos(j, c) for c in range(LW)] for j in range(LW)])
+    assert len(np.unique(p)) == LW * LW and p.min() == LW and p.max() == (LW + 1) * LW - 1
+    # the 8 column blocks cb = 0..7 of one block row and one in-block column cc are 8 consecutive positions
+    for j in range(LW):
+        for cc in range(3):
+            q = [pos(j, 3 * cb + cc) for cb in range(8)]
+            assert q == list(range(q[0], q[0] + 8))
+
+
+def test_perimeter_offsets_of_a_block():
+    """Columns -1, 0, 1, 2, 3 relative to the block's column 0 sit at +15, +0, +8, +16, +1 (kernel constant CO)."""
+    co = [int(v) for v in re.search(r"constexpr int CO\[5\] = \{([^}]*)\}", SRC).group(1).split(",")]
+    assert co == [15, 0, 8, 16, 1]
+    for cb in range(1, 7):  # interior column blocks: all five columns exist
+        base = pos(5, 3 * cb)
+        for k, dc in enumerate(range(-1, 4)):
+            assert pos(5, 3 * cb + dc) == base + co[k]
+    # the wrap-around of the outermost blocks stays inside the row (only ever feeds don't-care ring positions)
+    assert pos(5, 0) + 15 == pos(5, 22) and pos(5, 21) + 1 == pos(5, 1)
+
+
+def test_operand_rows_map_back_to_lattice_positions():
+    """UMMA A operand = positions of lattice rows 4..19 (384 rows, 3 M-tiles); the epilogue maps accumulator row m to
+    (row, column) with j = 4 + m / 24, p = m % 24, c = 3 * (p & 7) + (p >> 3)."""
+    start = (H + 1) * LW  # plane offset of lattice row 4, position 0
+    seen = set()
+    for m in range(3 * 128):
+        j, p = H + m // LW, m % LW
+        c = 3 * (p & 7) + (p >> 3)
+        assert pos(j, c) == start + m
+        if H <= c < H + T:
+            seen.add((j, c))
+    assert seen == {(j, c) for j in range(H, H + T) for c in range(H, H + T)}  # every own pixel exactly once
+
+
+def test_loader_mapping_covers_every_position_once():
+    """96 gather threads: t -> (q = t & 1, pl0 = t >> 1), in-row position pl0 % 24, rows 2k + pl0 / 24, k < 12."""
+    hit = np.zeros((2, LW, LW), dtype=int)
+    for t in range(96):
+        q, pl0 = t & 1, t >> 1
+        inpos, r0 = pl0 % LW, pl0 // LW
+        col = 3 * (inpos & 7) + (inpos >> 3)
+        for k in range(LW // 2):
+            row = 2 * k + r0
+            assert pos(row, col) == (row + 1) * LW + inpos
+            hit[q, row, col] += 1
+    assert (hit == 1).all()
+
+
+def test_direction_table_matches_the_plan_builder():
+    """dir_of(drow, dcol) of the kernel == index of (di = dcol, dj = drow) in lattice.py's (NB_XOFF, NB_YOFF), 8 = centre."""
+    def dir_of(dr, dc):
+        if dr == 0:
+            return 0 if dc < 0 else (4 if dc > 0 else 8)
+        if dr > 0:
+            return 1 if dc < 0 else (2 if dc == 0 else 3)
+        return 5 if dc > 0 else (6 if dc == 0 else 7)
+
+    for dr in (-1, 0, 1):
+        for dc in (-1, 0, 1):
+            if dr == 0 and dc == 0:
+                assert dir_of(dr, dc) == 8
+                continue
+            d = int(np.flatnonzero((np.asarray(hpx.NB_XOFF) == dc) & (np.asarray(hpx.NB_YOFF) == dr))[0])
+            assert dir_of(dr, dc) == d
+    # and the C++ source spells the same table
+    assert "dr == 0 ? (dc < 0 ? 0 : (dc > 0 ? 4 : 8))" in SRC
