@@ -22,7 +22,7 @@ int umma_tn_supported(int64_t R, int64_t N, int64_t Kc, int nseg);
 int64_t umma_tn_workspace_elems(int64_t R, int64_t N, int64_t Kc, int nseg);
 int launch_umma_gemm_tn(int64_t R, int64_t N, int64_t Kc, int nseg, const float* A0, const float* Arest, const float* D,
                         float* C, int64_t s_kc, int64_t s_seg, int64_t s_n, float* partial, int mode, cudaStream_t st);
-// fully fused recursion + contraction on the lattice (ds_lattice_conv.cu / ds_lattice_api.cu)
+// fully fused recursion + contraction on the lattice (ds_lattice_conv2.cu / ds_lattice_api.cu)
 bool fused_conv_usable(const ds_plan* plan, int32_t K, int64_t B, int64_t F, int64_t N, int32_t mode);
 int fused_conv(const ds_plan* plan, int32_t recursion, int32_t K, int64_t B, int64_t F, int64_t N, const float* in0,
                float* basis_out, const float* W, int64_t s_f, int64_t s_k, int64_t s_n, const float* bias, int act,

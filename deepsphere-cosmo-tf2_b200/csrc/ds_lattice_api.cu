@@ -131,10 +131,6 @@ int lattice_recursion(const ds_plan* plan, int64_t B, int F, int nsteps, const f
   return sub_problem_recursion(plan, B, F, nsteps, in0, add, out, alpha, beta, gamma, st);
 }
 
-bool lattice_conv_usable(const LatticeDev& L, int F, int N, int mode);
-int launch_lattice_conv(const LatticeDev& L, int64_t B, int64_t M, int F, int N, int recursion, const float* in0,
-                        float* const* out, const float* W, int64_t s_f, int64_t s_k, int64_t s_n, const float* bias,
-                        int act, float* y, int mode, cudaStream_t st);
 int umma_supported(int64_t Kc, int nseg, int64_t N);
 int launch_umma_gemm(int64_t R, int64_t N, int64_t Kc, int nseg, const float* A0, const float* Arest,
                      int64_t a_seg_stride_rows, const float* Bm, int64_t b_k_stride, int64_t b_seg_stride,
@@ -151,9 +147,7 @@ bool fused_conv_usable(const ds_plan* plan, int32_t K, int64_t B, int64_t F, int
   if (!plan->lattice || !plan->symmetric || K < 2) return false;
   const LatticeAttachment* L = plan->lattice;
   if (umma_supported(F, K, N) != 0) return false;  // the irregular tiles go through the tensor-core GEMM
-  if (lattice_conv2_usable(L->dev, K - 1, (int)F, (int)N, mode)) return true;  // register-resident kernel (ds_lattice_conv2.cu)
-  if (K - 1 != L->H) return false;
-  return lattice_conv_usable(L->dev, (int)F, (int)N, mode);
+  return lattice_conv2_usable(L->dev, K - 1, (int)F, (int)N, mode);  // register-resident kernel (ds_lattice_conv2.cu)
 }
 
 // y = act( sum_k T_k(L~)(in0) B_k + bias ),  B_k(f, n) = W[f*s_f + k*s_k + n*s_n];  basis_out (optional):
@@ -168,13 +162,9 @@ int fused_conv(const ds_plan* plan, int32_t recursion, int32_t K, int64_t B, int
   float* out[LAT_MAX_STEPS] = {};
   if (basis_out != nullptr)
     for (int s = 1; s < K; ++s) out[s - 1] = basis_out + (int64_t)(s - 1) * A;
-  if (lattice_conv2_usable(L->dev, K - 1, (int)F, (int)N, mode)) {
-    DS_TRY(launch_lattice_conv2(L->dev, K - 1, B, M, (int)F, (int)N, recursion, in0, basis_out ? out : nullptr, W, s_f,
-                                s_k, s_n, bias, act, y, st));
-  } else {
-    DS_TRY(launch_lattice_conv(L->dev, B, M, (int)F, (int)N, recursion, in0, basis_out ? out : nullptr, W, s_f, s_k, s_n,
-                               bias, act, y, mode, st));
-  }
+  DS_CHECK(lattice_conv2_usable(L->dev, K - 1, (int)F, (int)N, mode), "fused_conv: shape / mode not served by the fused kernel");
+  DS_TRY(launch_lattice_conv2(L->dev, K - 1, B, M, (int)F, (int)N, recursion, in0, basis_out ? out : nullptr, W, s_f,
+                              s_k, s_n, bias, act, y, st));
   if (L->n_own == 0) return 0;
   // ---- irregular tiles ----
   const int FV = (int)(F / 4), NV = (int)(N / 4);

@@ -3,8 +3,8 @@
 //   y[b, m, :] = act( sum_k T_k(L~) x [b, m, :] * W_k + bias )            (gnn_layers.py:131-159)
 //
 // Work item = (16x16-pixel tile + 4-ring halo = 24x24 lattice, batch element b, 8-channel chunk c).
-// What differs from ds_lattice_conv.cu (whose recursion is shared-memory-bandwidth bound at ~5 accesses per
-// 36 FMAs): every compute thread OWNS a 3x3 pixel block x 4 channels for all hops of an item and keeps
+// What differs from ds_lattice.cu and from the first fused kernel (git history: ds_lattice_conv.cu), whose recursion is
+// shared-memory-bandwidth bound at ~5 accesses per 36 FMAs: every compute thread OWNS a 3x3 pixel block x 4 channels for all hops of an item and keeps
 // T_{k-1} and T_{k-2} of that block in REGISTERS next to its 81 stencil weights.  Shared memory only carries
 // the neighbour exchange: per hop a thread stores its 9 new values and loads the 16 perimeter values
 // (2.8 accesses per 36 FMAs), and the very same exchange buffer is the K-major no-swizzle UMMA A operand

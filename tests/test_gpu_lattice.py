@@ -82,7 +82,8 @@ def test_lattice_masked_sky():
 @pytest.mark.parametrize("nside,B,Fin,Fout,K", [(32, 2, 16, 16, 5), (64, 2, 64, 64, 5), (32, 3, 32, 16, 3),
                                                 (32, 2, 16, 64, 2), (32, 1, 48, 32, 4), (32, 2, 24, 80, 5)])
 def test_fused_lattice_conv_matches_oracle(mode, tol, cls, nside, B, Fin, Fout, K):
-    """ds_lattice_conv.cu: recursion + tcgen05 contraction in one kernel (forward), and the same kernel on dz
+    """Fused path (tf32: ds_lattice_conv2.cu, recursion + tcgen05 contraction in one kernel; tf32x3: lattice recursion +
+    tensor-core GEMM kernels) - forward, and the same kernels on dz
     plus the transposed weight-gradient contraction (backward), against the float64 oracle."""
     g = SphereHealpix(nside, k=8)
     M = g.L.shape[0]
