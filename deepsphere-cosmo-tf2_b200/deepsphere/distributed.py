@@ -96,6 +96,29 @@ class _AllReduceSum(torch.autograd.Function):
         return g, None
 
 
+class _AllReduceSumReplicated(torch.autograd.Function):
+    """Sum over ranks whose RESULT is consumed by replicated computation (every rank evaluates the same loss on it):
+    the incoming gradient is already the full dL/dy on every rank, so the backward is the identity - summing it over
+    the ranks would count the loss once per rank."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        y = x.clone()
+        dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+def allreduce_sum_replicated(x, group=None):
+    """Sum of `x` over all ranks for a replicated consumer (see _AllReduceSumReplicated)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return x
+    return _AllReduceSumReplicated.apply(x, group)
+
+
 def allreduce_sum_autograd(x, group=None):
     """Sum of `x` over all ranks, differentiable (identity for a single process)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

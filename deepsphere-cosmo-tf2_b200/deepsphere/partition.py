@@ -185,3 +185,120 @@ class PartitionedGraphConv(torch.nn.Module):
         x_ext = halo_exchange(x_own, self.plan, self.group)
         y_ext = self.layer(x_ext, *args, **kwargs)
         return y_ext[:, self.plan.own_start: self.plan.own_start + self.plan.n_own, :]
+
+
+class PartitionedMean(torch.nn.Module):
+    """Mean over ALL pixels of the partitioned sphere (the `reduce_mean(axis=1)` head of the reference's networks):
+    local sum, one all-reduce of [B*F + 1] floats, replicated result [B, F].  The layers after it run replicated on
+    every rank (same loss everywhere), so its backward hands each rank the gradient of ITS partial sum only."""
+
+    def __init__(self, group=None):
+        super().__init__()
+        self.group = group
+
+    def forward(self, x_own):
+        from .distributed import allreduce_sum_replicated
+
+        B, n, F = x_own.shape
+        stats = torch.cat([x_own.sum(dim=1).reshape(-1), x_own.new_full((1,), float(n))])
+        # everything after the head is replicated (every rank evaluates the same loss): identity backward
+        stats = allreduce_sum_replicated(stats, self.group)
+        return stats[: B * F].reshape(B, F) / stats[B * F]
+
+
+class _Callable(torch.nn.Module):
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+    def forward(self, x):
+        return self.fn(x)
+
+
+class PartitionedHealpyGCNN(torch.nn.Module):
+    """healpy_networks.HealpyGCNN on a row-partitioned sphere.
+
+    Same layer list as HealpyGCNN.  Every rank owns a contiguous range of the (sorted, NESTED) input pixels, aligned
+    so that all pooling / pseudo-convolution levels of the network keep their 4^p siblings on one rank: those layers
+    run locally and unchanged.  Every HealpyChebyshev / HealpyMonomial becomes a PartitionedGraphConv on the graph of
+    its level (global lmax, one (K-1)-ring halo exchange per layer).  Use PartitionedMean for the mean-over-pixels
+    head; whatever follows it (Dense, ...) sees replicated tensors.  All ranks must construct the model with the same
+    torch seed (or broadcast the parameters), feed the SAME batch restricted to their rows, and sum the weight
+    gradients over the group after backward (`allreduce_gradients(params, average=False)`).
+    Not supported: use_bn inside graph layers (statistics would need the own-row mask), residual layers."""
+
+    def __init__(self, nside, indices, layers, n_neighbors=8, rank=None, world=None, group=None):
+        super().__init__()
+        import copy
+
+        from scipy.sparse.linalg import eigsh
+
+        from . import healpix as hpx
+        from . import healpy_layers as hp_nn
+        from .graph import SphereHealpix
+
+        if rank is None:
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if world is None:
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+        idx = np.sort(np.asarray(indices, dtype=np.int64))
+        M = len(idx)
+        # deepest pooling level reached anywhere in the network -> alignment of the row ranges
+        depth, max_depth = 0, 0
+        for layer in layers:
+            if isinstance(layer, (hp_nn.HealpyPool, hp_nn.HealpyPseudoConv)):
+                depth += int(layer.p)
+            elif isinstance(layer, hp_nn.HealpyPseudoConv_Transpose):
+                depth -= int(layer.p)
+            max_depth = max(max_depth, depth)
+        align = 4 ** max_depth
+        if M % align:
+            raise ValueError(f"{M} pixels cannot be pooled {max_depth} times: use utils.extend_indices first")
+        if M % 48 == 0 and (M // 48) % align == 0 and world <= 48:
+            align = M // 48  # quarter-face blocks of a full sphere
+        if M // align < world:
+            raise ValueError(f"{M // align} partition units for {world} ranks")
+        self.rank, self.world, self.group = rank, world, group
+        b, e = shard_range(M // align, rank, world)
+        self.own_range = (align * b, align * e)
+        self.layers_use = torch.nn.ModuleList()
+        cur_nside, cur_idx, cur_align = int(nside), idx, align
+        for layer in layers:
+            if isinstance(layer, (hp_nn.HealpyChebyshev, hp_nn.HealpyMonomial)):
+                if layer.use_bn:
+                    raise NotImplementedError("use_bn inside a partitioned graph layer")
+                sphere = SphereHealpix(subdivisions=cur_nside, indexes=cur_idx, nest=True, k=n_neighbors,
+                                       lap_type="normalized")
+                L = sphere.L
+                lmax = 1.02 * eigsh(sparse.csr_matrix(L, dtype=np.float64), k=1, which="LM",
+                                    return_eigenvectors=False)[0]
+
+                def make(L_ext, rows, layer=layer, lmax=lmax, nside_l=cur_nside, idx_l=cur_idx):
+                    f = copy.copy(layer)
+                    f.kwargs = dict(layer.kwargs, lmax=lmax, healpix=(nside_l, idx_l[rows]))
+                    return f._get_layer(L_ext)
+
+                self.layers_use.append(PartitionedGraphConv(L, int(layer.K) - 1, make, rank, world, group, cur_align))
+            elif isinstance(layer, (hp_nn.HealpyPool, hp_nn.HealpyPseudoConv)):
+                cur_idx = hpx.coarsen_indices(cur_idx, int(layer.p))
+                cur_nside //= 2 ** int(layer.p)
+                cur_align //= 4 ** int(layer.p)
+                self.layers_use.append(layer)
+            elif isinstance(layer, hp_nn.HealpyPseudoConv_Transpose):
+                cur_idx = hpx.refine_indices(cur_idx, int(layer.p))
+                cur_nside *= 2 ** int(layer.p)
+                cur_align *= 4 ** int(layer.p)
+                self.layers_use.append(layer)
+            elif isinstance(layer, hp_nn.Healpy_ResidualLayer):
+                raise NotImplementedError("residual layers on a partitioned sphere")
+            else:
+                self.layers_use.append(layer if isinstance(layer, torch.nn.Module) else _Callable(layer))
+
+    def forward(self, x_own, training=False):
+        from .keras_compat import _accepts_training
+
+        h = x_own
+        for layer in self.layers_use:
+            inner = layer.layer if isinstance(layer, PartitionedGraphConv) else layer
+            h = layer(h, training=training) if _accepts_training(inner) else layer(h)
+        return h

@@ -81,3 +81,68 @@ def test_partitioned_chebyshev_two_gpus(tmp_path, mode, tol):
         ey, edx, edw, n_own, n_ext, lattice = np.load(tmp_path / f"err{r}.npy")
         assert n_ext > n_own
         assert ey <= tol and edx <= tol and edw <= tol, (mode, r, ey, edx, edw)
+
+
+def _net_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+
+    import deepsphere
+    from deepsphere import distributed as dsd
+    from deepsphere import healpy_layers as hl
+    from deepsphere import keras_compat as kc
+    from deepsphere import partition
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dsd.init_from_env(backend="nccl")
+    dev = torch.device("cuda", rank)
+    nside, npix = 32, 12 * 32 * 32
+
+    def layers(head):
+        return [hl.HealpyPseudoConv(p=1, Fout=8, activation="elu"),
+                hl.HealpyChebyshev(K=5, Fout=16, use_bias=True, activation="elu", mode="tf32"),
+                hl.HealpyPool(p=1, pool_type="AVG"), hl.HealpyChebyshev(K=3, Fout=8), head, kc.Dense(2)]
+
+    torch.manual_seed(0)
+    whole = deepsphere.HealpyGCNN(nside=nside, indices=np.arange(npix), layers=layers(kc.Lambda(lambda v: v.mean(dim=1))))
+    part = partition.PartitionedHealpyGCNN(nside, np.arange(npix), layers(partition.PartitionedMean()))
+    gen = torch.Generator().manual_seed(2)
+    x = torch.randn(2, npix, 1, generator=gen).to(dev)
+    t = torch.randn(2, 2, generator=gen).to(dev)
+    b, e = part.own_range
+    xw = x.clone().requires_grad_(True)
+    xo = x[:, b:e].clone().requires_grad_(True)
+    yw = whole(xw, training=True)
+    part(xo.detach(), training=True)
+    pw, pp = list(whole.parameters()), list(part.parameters())
+    with torch.no_grad():
+        for a, c in zip(pw, pp):
+            c.copy_(a)
+    dsd.broadcast_parameters(part)
+    yp = part(xo, training=True)
+    ((yw - t) ** 2).sum().backward()
+    ((yp - t) ** 2).sum().backward()
+    graph_params = [p_ for m in part.layers_use if isinstance(m, partition.PartitionedGraphConv) for p_ in m.parameters()]
+    # the pseudo-convolution is row-local: its weight gradient is a partial sum over own rows too
+    local_params = [p_ for m in part.layers_use if isinstance(m, hl.HealpyPseudoConv) for p_ in m.parameters()]
+    dsd.allreduce_gradients(graph_params + local_params, average=False)
+    torch.cuda.synchronize()
+
+    def rel(a, ref):
+        return float((a - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+    errs = [rel(yp.detach(), yw.detach()), rel(xo.grad, xw.grad[:, b:e])] + [rel(c.grad, a.grad) for a, c in zip(pw, pp)]
+    np.save(os.path.join(out_dir, f"net{rank}.npy"), np.array(errs))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_partitioned_healpy_gcnn_two_gpus(tmp_path):
+    """PseudoConv -> Chebyshev (fused tf32 kernel) -> AVG pool -> Chebyshev -> mean over the sphere -> Dense on a sphere
+    split over 2 GPUs equals the whole-sphere HealpyGCNN: output, input gradient, every weight gradient."""
+    import torch.multiprocessing as mp
+
+    mp.spawn(_net_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r in (0, 1):
+        errs = np.load(tmp_path / f"net{r}.npy")
+        assert errs.max() <= 5e-3, errs

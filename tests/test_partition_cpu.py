@@ -79,10 +79,14 @@ def test_partitioned_graph_conv_equals_single_process(tmp_path):
         assert np.allclose(np.load(tmp_path / f"dw{r}.npy"), wg.grad.numpy(), atol=1e-10)
 
 
-def test_halo_plan_is_the_hop_closure():
-    """The halo is derived from the sparsity of L: own + halo == everything within n_hops, and the send / receive
-    lists of the two ranks mirror each other."""
-    g = SphereHealpix(NSIDE, k=8)
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("k", [8, 20])
+def test_halo_plan_is_the_hop_closure(k):
+    """The halo is derived from the sparsity of L (k = 20 reaches about two pixel rings per hop): own + halo ==
+    everything within n_hops, and the send / receive lists of the ranks mirror each other."""
+    g = SphereHealpix(NSIDE, k=k)
     M = g.L.shape[0]
     plans = [partition.HaloPlan(g.L, 2, r, 3, align=4) for r in range(3)]
     A = (abs(g.L) > 0).astype(np.float64)
@@ -100,3 +104,87 @@ def test_halo_plan_is_the_hop_closure():
                 # what r sends to q (global rows) is what q expects from r
                 assert np.array_equal(p.send_rows[q] + b, pq.ext[pq.recv_pos[r]])
     assert sum(p.n_own for p in plans) == M
+
+
+# ---- the partitioned NETWORK through the real layer classes, with CPU stand-ins for the CUDA ops -------------------
+def _install_cpu_ops():
+    """Replace the CUDA entry points the layers call by float64 torch-CPU restatements (oracle arithmetic)."""
+    from scipy import sparse as sp
+
+    from deepsphere import _native as nat
+    from deepsphere import _ops
+
+    def graph_conv(x, kernel, bias, plan, recursion, K, act=nat.ACT_LINEAR, mode=nat.MODE_FP32):
+        Lt = sp.csr_matrix((plan.values.astype(np.float64), (plan.indices[:, 0], plan.indices[:, 1])), shape=plan.shape)
+        rec = "chebyshev" if recursion == nat.RECURSION_CHEBYSHEV else "monomial"
+        y = orc.torch_cpu_graph_conv(x.double(), Lt, kernel.double(), K, rec)
+        if bias is not None:
+            y = y + bias.double().reshape(1, 1, -1)
+        if act == nat.ACT_RELU:
+            y = torch.relu(y)
+        elif act != nat.ACT_LINEAR:
+            raise NotImplementedError
+        return y
+
+    def pool(x, p, pool_type):
+        B, M, F = x.shape
+        v = x.reshape(B, M // 4**p, 4**p, F)
+        return v.max(dim=2).values if pool_type == nat.POOL_MAX else v.mean(dim=2)
+
+    _ops.graph_conv, _ops.pool = graph_conv, pool
+
+
+def _layers(head):
+    from deepsphere import healpy_layers as hl
+    from deepsphere import keras_compat as kc
+
+    return [hl.HealpyChebyshev(K=3, Fout=4, use_bias=True, activation="relu"), hl.HealpyPool(p=1, pool_type="MAX"),
+            hl.HealpyChebyshev(K=4, Fout=2), head, kc.Dense(3)]
+
+
+def _net_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dsd.init_from_env(backend="gloo")
+    import deepsphere
+    from deepsphere import keras_compat as kc
+
+    _install_cpu_ops()
+    nside, npix = 8, 12 * 8 * 8
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(3, npix, 2, generator=gen, dtype=torch.float64)
+    t = torch.randn(3, 3, generator=gen, dtype=torch.float64)
+    torch.manual_seed(0)  # the whole-sphere reference (and hence the copied weights) must be the same on every rank
+    whole = deepsphere.HealpyGCNN(nside=nside, indices=np.arange(npix), layers=_layers(kc.Lambda(lambda v: v.mean(dim=1))))
+    part = partition.PartitionedHealpyGCNN(nside, np.arange(npix), _layers(partition.PartitionedMean()))
+    b, e = part.own_range
+    assert (e - b) % 4 == 0 and (b, e) == ((0, npix // 2) if rank == 0 else (npix // 2, npix))
+    xw = x.clone().requires_grad_(True)
+    xo = x[:, b:e].clone().requires_grad_(True)
+    yw = whole(xw, training=True)
+    part(xo.detach(), training=True)  # builds the weights
+    pw, pp = list(whole.parameters()), list(part.parameters())
+    assert len(pw) == len(pp) and all(a.shape == c.shape for a, c in zip(pw, pp))
+    with torch.no_grad():
+        for a, c in zip(pw, pp):
+            c.copy_(a)
+    dsd.broadcast_parameters(part)  # what a training script does: every rank holds rank 0's weights
+    yp = part(xo, training=True)
+    ((yw - t) ** 2).sum().backward()
+    ((yp - t) ** 2).sum().backward()
+    # graph-layer weights hold partial sums over own rows; the Dense head sees replicated activations on every rank
+    graph_params = [p_ for m in part.layers_use if isinstance(m, partition.PartitionedGraphConv) for p_ in m.parameters()]
+    dsd.allreduce_gradients(graph_params, average=False)
+    errs = [float((yp - yw).abs().max()), float((xo.grad - xw.grad[:, b:e]).abs().max())]
+    errs += [float((c.grad.double() - a.grad.double()).abs().max()) for a, c in zip(pw, pp)]
+    np.save(os.path.join(out_dir, f"net{rank}.npy"), np.array(errs))
+    dist.destroy_process_group()
+
+
+def test_partitioned_healpy_gcnn_equals_single_process(tmp_path):
+    """Chebyshev -> MAX pool -> Chebyshev -> mean over the sphere -> Dense on 2 ranks: output, input gradient and every
+    weight gradient equal the whole-sphere HealpyGCNN (the pooling level keeps 4^p siblings on one rank)."""
+    mp.spawn(_net_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r in (0, 1):
+        errs = np.load(tmp_path / f"net{r}.npy")
+        assert errs.max() <= 1e-5, errs
