@@ -60,10 +60,10 @@ __device__ __forceinline__ void st_async_v4(void* dst, const float4& v, uint64_t
                ::"r"(smem_u32(dst)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(smem_u32(bar))
                : "memory");
 }
-// bounded wait: ~seconds of polling, then trap (surfaces as a launch failure, never a hang)
+// bounded wait: 2^22 suspended try_waits (each returns after <= 20 us or the shorter system limit: 4 - 80 s), then trap (surfaces as a launch failure, never a hang)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #pragma unroll 1
-  for (uint32_t i = 0; i < (1u << 28); ++i)
+  for (uint32_t i = 0; i < (1u << 22); ++i)
     if (mbar_try_wait(bar, parity)) return;
   printf("deepsphere_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
   __trap();
@@ -72,7 +72,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // same, for the producer / issuer roles that must not steal issue slots from the math warps while they poll
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
 #pragma unroll 1
-  for (uint32_t i = 0; i < (1u << 26); ++i) {
+  for (uint32_t i = 0; i < (1u << 22); ++i) {
     if (mbar_try_wait(bar, parity)) return;
     if (ns) __nanosleep(ns);
   }
