@@ -87,3 +87,66 @@ def test_direction_table_matches_the_plan_builder():
             assert dir_of(dr, dc) == d
     # and the C++ source spells the same table
     assert "dr == 0 ? (dc < 0 ? 0 : (dc > 0 ? 4 : 8))" in SRC
+
+
+def test_block_recursion_emulation_matches_oracle_and_contains_garbage():
+    """numpy emulation of what lattice_conv2_kernel computes on one tile: every one of the 24 x 24 positions is updated on
+    every hop from its 3 x 3 lattice neighbourhood with the plan's weights (Chebyshev: weights 2 L~, hop 1 halved,
+    T_k = (2L~) T_{k-1} - T_{k-2}); reads beyond the lattice hit the pad rows (NaN here) or wrap inside the row exactly like
+    the kernel's position arithmetic.  Claim guarded: the don't-care values (NaN) never reach the tile's own pixels, whose
+    T_1..T_4 equal the sparse-matrix oracle."""
+    from deepsphere import lattice, utils
+    from deepsphere.graph import SphereHealpix
+    from scipy import sparse
+
+    nside = 32
+    g = SphereHealpix(nside, k=8)
+    Lt = utils.rescale_L(sparse.csr_matrix(g.L, dtype=np.float64), lmax=1.9, scale=0.75)
+    plan = lattice.build_lattice_plan(Lt, nside, np.arange(12 * nside * nside), H)
+    assert plan is not None and plan.LW == LW
+    tile = int(np.flatnonzero(plan.regular)[7])
+    pix = plan.pix[tile].reshape(LW, LW)
+    w = plan.w[tile].astype(np.float64).reshape(LW, LW, 9)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(Lt.shape[0])
+    # oracle basis
+    basis = [x, Lt @ x]
+    for _ in range(2, H + 1):
+        basis.append(2 * (Lt @ basis[-1]) - basis[-2])
+    # emulation on the padded lattice: row index j + 1, pad rows 0 and LW + 1 hold NaN
+    def padded(v):
+        out = np.full((LW + 2, LW), np.nan)
+        out[1:-1] = v
+        return out
+
+    offs = {0: (0, -1), 1: (1, -1), 2: (1, 0), 3: (1, 1), 4: (0, 1), 5: (-1, 1), 6: (-1, 0), 7: (-1, -1), 8: (0, 0)}
+    cur = np.where(pix >= 0, x[np.where(pix >= 0, pix, 0)], 0.0)
+    old = None
+    own = np.zeros((LW, LW), dtype=bool)
+    own[H:H + T, H:H + T] = True
+    for s in range(1, H + 1):
+        P = padded(cur)
+        new = np.zeros((LW, LW))
+        for j in range(LW):
+            for c in range(LW):
+                acc = 0.0
+                for d, (dr, dc) in offs.items():
+                    cc = c + dc
+                    if cc < 0:
+                        cc = 22      # kernel: position +15 of the first column block -> column 22 of the same row
+                    elif cc >= LW:
+                        cc = 1       # kernel: position +1 of the last column block -> column 1
+                    acc += 2.0 * w[j, c, d] * P[j + 1 + dr, cc]
+                new[j, c] = acc
+        if s == 1:
+            new = 0.5 * new
+        else:
+            new = new - old
+        old, cur = cur, new
+        got = cur[own]
+        assert np.isfinite(got).all(), f"don't-care values reached the own pixels at hop {s}"
+        ref = basis[s][pix[own]]
+        # the plan stores the stencil weights in fp32 (as the kernel reads them): agreement to fp32 rounding
+        assert np.abs(got - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max()), (s, np.abs(got - ref).max())
+    # and the don't-care region really is contaminated (the test would be vacuous otherwise)
+    assert not np.isfinite(cur).all()
