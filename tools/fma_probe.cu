@@ -1,5 +1,5 @@
 // Micro-probe: fp32 FFMA vs packed FFMA2 issue rate per SM sub-partition on sm_100a.
-// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o fma_probe fma_probe.cu
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/fma_probe tools/fma_probe.cu  (binary is git-ignored)
 #include <cstdio>
 #include <cuda_runtime.h>
 
