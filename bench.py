@@ -159,8 +159,8 @@ def model_train_bench(args, mode, device, world):
     """Second half of BASELINE.json's metric: HealpyGCNN training throughput (maps/s).  The regression network of
     SURVEY 8d config C5 (PseudoConv p=1 F16 -> [Chebyshev K5 F32 + MAX pool] x 3 -> Chebyshev K5 F64 -> pool ->
     mean over pixels -> Dense(2)) on synthetic full-sphere maps, batch sharded over the ranks, MSE loss, Adam,
-    one flat gradient all-reduce per step.  nside 256 here (C5's nside 1024 needs the sphere-partitioned path that
-    is not built yet)."""
+    one flat gradient all-reduce per step.  nside 256 here, batch sharded; C5's nside 1024 runs on the
+    sphere-partitioned path (deepsphere/partition.py, tools/bench_partition.py)."""
     import deepsphere
     from deepsphere import distributed as dsd
     from deepsphere import healpy_layers as hl, keras_compat as kc
@@ -209,7 +209,7 @@ def model_train_bench(args, mode, device, world):
     del model, opt, x, t
     torch.cuda.empty_cache()
     return {"metric": "HealpyGCNN train maps/s", "value": world * Bm / (ms * 1e-3), "unit": "maps/s",
-            "ms_per_step": ms, "batch_per_gpu": Bm, "n_gpus": world, "parameters": n_params, "final_loss": float(loss),
+            "ms_per_step": ms, "batch_per_gpu": Bm, "n_gpus": world, "parameters": n_params, "final_loss": float(loss.detach()),
             "config": f"nside {nside} full sphere ({npix} px): PseudoConv p1 F16 -> [Chebyshev K5 F32 + MAX pool] x3 -> "
                       f"Chebyshev K5 F64 -> AVG pool -> mean -> Dense(2); MSE, Adam, fwd+bwd+all-reduce+step, mode {mode}"}
 
@@ -397,8 +397,11 @@ def main():
             free_host = psutil.virtual_memory().available
         except Exception:
             free_host = 0
+        # every rank of the node pins its own buffers at the same time: budget 40 % of the host memory over
+        # the local ranks (8 ranks x 19.3 GB would not fit a 196 GB box)
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
         Be = B
-        while Be > 1 and 3 * 4 * Be * M * F > 0.4 * free_host:
+        while Be > 1 and 3 * 4 * Be * M * F > 0.4 * free_host / max(local_world, 1):
             Be //= 2
         xh = torch.empty((Be, M, F), dtype=torch.float32).pin_memory()
         dyh = torch.empty((Be, M, F), dtype=torch.float32).pin_memory()
