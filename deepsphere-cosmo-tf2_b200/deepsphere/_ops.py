@@ -245,6 +245,24 @@ def spmm(plan, x, alpha=1.0, prev=None, beta=0.0, add=None, gamma=0.0, transpose
     return out
 
 
+class _SparseMatmul(torch.autograd.Function):
+    """y[b] = S x[b] for a fixed sparse S given as a GraphPlan; dx[b] = S^T dy[b]."""
+
+    @staticmethod
+    def forward(ctx, x, plan):
+        ctx.plan = plan
+        return spmm(plan, x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return spmm(ctx.plan, dy, transpose=True), None
+
+
+def sparse_matmul(plan, x):
+    """Differentiable ``S @ x`` on [B, M, F] tensors (one ds_spmm launch each way)."""
+    return _SparseMatmul.apply(x, plan)
+
+
 def basis(plan, x, K, recursion=nat.RECURSION_CHEBYSHEV, transpose=False):
     """T_1..T_{K-1} of the recursion (gnn_layers.py:135-143) as a [K-1, B, M, F] tensor (no autograd)."""
     _need_cuda(x, "basis")

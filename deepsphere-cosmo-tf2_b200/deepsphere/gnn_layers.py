@@ -51,6 +51,15 @@ class _GraphConvBase(Model):
     _recursion = None
     _scale = None
 
+    @property
+    def _n_terms(self):
+        """Number of basis tensors T_0..T_{n-1} of the recursion = rows of the kernel per input channel."""
+        return self.K
+
+    def _device_kernel(self):
+        """The [n_terms*Fin, Fout] weights the C-ABI contraction receives (row order f*n_terms + k)."""
+        return self.kernel
+
     def __init__(self, L, K, Fout=None, initializer=None, activation=None, use_bias=False, use_bn=False,
                  n_matmul_splits=1, **kwargs):
         super().__init__()
@@ -100,7 +109,7 @@ class _GraphConvBase(Model):
         from . import healpix as hpx
         from . import lattice
 
-        if self.K < 2:
+        if self._n_terms < 2:
             return None
         geo = self._healpix
         M = int(self._L_shape[0])
@@ -118,12 +127,12 @@ class _GraphConvBase(Model):
         try:
             # K <= 5: always a 4-ring halo (24 x 24 lattice) - the geometry of the register-resident fused kernel
             # (ds_lattice_conv2.cu); the kernels run K - 1 <= 4 hops on it
-            return lattice.make_payload(Lt, nside, indices, max(self.K - 1, 4))
+            return lattice.make_payload(Lt, nside, indices, max(self._n_terms - 1, 4))
         except Exception as exc:  # never let the optional fast path break the layer
             logger.warning(f"lattice plan construction failed ({exc!r}); using the generic kernels")
             return None
 
-    def _default_initializer(self, Fin):
+    def _default_initializer(self, Fin, Fout):
         raise NotImplementedError
 
     def build(self, input_shape):
@@ -131,11 +140,11 @@ class _GraphConvBase(Model):
         Fin = int(input_shape[-1])
         Fout = Fin if self.Fout is None else int(self.Fout)
         if self.initializer is None:
-            initializer = self._default_initializer(Fin)
+            initializer = self._default_initializer(Fin, Fout)
         else:
             logger.debug(self.kwargs)
             initializer = self.initializer
-        self.kernel = self.add_weight(name="kernel", shape=[self.K * Fin, Fout], initializer=initializer,
+        self.kernel = self.add_weight(name="kernel", shape=[self._n_terms * Fin, Fout], initializer=initializer,
                                       **self.kwargs)
         if self.use_bias:
             # Keras' add_weight default initialiser (glorot_uniform) — gnn_layers.py:104
@@ -153,8 +162,8 @@ class _GraphConvBase(Model):
         N, M, Fin = input_tensor.shape
         if M != self._plan.M:
             raise ValueError(f"input has {M} nodes but the graph Laplacian is {self._plan.M} x {self._plan.M}")
-        if self.kernel.shape[0] != self.K * Fin:
-            raise ValueError(f"layer was built for {self.kernel.shape[0] // self.K} input channels, got {Fin}")
+        if self.kernel.shape[0] != self._n_terms * Fin:
+            raise ValueError(f"layer was built for {self.kernel.shape[0] // self._n_terms} input channels, got {Fin}")
         mode = self.mode if self.mode is not None else _default_mode()
         if isinstance(mode, str):
             mode = nat.MODES[mode]
@@ -163,7 +172,7 @@ class _GraphConvBase(Model):
         # them (gnn_layers.py:152-159) or the activation is an arbitrary callable
         fuse = (not self.use_bn) and self._act_id is not None
         x = _ops.graph_conv(
-            input_tensor, self.kernel, bias if fuse else None, self._plan, self._recursion, self.K,
+            input_tensor, self._device_kernel(), bias if fuse else None, self._plan, self._recursion, self._n_terms,
             self._act_id if fuse else nat.ACT_LINEAR, mode,
         )
         if fuse:
@@ -184,7 +193,7 @@ class Chebyshev(_GraphConvBase):
     _recursion = nat.RECURSION_CHEBYSHEV
     _scale = 0.75  # gnn_layers.py:67
 
-    def _default_initializer(self, Fin):
+    def _default_initializer(self, Fin, Fout):
         stddev = 1 / np.sqrt(Fin * (self.K + 0.5) / 2)  # gnn_layers.py:92
         return TruncatedNormal(stddev=stddev)
 
@@ -196,8 +205,90 @@ class Monomial(_GraphConvBase):
     _recursion = nat.RECURSION_MONOMIAL
     _scale = 1.0  # gnn_layers.py:219 (rescale_L default scale)
 
-    def _default_initializer(self, Fin):
+    def _default_initializer(self, Fin, Fout):
         return TruncatedNormal(stddev=0.1)  # gnn_layers.py:243
+
+
+def bernstein_polynomials(K, stale_last_term=True):
+    """The K+1 basis polynomials of the reference's Bernstein layer as callables' values: returns
+    ``p(lam)[i]`` evaluated on an array ``lam`` (gnn_layers.py:543-554).
+
+    ``p_i(lam) = theta_i (2 - lam)^(K-i) lam^i`` with ``theta_i = C(K, i) / 2^K``.  In the reference
+    the inner loop of the last term (i = K) is empty, so its ``x3`` is the already scaled tensor
+    of i = K-1 and the last basis column is ``theta_K * theta_{K-1} (2 - lam) lam^(K-1)`` rather
+    than ``theta_K lam^K``.  ``stale_last_term=True`` reproduces that (weights trained
+    with the reference give the same outputs); False evaluates the textbook polynomial."""
+    from math import comb
+
+    def evaluate(lam):
+        lam = np.asarray(lam, dtype=np.float64)
+        out = np.empty((K + 1,) + lam.shape, dtype=np.float64)
+        for i in range(K + 1):
+            theta = comb(K, i) / 2.0**K
+            out[i] = theta * (2.0 - lam) ** (K - i) * lam**i
+        if stale_last_term:
+            out[K] = (1.0 / 2.0**K) * out[K - 1]
+        return out
+
+    return evaluate
+
+
+def bernstein_to_chebyshev(K, stale_last_term=True):
+    """``C[i, j]`` with ``p_i(lam) = sum_j C[i, j] T_j(lam)`` (float64, [K+1, K+1]).
+
+    Computed by interpolation at the K+1 Chebyshev nodes (exact for degree-K polynomials and free
+    of the cancellation a monomial expansion of ``(2 - lam)^(K-i)`` would bring): the entries are
+    bounded by ``max |p_i|`` on [-1, 1] <= 1.5^K."""
+    n = K + 1
+    m = np.arange(n)
+    nodes = np.cos(np.pi * (m + 0.5) / n)
+    vals = bernstein_polynomials(K, stale_last_term)(nodes)                    # [K+1, n]
+    dct = np.cos(np.pi * np.outer(np.arange(n), m + 0.5) / n)                  # [j, m]
+    C = (2.0 / n) * vals @ dct.T
+    C[:, 0] *= 0.5
+    return C
+
+
+class Bernstein(_GraphConvBase):
+    """A graph convolutional layer using the Bernstein approximation (gnn_layers.py:416-572,
+    https://arxiv.org/abs/2106.10994): ``y = sum_i p_i(L~) x W_i``, ``L~ = 1.5 L / lmax - I``, K = ORDER of
+    the polynomial, kernel ``[(K+1)*Fin, Fout]`` with row order ``f*(K+1) + i``.
+
+    The reference evaluates every ``p_i(L~) x`` separately, K(K+1)/2 + K sparse products per call.  All
+    p_i are polynomials of degree <= K in the same L~ that the Chebyshev layer uses (scale 0.75), so here the
+    layer IS the (K+1)-term Chebyshev graph convolution (K hops, the fused sm_100a kernel for K <= 4) with the
+    weights moved to the Chebyshev basis on the fly, ``W'_j = sum_i C[i, j] W_i`` (a [(K+1) x (K+1)] matrix
+    from `bernstein_to_chebyshev`, applied to the small weight tensor inside autograd): same polynomial of L~,
+    same result up to fp32 rounding, same trainable variable as the reference."""
+
+    _recursion = nat.RECURSION_CHEBYSHEV
+    _scale = 0.75  # gnn_layers.py:473
+
+    def __init__(self, L, K, Fout=None, initializer=None, activation=None, use_bias=False, use_bn=False,
+                 n_matmul_splits=1, **kwargs):
+        self.stale_last_term = bool(kwargs.pop("stale_last_term", True))
+        super().__init__(L, K, Fout=Fout, initializer=initializer, activation=activation, use_bias=use_bias,
+                         use_bn=use_bn, n_matmul_splits=n_matmul_splits, **kwargs)
+        # (K = 0 raises NameError in the reference: its x3 is never assigned; the base class rejects K < 1)
+        # a constant of the layer, not a Keras weight: kept out of parameters()/buffers()
+        self._basis_change = bernstein_to_chebyshev(self.K, self.stale_last_term)
+        self._basis_change_dev = {}
+
+    @property
+    def _n_terms(self):
+        return self.K + 1
+
+    def _default_initializer(self, Fin, Fout):
+        return TruncatedNormal(stddev=np.sqrt(6 / (Fin + Fout)))  # gnn_layers.py:498-499
+
+    def _device_kernel(self):
+        n = self.K + 1
+        Fout = self.kernel.shape[1]
+        dev = self.kernel.device
+        C = self._basis_change_dev.get(dev)
+        if C is None:
+            C = self._basis_change_dev[dev] = torch.tensor(self._basis_change, dtype=torch.float32, device=dev)
+        return torch.einsum("ij,fio->fjo", C, self.kernel.reshape(-1, n, Fout)).reshape(-1, Fout)
 
 
 class GCNN_ResidualLayer(Model):

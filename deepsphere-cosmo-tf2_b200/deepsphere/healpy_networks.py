@@ -90,7 +90,8 @@ class HealpyGCNN(Sequential):
         graph_cache = {}
 
         for layer in self.layers_in:
-            if isinstance(layer, (hp_nn.HealpyChebyshev, hp_nn.HealpyMonomial, hp_nn.Healpy_ResidualLayer)):
+            if isinstance(layer, (hp_nn.HealpyChebyshev, hp_nn.HealpyMonomial, hp_nn.Healpy_ResidualLayer,
+                                  hp_nn.HealpyBernstein)):
                 # the reference builds one SphereHealpix per graph layer even at equal nside
                 # (healpy_networks.py:110); the result only depends on (nside, indices, k), so cache it
                 key = (current_nside, len(current_indices), int(current_indices[0]), int(current_indices[-1]),
@@ -149,14 +150,63 @@ class HealpyGCNN(Sequential):
         return hpx.refine_indices(indices, hpx.nside2order(nside_out) - hpx.nside2order(nside_in))
 
     def _get_filter_coeffs(self, layer, ind_in=None, ind_out=None):
-        """Chebyshev filter coefficients of a layer as [Fin, Fout, K] (healpy_networks.py:190-217):
-        the kernel is read as Fin x K x Fout, which is what pins the f*K + k row order."""
-        K, Fout = layer.K, layer.kernel.shape[1]
-        weights = layer.kernel.detach().cpu().numpy()
-        Fin = weights.shape[0] // K
-        weights = weights.reshape((Fin, K, Fout)).transpose(0, 2, 1)
-        if ind_in is not None:
-            weights = weights[ind_in]
-        if ind_out is not None:
-            weights = weights[:, ind_out]
-        return weights
+        """Chebyshev filter coefficients of a layer as [K, Fout, Fin] (healpy_networks.py:190-212): the kernel
+        is read as Fin x K x Fout — which is what pins the f*K + k row order — and transposed to K x Fout x Fin.
+        ``ind_in`` / ``ind_out`` select input / output filters (tested for truthiness like there, so index 0 alone
+        selects everything)."""
+        K, Fout = layer.K, layer.Fout
+        trained_weights = layer.kernel.detach().cpu().numpy()  # Fin*K x Fout
+        if Fout is None:  # possible in res layers: Fin == Fout
+            Fout = int(np.sqrt(np.prod(trained_weights.shape) // K))
+        trained_weights = trained_weights.reshape((-1, K, Fout)).transpose([1, 2, 0])
+        if ind_in:
+            trained_weights = trained_weights[:, :, ind_in]
+        if ind_out:
+            trained_weights = trained_weights[:, ind_out, :]
+        return trained_weights
+
+    def get_gsp_filters(self, layer, ind_in=None, ind_out=None, return_weights=False):
+        """The Chebyshev filters of a layer (healpy_networks.py:214-289).  ``layer`` is an index or a name;
+        only Chebyshev layers and residual layers with Chebyshev sub-layers qualify (ValueError otherwise).
+        ``return_weights=True`` gives the list of [K, Fout, Fin] coefficient arrays exactly like the reference.
+        Otherwise the reference wraps them into ``pygsp.filters.Chebyshev`` objects on a full-sphere graph of
+        the layer's nside; PyGSP is not a dependency here, so a `ChebyshevFilter` with the same ``evaluate(x)``
+        contract (frequency response on [0, lmax]) is returned instead."""
+        if isinstance(layer, (int, np.integer)):
+            tf_layer = self.get_layer(index=int(layer))
+        elif isinstance(layer, str):
+            tf_layer = self.get_layer(name=layer)
+        else:
+            raise ValueError("layer should be either string or int.")
+        msg = (f"The requested layer ({layer}) is of type {type(tf_layer)}, but only Chebyshev5 or "
+               f"GCNN_ResidualLayer layers (with Chebyshev5 sublayers) are supported...")
+        if isinstance(tf_layer, gnn.GCNN_ResidualLayer):
+            if not (isinstance(tf_layer.layer1, gnn.Chebyshev) and isinstance(tf_layer.layer2, gnn.Chebyshev)):
+                raise ValueError(msg)
+            subs = [tf_layer.layer1, tf_layer.layer2]
+        elif isinstance(tf_layer, gnn.Chebyshev):
+            subs = [tf_layer]
+        else:
+            raise ValueError(msg)
+        weights = [self._get_filter_coeffs(sub, ind_in=ind_in, ind_out=ind_out) for sub in subs]
+        if return_weights:
+            return weights
+        return [ChebyshevFilter(w, sub.lmax) for w, sub in zip(weights, subs)]
+
+
+class ChebyshevFilter:
+    """Frequency response of a bank of Chebyshev filters, the part of ``pygsp.filters.Chebyshev`` that
+    HealpyGCNN's plotting helpers use (healpy_networks.py:286, 312-329).  ``coefficients`` [K, Fout, Fin];
+    ``lmax`` = the 1.02 * lambda_max the layer rescaled its Laplacian with.  The layer maps an eigenvalue lam
+    of L to ``1.5 * lam / lmax - 1`` (gnn_layers.py:66-67) and its response is ``sum_k c_k T_k`` of that."""
+
+    def __init__(self, coefficients, lmax):
+        self.coefficients = np.asarray(coefficients, dtype=np.float64)
+        self.lmax = float(lmax)
+        self.n_filters = int(np.prod(self.coefficients.shape[1:]))
+
+    def evaluate(self, x):
+        """Response at graph frequencies ``x`` (eigenvalues of L): array [Fout, Fin, len(x)]."""
+        lam = 1.5 * np.asarray(x, dtype=np.float64) / self.lmax - 1.0
+        T = np.polynomial.chebyshev.chebvander(lam, self.coefficients.shape[0] - 1)  # [n, K]
+        return np.einsum("nk,kof->ofn", T, self.coefficients)

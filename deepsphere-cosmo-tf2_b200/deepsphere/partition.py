@@ -264,7 +264,7 @@ class PartitionedHealpyGCNN(torch.nn.Module):
         self.layers_use = torch.nn.ModuleList()
         cur_nside, cur_idx, cur_align = int(nside), idx, align
         for layer in layers:
-            if isinstance(layer, (hp_nn.HealpyChebyshev, hp_nn.HealpyMonomial)):
+            if isinstance(layer, (hp_nn.HealpyChebyshev, hp_nn.HealpyMonomial, hp_nn.HealpyBernstein)):
                 if layer.use_bn:
                     raise NotImplementedError("use_bn inside a partitioned graph layer")
                 sphere = SphereHealpix(subdivisions=cur_nside, indexes=cur_idx, nest=True, k=n_neighbors,
@@ -278,7 +278,9 @@ class PartitionedHealpyGCNN(torch.nn.Module):
                     f.kwargs = dict(layer.kwargs, lmax=lmax, healpix=(nside_l, idx_l[rows]))
                     return f._get_layer(L_ext)
 
-                self.layers_use.append(PartitionedGraphConv(L, int(layer.K) - 1, make, rank, world, group, cur_align))
+                # hops = polynomial degree: K - 1 for K-term Chebyshev / Monomial, K for an order-K Bernstein layer
+                hops = int(layer.K) if isinstance(layer, hp_nn.HealpyBernstein) else int(layer.K) - 1
+                self.layers_use.append(PartitionedGraphConv(L, hops, make, rank, world, group, cur_align))
             elif isinstance(layer, (hp_nn.HealpyPool, hp_nn.HealpyPseudoConv)):
                 cur_idx = hpx.coarsen_indices(cur_idx, int(layer.p))
                 cur_nside //= 2 ** int(layer.p)

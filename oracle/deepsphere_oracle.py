@@ -11,6 +11,8 @@ through TensorFlow ops (file:line into /root/reference/src/deepsphere/):
 * Laplacian preparation            gnn_layers.py:64-72, utils.py:40-46
 * Chebyshev.call                   gnn_layers.py:130-161
 * Monomial.call                    gnn_layers.py:281-309
+* Bernstein.call                   gnn_layers.py:518-572 (incl. its stale last term)
+* HealpySmoothing kernel + call    healpy_layers.py:725-764, 831-846
 * BatchNormalization config        gnn_layers.py:53
 * HealpyPool                       healpy_layers.py:48-63
 * HealpyPseudoConv (Conv1D)        healpy_layers.py:118-126
@@ -195,6 +197,89 @@ def graph_conv_backward(x, Lt, kernel, K, dy, recursion="chebyshev", dtype=np.fl
     return np.ascontiguousarray(dx), dkernel, dbias
 
 
+def bernstein_forward(x, Lt, kernel, K, bias=None, activation=None, dtype=np.float32):
+    """Bernstein.call (gnn_layers.py:518-572), loop for loop: K = polynomial ORDER, kernel
+    [(K+1)*Fin, Fout] with row order f*(K+1) + i, Lt prepared with scale 0.75 (:473).
+
+    The stale ``x3`` of the last term is reproduced as written (:543-554): for i = K the loop
+    ``range(K - i)`` is empty, so ``x3`` is still the (already theta-scaled) tensor of i = K-1."""
+    from math import comb
+
+    dtype = np.dtype(dtype).type
+    N, M, Fin = x.shape
+    Ls = sparse.csr_matrix(Lt, dtype=dtype)
+    x0 = np.transpose(x.astype(dtype), (1, 2, 0)).reshape(M, Fin * N)  # :535-536
+    stack = []
+    x3 = None
+    for i in range(0, K + 1):  # :540
+        x1 = x0
+        theta = dtype(comb(K, i) / (2**K))
+        for _ in range(i):
+            x1 = Ls @ x1
+        x2 = x1
+        for _ in range(K - i):
+            x3 = dtype(2) * x2 - Ls @ x2
+            x2 = x3
+        x3 = theta * x3  # NameError in the reference when K = 0
+        stack.append(x3)
+    X = np.stack(stack, axis=0).reshape(K + 1, M, Fin, N)  # :555-556
+    X = np.ascontiguousarray(np.transpose(X, (3, 1, 2, 0))).reshape(N * M, Fin * (K + 1))  # :557-558
+    z = (X @ kernel.astype(dtype)).reshape(N, M, -1)  # :560-561
+    if bias is not None:
+        z = z + bias.astype(dtype).reshape(1, 1, -1)
+    return _act(activation)(z).astype(dtype)
+
+
+def smoothing_neighbours(lat, lon, sigma_rad, n_sigma_support=3):
+    """HealpySmoothing._build_tree + _build_kernel (healpy_layers.py:766-829) with the reference's own tool,
+    a scikit-learn BallTree under the haversine metric: every pixel gets its ``max_neighbors`` nearest pixels,
+    max_neighbors = the largest population of any radius-(n_sigma * sigma) ball.  Returns (ind_coo [nnz, 2]
+    int64, val_coo [nnz] float32)."""
+    from sklearn.neighbors import BallTree
+
+    theta = np.stack([lat, lon], axis=1)
+    tree = BallTree(theta, metric="haversine")
+    inds_r = tree.query_radius(theta, r=sigma_rad * n_sigma_support)
+    max_neighbors = int(np.max([len(i) for i in inds_r]))
+    dist_k, inds_k = tree.query(theta, k=max_neighbors, return_distance=True, sort_results=True)
+    kernel_k = np.exp(-0.5 / sigma_rad**2 * dist_k**2).astype(np.float32)
+    n = len(lat)
+    rows = np.repeat(np.arange(n, dtype=np.int64)[:, None], max_neighbors, axis=1)
+    ind_coo = np.concatenate([rows.reshape(-1, 1), inds_k.astype(np.int64).reshape(-1, 1)], axis=1)
+    return ind_coo, kernel_k.reshape(-1)
+
+
+def smoothing_kernel(ind_coo, val_coo, n):
+    """HealpySmoothing._build_sparse_tensor (healpy_layers.py:831-846): COO -> row-major sparse,
+    then ``sparse_kernel / expand_dims(reduce_sum(sparse_kernel, axis=1), axis=0)``.  The row sums
+    get shape [1, n] and broadcast along the LAST axis: entry (i, j) is divided by the row sum of row
+    j, not of row i (the comment there says "rows have to sum to one"; they only do when the kernel
+    is symmetric).  Restated as written."""
+    Ks = sparse.csr_matrix((np.asarray(val_coo, dtype=np.float32), (ind_coo[:, 0], ind_coo[:, 1])), shape=(n, n))
+    row_sum = np.asarray(Ks.sum(axis=1)).ravel().astype(np.float32)
+    coo = Ks.tocoo()
+    return sparse.csr_matrix((coo.data / row_sum[coo.col], (coo.row, coo.col)), shape=(n, n))
+
+
+def smoothing_forward(x, Ks, per_channel_repetitions=None, mask=None, dtype=np.float32):
+    """HealpySmoothing.call (healpy_layers.py:725-764): every channel [n_indices, n_batch] is multiplied
+    by the sparse kernel once, or per_channel_repetitions[i] times; then the optional mask."""
+    dtype = np.dtype(dtype).type
+    Kd = sparse.csr_matrix(Ks, dtype=dtype)
+    xt = np.transpose(x.astype(dtype), (1, 0, 2))  # :732
+    out = []
+    for i in range(xt.shape[2]):  # :738-748
+        c = xt[:, :, i]
+        reps = 1 if per_channel_repetitions is None else int(per_channel_repetitions[i])
+        for _ in range(reps):
+            c = Kd @ c
+        out.append(c)
+    y = np.transpose(np.stack(out, axis=2), (1, 0, 2))  # :751-754
+    if mask is not None:
+        y = y * mask.astype(dtype)
+    return y
+
+
 # --------------------------------------------------------------------------------------
 # Pool / pseudo-convolutions
 # --------------------------------------------------------------------------------------
@@ -311,4 +396,30 @@ def torch_cpu_graph_conv(x, Lt, kernel, K, recursion="chebyshev"):
             stack.append(x1)
             x0 = x1
     X = torch.stack(stack, dim=0).reshape(K, M, Fin, N).permute(3, 1, 2, 0).reshape(N * M, Fin * K)
+    return (X @ kernel).reshape(N, M, -1)
+
+
+def torch_cpu_bernstein(x, Lt, kernel, K):
+    """Bernstein.call (gnn_layers.py:518-561) with differentiable torch CPU ops in x's dtype, loop for loop
+    (incl. the stale last term) — the autograd yardstick for the Bernstein gradients."""
+    import torch
+    from math import comb
+
+    N, M, Fin = x.shape
+    coo = sparse.coo_matrix(Lt)
+    Ls = torch.sparse_coo_tensor(np.vstack((coo.row, coo.col)), torch.tensor(coo.data, dtype=x.dtype), coo.shape).coalesce()
+    x0 = x.permute(1, 2, 0).reshape(M, Fin * N)
+    stack = []
+    x3 = None
+    for i in range(K + 1):
+        x1 = x0
+        for _ in range(i):
+            x1 = torch.sparse.mm(Ls, x1)
+        x2 = x1
+        for _ in range(K - i):
+            x3 = 2 * x2 - torch.sparse.mm(Ls, x2)
+            x2 = x3
+        x3 = (comb(K, i) / 2**K) * x3
+        stack.append(x3)
+    X = torch.stack(stack, dim=0).reshape(K + 1, M, Fin, N).permute(3, 1, 2, 0).reshape(N * M, Fin * (K + 1))
     return (X @ kernel).reshape(N, M, -1)

@@ -51,6 +51,63 @@ def conv_case(name, L, recursion, K, B, Fin, Fout, seed, bias=False, activation=
           np.abs(y32 - y64).max() / np.abs(y64).max())
 
 
+def bernstein_case(name, L, K, B, Fin, Fout, seed, stale=True):
+    """Bernstein layer (gnn_layers.py:416-572): y from the literal loop restatement; gradients of the linear part
+    from float64 torch autograd over the same loops (torch.sparse.mm)."""
+    import torch
+
+    rng = np.random.default_rng(seed)
+    Lt, lmax = orc.prepare_laplacian(L, 0.75)
+    M = Lt.shape[0]
+    x = rng.standard_normal((B, M, Fin))
+    kernel = rng.standard_normal(((K + 1) * Fin, Fout)) * np.sqrt(6 / (Fin + Fout))
+    dy = rng.standard_normal((B, M, Fout))
+    y64 = orc.bernstein_forward(x, Lt, kernel, K, dtype=np.float64)
+    xt = torch.tensor(x, requires_grad=True)
+    wt = torch.tensor(kernel, requires_grad=True)
+    yt = orc.torch_cpu_bernstein(xt, Lt, wt, K)
+    assert np.abs(yt.detach().numpy() - y64).max() <= 1e-12 * np.abs(y64).max()
+    yt.backward(torch.tensor(dy))
+    coo, Lin = Lt.tocoo(), sparse.coo_matrix(L)
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        L_row=Lin.row.astype(np.int64), L_col=Lin.col.astype(np.int64), L_val=Lin.data.astype(np.float64),
+        Lt_row=coo.row.astype(np.int64), Lt_col=coo.col.astype(np.int64), Lt_val=coo.data.astype(np.float64),
+        M=M, lmax=lmax, K=K, recursion="bernstein", x=x, kernel=kernel, bias=np.zeros(0), activation="",
+        dy=dy, y64=y64, dx64=xt.grad.numpy(), dkernel64=wt.grad.numpy(),
+    )
+    print(name, "M", M, "K", K, "max|y|", np.abs(y64).max())
+
+
+def smoothing_case(name, nside, indices, sigma_arcmin, B, C, reps, seed):
+    """HealpySmoothing (healpy_layers.py:510-853): kernel from the reference's BallTree recipe on this repo's pixel
+    centres, normalised as written there, applied once and with per-channel repetitions + mask."""
+    rng = np.random.default_rng(seed)
+    theta, phi = hpx.pix2ang(nside, indices)
+    sigma_rad = sigma_arcmin * np.pi / (60 * 180)
+    ind_coo, val_coo = orc.smoothing_neighbours(0.5 * np.pi - theta, phi, sigma_rad, 3)
+    n = len(indices)
+    Ks = orc.smoothing_kernel(ind_coo, val_coo, n)
+    x = rng.standard_normal((B, n, C))
+    mask = (rng.random((n, 1)) > 0.2)
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"), M=n, nside=nside, indices=np.asarray(indices, dtype=np.int64),
+        sigma_arcmin=sigma_arcmin, ind_coo=ind_coo, val_coo=val_coo, x=x, reps=np.asarray(reps, dtype=np.int64),
+        mask=mask, y_once64=orc.smoothing_forward(x, Ks, dtype=np.float64),
+        y_reps_mask64=orc.smoothing_forward(x, Ks, reps, mask[None], dtype=np.float64),
+    )
+    print(name, "n", n, "nnz", len(val_coo), "neighbours per row", len(val_coo) // n)
+
+
+def next_cases():
+    """Bernstein and HealpySmoothing."""
+    bernstein_case("bern_nside4_k8", SphereHealpix(4, k=8).L, 4, 2, 3, 5, seed=21)
+    disc = hpx.query_disc(16, [1, 0, 0], 0.9)
+    ext = orc.extend_indices(disc, 16, 4)
+    bernstein_case("bern_masked16_k20", SphereHealpix(16, indexes=ext, k=20).L, 7, 2, 2, 3, seed=22)
+    smoothing_case("smooth_masked16", 16, ext, 300.0, 2, 3, [1, 3, 2], seed=23)
+
+
 def main():
     # 1. the reference's own test input shape: L = A A^T (3x3), x [5,3,7], K = 4, Fout = 3
     #    (tests/test_gnn_layers.py:9-33; TF's RNG is not reproducible here -> numpy seed 11)
@@ -90,8 +147,12 @@ def main():
         os.path.join(OUT, "pconv_nside8.npz"), x=x, w=w, b=b, wt=wt,
         y=orc.pseudo_conv(x, w, b, "elu"), yt=orc.pseudo_conv_transpose(x[:, :48], wt, b, "relu"),
     )
+    next_cases()
     print("golden written to", OUT)
 
 
 if __name__ == "__main__":
-    main()
+    if "--next-only" in sys.argv:  # only the section-8f cases (leaves the other files untouched)
+        next_cases()
+    else:
+        main()
