@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 
 #include "../../include/deepsphere_b200.h"
@@ -42,6 +43,25 @@ extern std::atomic<int64_t> g_launches;
     ds::g_launches.fetch_add(1, std::memory_order_relaxed); \
     DS_CUDA(cudaGetLastError());                       \
   } while (0)
+
+// Function attributes (opt-in dynamic shared memory, carve-out) belong to the device a kernel is loaded on, so a
+// process that drives several GPUs has to set them once per device, not once per process.
+//   static PerDeviceOnce once;  DS_TRY(once.run([&]() -> int { DS_CUDA(cudaFuncSetAttribute(...)); return 0; }));
+struct PerDeviceOnce {
+  std::mutex m;
+  uint64_t done[4] = {0, 0, 0, 0};  // bit per device ordinal (256 devices)
+  template <class F>
+  int run(F&& f) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 256) dev = 0;
+    std::lock_guard<std::mutex> lock(m);
+    const uint64_t bit = 1ull << (dev & 63);
+    if (done[dev >> 6] & bit) return 0;
+    const int rc = f();
+    if (rc == 0) done[dev >> 6] |= bit;
+    return rc;
+  }
+};
 
 inline int num_sms() {
   static int n = 0;

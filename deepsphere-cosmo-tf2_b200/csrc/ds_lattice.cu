@@ -235,13 +235,15 @@ template <int H, int FC, int S>
 int launch_instance(const LatticeArgs& a, cudaStream_t st) {
   constexpr int LW = LAT_T + 2 * H;
   constexpr int smem = 2 * (FC / 4) * lat_plane(LW) * 16 + LW * LW * 4 + 64;
-  static int ctas_per_sm = 0;
-  if (ctas_per_sm == 0) {
+  static std::atomic<int> ctas_per_sm{0};  // identical on every device of one box
+  static PerDeviceOnce attr_once;
+  DS_TRY(attr_once.run([&]() -> int {
     DS_CUDA(cudaFuncSetAttribute(lattice_recursion_kernel<H, FC, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int n = 1;
     DS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, lattice_recursion_kernel<H, FC, S>, lat_threads(LW, FC, S), smem));
     ctas_per_sm = std::max(1, n);
-  }
+    return 0;
+  }));
   const int n_units = a.n_tiles * a.b_split;
   const int grid = std::min(n_units, num_sms() * ctas_per_sm);
   lattice_recursion_kernel<H, FC, S><<<grid, lat_threads(LW, FC, S), smem, st>>>(a);

@@ -629,8 +629,8 @@ int launch_lattice_conv2(const LatticeDev& L, int nsteps, int64_t B, int64_t M, 
   g_launches.fetch_add(1);
   a.b_img = img;
   const size_t smem = conv2_smem_bytes(N, nsteps);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  const int attr_rc = attr_once.run([&]() -> int {
     int dev = 0, max_smem = 0;
     DS_CUDA(cudaGetDevice(&dev));
     DS_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -638,7 +638,12 @@ int launch_lattice_conv2(const LatticeDev& L, int nsteps, int64_t B, int64_t M, 
     DS_CUDA(cudaFuncSetAttribute(lattice_conv2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     DS_CUDA(cudaFuncSetAttribute(lattice_conv2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     DS_CUDA(cudaFuncSetAttribute(lattice_conv2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_done = true;
+    return 0;
+  });
+  if (attr_rc != 0) {
+    cudaFreeAsync(img, st);
+    if (a.dbg != nullptr) cudaFree(a.dbg);
+    return attr_rc;
   }
   const int n_units = a.n_tiles * a.b_split;
   const int grid = std::min(n_units, 2 * num_sms());

@@ -356,11 +356,11 @@ int launch_spmm(const SparseDev& S, int64_t B, int64_t F, const float* in, float
     DS_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     int nstage = (int)std::min<size_t>(4, (max_smem - 1024) / stage_bytes);
     if (nstage >= 2) {
-      static bool attr_done = false;
-      if (!attr_done) {
+      static PerDeviceOnce attr_once;
+      DS_TRY(attr_once.run([&]() -> int {
         DS_CUDA(cudaFuncSetAttribute(spmm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        attr_done = true;
-      }
+        return 0;
+      }));
       const int64_t upb = (S.M + U - 1) / U;
       const int64_t nblk = std::max<int64_t>(1, std::min<int64_t>(B * upb, num_sms()));
       spmm_tile_kernel<<<(unsigned)nblk, 544, nstage * stage_bytes + nstage * sizeof(TileStage) + 64, st>>>(

@@ -413,12 +413,15 @@ int launch_umma_gemm(int64_t R, int64_t N, int64_t Kc, int nseg, const float* A0
     cudaFreeAsync(img, st);
     return rc;
   }
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [&] {
-    attr_err = cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  static PerDeviceOnce attr_once;
+  rc = attr_once.run([&]() -> int {
+    DS_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    return 0;
   });
-  DS_CHECK(attr_err == cudaSuccess, "cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(attr_err));
+  if (rc != 0) {
+    cudaFreeAsync(img, st);
+    return rc;
+  }
   const int64_t n_tiles = (R + BM - 1) / BM;
   const unsigned grid = (unsigned)std::min<int64_t>(n_tiles, num_sms());
   umma_gemm_kernel<<<grid, three ? NUM_THREADS_3X : NUM_THREADS_TF32, smem_bytes, st>>>(map0, map1, mapc, p);

@@ -387,15 +387,14 @@ int launch_umma_gemm_tn(int64_t R, int64_t N, int64_t Kc, int nseg, const float*
   DS_TRY(make_rows_map(&m0, A0, 1, R, Kc));
   DS_TRY(nseg > 1 ? make_rows_map(&m1, Arest, nseg - 1, R, Kc) : make_rows_map(&m1, A0, 1, R, Kc));
   DS_TRY(make_rows_map(&md, D, 1, R, N));
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [&] {
+  static PerDeviceOnce attr_once;
+  DS_TRY(attr_once.run([&]() -> int {
     int dev = 0, max_smem = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    attr_err = cudaFuncSetAttribute(umma_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-  });
-  DS_CHECK(attr_err == cudaSuccess, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+    DS_CUDA(cudaGetDevice(&dev));
+    DS_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    DS_CUDA(cudaFuncSetAttribute(umma_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    return 0;
+  }));
   umma_gemm_tn_kernel<<<g.n_cta, three ? 320 : 192, g.smem_bytes, st>>>(m0, m1, md, p);
   DS_LAUNCHED();
   const int64_t total = (int64_t)g.n_q * BLK * N;
