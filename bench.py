@@ -42,6 +42,10 @@ def parse():
     ap.add_argument("--mode", default=os.environ.get("DEEPSPHERE_MODE", "tf32"), choices=["fp32", "tf32", "tf32x3"])
     ap.add_argument("--no-other-modes", action="store_true")
     ap.add_argument("--no-model", action="store_true")
+    ap.add_argument("--model-only", action="store_true",
+                    help="only the HealpyGCNN training-step measurement; prints its JSON object (used for the "
+                         "experimental-kernel child process)")
+    ap.add_argument("--no-experimental", action="store_true")
     ap.add_argument("--model-nside", type=int, default=256)
     ap.add_argument("--model-batch", type=int, default=16)
     ap.add_argument("--nside", type=int, default=256)
@@ -191,6 +195,12 @@ def model_train_bench(args, mode, device, world):
         opt.step()
         return loss
 
+    # fingerprint of the very first step (same seeds on every run): loss and per-parameter gradient norms before any
+    # update - what an alternative kernel build must reproduce (bench.py --model-only, experimental_model_run)
+    opt.zero_grad(set_to_none=True)
+    loss0 = ((model(x, training=True) - t) ** 2).mean()
+    loss0.backward()
+    first_step = {"loss": float(loss0.detach()), "grad_norms": [float(p.grad.norm()) for p in params]}
     for _ in range(3):
         train_step()
     torch.cuda.synchronize()
@@ -210,8 +220,37 @@ def model_train_bench(args, mode, device, world):
     torch.cuda.empty_cache()
     return {"metric": "HealpyGCNN train maps/s", "value": world * Bm / (ms * 1e-3), "unit": "maps/s",
             "ms_per_step": ms, "batch_per_gpu": Bm, "n_gpus": world, "parameters": n_params, "final_loss": float(loss.detach()),
+            "first_step": first_step,
             "config": f"nside {nside} full sphere ({npix} px): PseudoConv p1 F16 -> [Chebyshev K5 F32 + MAX pool] x3 -> "
                       f"Chebyshev K5 F64 -> AVG pool -> mean -> Dense(2); MSE, Adam, fwd+bwd+all-reduce+step, mode {mode}"}
+
+
+def experimental_model_run(args, baseline):
+    """`bench.py --model-only` in a child process with DEEPSPHERE_SKINNY=1 (bounded: 10 minutes)."""
+    import subprocess
+
+    env = dict(os.environ, DEEPSPHERE_SKINNY="1", CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0"))
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.abspath(__file__), "--model-only", "--mode", args.mode,
+           "--model-nside", str(args.model_nside), "--model-batch", str(args.model_batch)]
+    try:
+        res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+        lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+        if res.returncode != 0 or not lines:
+            return {"switch": "DEEPSPHERE_SKINNY=1", "error": (res.stderr or res.stdout)[-300:]}
+        out = json.loads(lines[-1])
+        out["switch"] = "DEEPSPHERE_SKINNY=1"
+        a, b = baseline["first_step"], out["first_step"]
+        rel = [abs(a["loss"] - b["loss"]) / max(abs(a["loss"]), 1e-12)]
+        rel += [abs(u - v) / max(abs(u), 1e-12) for u, v in zip(a["grad_norms"], b["grad_norms"])]
+        out["first_step_max_rel_diff"] = max(rel)
+        # same forward, same gradients (fp32 summation order differs in the fused weight-gradient sweep)
+        out["validated"] = bool(max(rel) <= 1e-4 and len(a["grad_norms"]) == len(b["grad_norms"]))
+        out["speedup_vs_default"] = baseline["ms_per_step"] / out["ms_per_step"]
+        return out
+    except Exception as exc:
+        return {"switch": "DEEPSPHERE_SKINNY=1", "error": str(exc)[:300]}
 
 
 def main():
@@ -252,6 +291,11 @@ def main():
     device = torch.device("cuda", local_rank)
     dsd.init_from_env()
     mode = args.mode
+    if args.model_only:
+        out = model_train_bench(args, mode, device, world)
+        if rank == 0:
+            print(json.dumps(out))
+        return
     g, layer = build_layer(args, mode)
     M, F, B, K = g.L.shape[0], args.features, args.batch, args.K
     layer.build_from_shape((B, M, F))
@@ -388,6 +432,13 @@ def main():
         except Exception as exc:
             model_train = {"error": str(exc)[:200]}
 
+    # ---- the same training step with the opt-in streaming pseudo-convolution kernels (ds_skinny.cu, written after
+    # this round's GPU budget was spent: host-emulated only, hence not the default).  Separate process so that a fault
+    # there cannot touch this measurement; "validated" = its loss after the same 13 seeded steps equals ours.
+    model_train_experimental = None
+    if model_train is not None and "error" not in model_train and not args.no_experimental and world == 1:
+        model_train_experimental = experimental_model_run(args, model_train)
+
     # ---- e2e: public layer API, pinned host buffers, H2D + D2H inside the timed region ------------
     e2e = None
     if not args.no_e2e:
@@ -492,6 +543,7 @@ def main():
                                    f"batch {B}/GPU fwd+bwd, 8-neighbour HEALPix graph",
                        "mode": mode, "parallelism": f"batch-sharded x{world}", "l2": "inputs (6.4 GB/tensor) >> L2"},
             "roofline": roofline, "layer_roofline": layer_roofline, "kernels": kernels, "other_modes": other_modes, "model_train": model_train,
+            "model_train_experimental": model_train_experimental,
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
         }
         print(json.dumps(line))

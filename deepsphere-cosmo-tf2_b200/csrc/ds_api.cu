@@ -246,6 +246,10 @@ int ds_pconv_forward(int64_t B, int64_t M, int64_t Fin, int64_t Fout, int32_t p,
   DS_TRY(pconv_check(B, M, Fin, Fout, p, act, mode, true, "ds_pconv_forward"));
   DS_CHECK(x && w && y, "ds_pconv_forward: NULL tensor");
   const int64_t r = 1LL << (2 * p), Ro = B * (M / r), Kc = r * Fin;
+  if (skinny_usable(Ro, Kc, Fout)) {  // short reduction (e.g. 4 -> 16 at the head of a network): streaming kernel
+    const int rc = launch_skinny_nn(Ro, Fout, Kc, x, w, bias, Fout, act, y, (cudaStream_t)stream);
+    if (rc >= 0) return rc;
+  }
   return launch_gemm_nn(Ro, Fout, Kc, 1, x, nullptr, 0, Kc, w, Fout, 1, 0, bias, Fout, act, y, Fout,
                         (cudaStream_t)stream);
 }
@@ -254,7 +258,7 @@ int64_t ds_pconv_backward_workspace_elems(int64_t B, int64_t M, int64_t Fin, int
   using namespace ds;
   const int64_t r = 1LL << (2 * p), Ro = B * (M / r), Kc = r * Fin;
   return (act != DS_ACT_LINEAR ? Ro * Fout : 0) + gemm_tn_workspace_elems(Ro, Kc, 1, Fout) +
-         colsum_workspace_elems(Fout) + 64;
+         colsum_workspace_elems(Fout) + skinny_bwd_workspace_elems(Ro, Kc, Fout) + 64;
 }
 
 int ds_pconv_backward(int64_t B, int64_t M, int64_t Fin, int64_t Fout, int32_t p, const float* x, const float* w,
@@ -268,16 +272,26 @@ int ds_pconv_backward(int64_t B, int64_t M, int64_t Fin, int64_t Fout, int32_t p
   const int64_t r = 1LL << (2 * p), Ro = B * (M / r), Kc = r * Fin;
   float* ws = workspace;
   auto take = [&](int64_t n) { float* q = ws; ws += (n + 3) / 4 * 4; return q; };
-  const float* dz = dy;
-  if (act != DS_ACT_LINEAR) {
-    float* dzb = take(Ro * Fout);
-    DS_TRY(launch_act_backward(Ro, Fout, Fout, y, dy, act, dzb, st));
-    dz = dzb;
-  }
+  float* dzb = act != DS_ACT_LINEAR ? take(Ro * Fout) : nullptr;
   float* tn_partial = take(gemm_tn_workspace_elems(Ro, Kc, 1, Fout));
   float* cs_partial = take(colsum_workspace_elems(Fout));
-  if (dbias) DS_TRY(launch_colsum(Ro, Fout, Fout, dz, dbias, cs_partial, st));
-  DS_TRY(launch_gemm_tn(Ro, Fout, Kc, 1, x, nullptr, 0, Kc, dz, Fout, dw, Fout, 1, 0, tn_partial, st));
+  const float* dz = dy;
+  bool done = false;  // dz, dw, dbias produced by the fused streaming sweep
+  if (skinny_usable(Ro, Kc, Fout)) {
+    float* sk_partial = take(skinny_bwd_workspace_elems(Ro, Kc, Fout));
+    const int rc = launch_skinny_pconv_bwd(Ro, Fout, Kc, x, y, dy, act, dx ? dzb : nullptr, dw, dbias, sk_partial, st);
+    if (rc > 0) return rc;
+    done = rc == 0;
+    if (done && dzb != nullptr) dz = dzb;  // only valid (and only needed) when dx is wanted
+  }
+  if (!done) {
+    if (act != DS_ACT_LINEAR) {
+      DS_TRY(launch_act_backward(Ro, Fout, Fout, y, dy, act, dzb, st));
+      dz = dzb;
+    }
+    if (dbias) DS_TRY(launch_colsum(Ro, Fout, Fout, dz, dbias, cs_partial, st));
+    DS_TRY(launch_gemm_tn(Ro, Fout, Kc, 1, x, nullptr, 0, Kc, dz, Fout, dw, Fout, 1, 0, tn_partial, st));
+  }
   if (dx) DS_TRY(launch_gemm_nt(Ro, Kc, Fout, 1, dz, Fout, w, Fout, 1, 0, nullptr, 1, DS_ACT_LINEAR, dx, Kc, 0, st));
   return 0;
 }

@@ -162,4 +162,14 @@ int launch_act_backward(int64_t R, int64_t Ncols, int64_t F, const float* y, con
 int64_t colsum_workspace_elems(int64_t Ncols);
 int launch_colsum(int64_t R, int64_t Ncols, int64_t F, const float* Z, float* out, float* workspace, cudaStream_t st);
 
+// streaming kernels for contractions with a very short reduction (ds_skinny.cu; opt-in with DEEPSPHERE_SKINNY=1).
+// The launchers return -1 (nothing launched) when an operand is not 16-byte aligned: the caller then takes the
+// tiled kernels; 0 = done, > 0 = error (ds_last_error).
+bool skinny_usable(int64_t R, int64_t Kc, int64_t N);
+int64_t skinny_bwd_workspace_elems(int64_t R, int64_t Kc, int64_t N);
+int launch_skinny_nn(int64_t R, int64_t N, int64_t Kc, const float* A, const float* Bm, const float* bias,
+                     int64_t bias_mod, int act, float* C, cudaStream_t st);
+int launch_skinny_pconv_bwd(int64_t R, int64_t N, int64_t Kc, const float* X, const float* y, const float* dy, int act,
+                            float* dz_out, float* dw, float* dbias, float* partial, cudaStream_t st);
+
 }  // namespace ds

@@ -1,0 +1,90 @@
+// CPU stand-in for <cuda_runtime.h> — TEST INFRASTRUCTURE.  Lets g++ compile a simple CUDA kernel source unchanged and
+// run its thread blocks on the host (tests/emul/README in cuda_emul.h): every CUDA thread of a block is a std::thread,
+// __syncthreads() is a block-wide barrier, warp shuffles go through a per-warp exchange buffer.  Only what the
+// emulated sources (csrc/ds_common.cuh, csrc/ds_skinny.cu) use is provided.
+#pragma once
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+#define __launch_bounds__(...)
+
+struct float4 { float x, y, z, w; };
+struct float2 { float x, y; };
+struct int4 { int x, y, z, w; };
+struct uint3 { unsigned x, y, z; };
+struct dim3 { unsigned x = 1, y = 1, z = 1; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+constexpr cudaError_t cudaSuccess = 0;
+constexpr int cudaDevAttrMultiProcessorCount = 16;
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 148; return cudaSuccess; }
+
+namespace emul {
+struct BlockState {
+  std::unique_ptr<std::barrier<>> block_bar;
+  std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
+  std::vector<float> shfl;  // [warps][32]
+};
+inline BlockState*& state() { static BlockState* s = nullptr; return s; }
+}  // namespace emul
+
+inline thread_local uint3 threadIdx{0, 0, 0};
+inline thread_local uint3 blockIdx{0, 0, 0};
+inline thread_local dim3 blockDim;
+inline thread_local dim3 gridDim;
+
+inline void __syncthreads() { emul::state()->block_bar->arrive_and_wait(); }
+inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+  emul::BlockState* s = emul::state();
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  s->shfl[warp * 32 + lane] = v;
+  s->warp_bar[warp]->arrive_and_wait();
+  const float r = s->shfl[warp * 32 + (lane ^ (unsigned)lane_mask)];
+  s->warp_bar[warp]->arrive_and_wait();
+  return r;
+}
+template <class T>
+inline T __ldg(const T* p) { return *p; }
+
+namespace emul {
+// run `kernel()` for every thread of a grid x block launch (1-D), blocks one after the other
+inline void launch(unsigned grid, unsigned block, const std::function<void()>& kernel) {
+  if (block % 32 != 0) { std::fprintf(stderr, "emul: block size must be a multiple of 32\n"); std::abort(); }
+  for (unsigned b = 0; b < grid; ++b) {
+    BlockState st;
+    st.block_bar = std::make_unique<std::barrier<>>(block);
+    for (unsigned w = 0; w < block / 32; ++w) st.warp_bar.push_back(std::make_unique<std::barrier<>>(32));
+    st.shfl.assign(block, 0.f);
+    state() = &st;
+    std::vector<std::thread> threads;
+    for (unsigned t = 0; t < block; ++t)
+      threads.emplace_back([&, t] {
+        threadIdx = uint3{t, 0, 0};
+        blockIdx = uint3{b, 0, 0};
+        blockDim = dim3(block);
+        gridDim = dim3(grid);
+        kernel();
+      });
+    for (auto& th : threads) th.join();
+    state() = nullptr;
+  }
+}
+}  // namespace emul

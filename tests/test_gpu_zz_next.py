@@ -151,3 +151,63 @@ def test_smoothing_built_in_place_preserves_constants(tmp_path):
     assert rel_err(y, orc.smoothing_forward(x, Ks, dtype=np.float64)) <= TOL_FP32
     ones = layer(torch.ones(1, len(idx), 1, device="cuda")).cpu().numpy()
     assert np.abs(ones - 1).max() < 0.05
+
+
+_SKINNY_CHILD = r"""
+import sys
+import numpy as np, torch
+sys.path[:0] = [%(pkg)r, %(root)r]
+from deepsphere import healpy_layers as hl, _native as nat
+from oracle import deepsphere_oracle as orc
+rng = np.random.default_rng(0)
+worst = 0.0
+for (p, Fin, Fout, act, need_dx) in [(1, 1, 16, "relu", False), (1, 2, 8, "elu", True), (2, 1, 64, None, True),
+                                     (1, 3, 32, "tanh", True), (1, 4, 4, "sigmoid", False)]:
+    M, B = 12 * 8 * 8, 3
+    x = rng.standard_normal((B, M, Fin)).astype(np.float32)
+    layer = hl.HealpyPseudoConv(p=p, Fout=Fout, activation=act)
+    layer.build_from_shape(x.shape)
+    with torch.no_grad():
+        layer.bias.normal_()
+    xt = torch.tensor(x, device="cuda", requires_grad=need_dx)
+    y = layer(xt)
+    w = layer.kernel.detach().cpu().numpy().astype(np.float64)
+    b = layer.bias.detach().cpu().numpy().astype(np.float64)
+    ref = orc.pseudo_conv(x.astype(np.float64), w, b, act)
+    e = np.abs(y.detach().cpu().numpy() - ref).max() / np.abs(ref).max()
+    dy = rng.standard_normal(ref.shape).astype(np.float32)
+    y.backward(torch.tensor(dy, device="cuda"))
+    # float64 autograd reference of the same Conv1D
+    xr = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    wr = torch.tensor(w, requires_grad=True); br = torch.tensor(b, requires_grad=True)
+    r = 4 ** p
+    z = xr.reshape(B, M // r, r * Fin) @ wr.reshape(r * Fin, Fout) + br
+    yr = {None: lambda v: v, "relu": torch.relu, "elu": torch.nn.functional.elu, "tanh": torch.tanh,
+          "sigmoid": torch.sigmoid}[act](z)
+    yr.backward(torch.tensor(dy, dtype=torch.float64))
+    rel = lambda a, c: float(np.abs(a - c).max() / max(np.abs(c).max(), 1e-300))
+    e = max(e, rel(layer.kernel.grad.cpu().numpy().reshape(r * Fin, Fout), wr.grad.numpy().reshape(r * Fin, Fout)),
+            rel(layer.bias.grad.cpu().numpy().ravel(), br.grad.numpy().ravel()))
+    if need_dx:
+        e = max(e, rel(xt.grad.cpu().numpy(), xr.grad.numpy()))
+    worst = max(worst, e)
+print("SKINNY_WORST", worst)
+"""
+
+
+def test_streaming_pseudo_conv_kernels_opt_in(tmp_path):
+    """csrc/ds_skinny.cu (DEEPSPHERE_SKINNY=1, read once per process -> child process): forward, weight, bias and
+    input gradients of HealpyPseudoConv on the shapes the streaming kernels serve, against the oracle / float64
+    autograd at the fp32 bar."""
+    import subprocess
+    import sys
+
+    from conftest import PKG, ROOT
+
+    script = tmp_path / "skinny_child.py"
+    script.write_text(_SKINNY_CHILD % {"pkg": PKG, "root": ROOT})
+    env = dict(os.environ, DEEPSPHERE_SKINNY="1")
+    res = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    worst = float([ln for ln in res.stdout.splitlines() if ln.startswith("SKINNY_WORST")][-1].split()[1])
+    assert worst <= TOL_FP32
