@@ -158,11 +158,16 @@ int ds_graph_conv_backward(const ds_plan_t* plan, int32_t recursion, int32_t K, 
   float* ws = workspace;
   auto take = [&](int64_t n) { float* p = ws; ws += (n + 3) / 4 * 4; return p; };
 
-  // 1. gradient w.r.t. the pre-activation
+  // 1. gradient w.r.t. the pre-activation (and, when the opt-in streaming kernel applies, dbias in the same sweep)
   const float* dz = dy;
+  float* cs_partial = take(colsum_workspace_elems(Fout));
+  bool dbias_done = dbias == nullptr;
   if (act != DS_ACT_LINEAR) {
     float* dzb = take(R * Fout);
-    DS_TRY(launch_act_backward(R, Fout, Fout, y, dy, act, dzb, st));
+    const int rc = launch_act_backward_colsum(R, Fout, y, dy, act, dzb, dbias, cs_partial, st);
+    if (rc > 0) return rc;
+    if (rc == 0) dbias_done = true;
+    else DS_TRY(launch_act_backward(R, Fout, Fout, y, dy, act, dzb, st));
     dz = dzb;
   }
   // fused path: dx = fused conv on dz (also emits U_k = T_k(L~^T) dz), dkernel = [dz|U_1..]^T-contracted with x
@@ -170,8 +175,7 @@ int ds_graph_conv_backward(const ds_plan_t* plan, int32_t recursion, int32_t K, 
       umma_tn_supported(R, Fin, Fout, K) == 0) {
     float* U = take((int64_t)(K - 1) * R * Fout);
     float* tn_partial = take(umma_tn_workspace_elems(R, Fin, Fout, K));
-    float* cs_partial = take(colsum_workspace_elems(Fout));
-    if (dbias != nullptr) DS_TRY(launch_colsum(R, Fout, Fout, dz, dbias, cs_partial, st));
+    if (!dbias_done) DS_TRY(launch_colsum(R, Fout, Fout, dz, dbias, cs_partial, st));
     // B_k(o, f) = kernel[(f*K + k)*Fout + o]
     DS_TRY(fused_conv(plan, recursion, K, B, Fout, Fin, dz, U, kernel, 1, Fout, (int64_t)K * Fout, nullptr,
                       DS_ACT_LINEAR, dx, mode, st));
@@ -187,10 +191,9 @@ int ds_graph_conv_backward(const ds_plan_t* plan, int32_t recursion, int32_t K, 
   }
   float* U = K > 1 ? take((int64_t)(K - 1) * R * Fout) : nullptr;
   float* tn_partial = take(std::max(gemm_tn_workspace_elems(R, Fin, K, Fout), umma_tn_workspace_elems(R, Fout, Fin, K)));
-  float* cs_partial = take(colsum_workspace_elems(Fout));
 
   // 3. dbias = sum_{b,m} dz
-  if (dbias != nullptr) DS_TRY(launch_colsum(R, Fout, Fout, dz, dbias, cs_partial, st));
+  if (!dbias_done) DS_TRY(launch_colsum(R, Fout, Fout, dz, dbias, cs_partial, st));
   // 4. dkernel[f*K + k, o] = sum_{b,m} T_k[b,m,f] dz[b,m,o]
   if (mode != DS_MODE_FP32 && umma_tn_supported(R, Fout, Fin, K) == 0) {
     DS_TRY(launch_umma_gemm_tn(R, Fout, Fin, K, x, T, dz, dkernel, (int64_t)K * Fout, Fout, 1, tn_partial, mode, st));
@@ -217,8 +220,13 @@ int ds_bias_act_backward(int64_t R, int64_t F, const float* y, const float* dy, 
   DS_CHECK(dy && dz && R > 0 && F > 0, "ds_bias_act_backward: bad argument");
   DS_CHECK(act == DS_ACT_LINEAR || y != nullptr, "ds_bias_act_backward: y required");
   cudaStream_t st = (cudaStream_t)stream;
-  if (act != DS_ACT_LINEAR) DS_TRY(launch_act_backward(R, F, F, y, dy, act, dz, st));
-  else if (dz != dy) DS_CUDA(cudaMemcpyAsync(dz, dy, sizeof(float) * R * F, cudaMemcpyDeviceToDevice, st));
+  if (act != DS_ACT_LINEAR) {
+    const int rc = workspace != nullptr ? launch_act_backward_colsum(R, F, y, dy, act, dz, dbias, workspace, st) : -1;
+    if (rc >= 0) return rc;  // dz and dbias in one sweep (opt-in streaming kernel)
+    DS_TRY(launch_act_backward(R, F, F, y, dy, act, dz, st));
+  } else if (dz != dy) {
+    DS_CUDA(cudaMemcpyAsync(dz, dy, sizeof(float) * R * F, cudaMemcpyDeviceToDevice, st));
+  }
   if (dbias != nullptr) {
     DS_CHECK(workspace != nullptr, "ds_bias_act_backward: workspace required for dbias");
     DS_TRY(launch_colsum(R, F, F, dz, dbias, workspace, st));

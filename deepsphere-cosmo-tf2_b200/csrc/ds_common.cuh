@@ -161,6 +161,7 @@ int launch_act_backward(int64_t R, int64_t Ncols, int64_t F, const float* y, con
 // colsum[c % F] = sum over rows and folded columns of Z[R, Ncols];  workspace colsum_workspace_elems floats
 int64_t colsum_workspace_elems(int64_t Ncols);
 int launch_colsum(int64_t R, int64_t Ncols, int64_t F, const float* Z, float* out, float* workspace, cudaStream_t st);
+int launch_colsum_final(int64_t Ncols, int64_t F, int nblk, const float* partial, float* out, cudaStream_t st);
 
 // streaming kernels for contractions with a very short reduction (ds_skinny.cu; opt-in with DEEPSPHERE_SKINNY=1).
 // The launchers return -1 (nothing launched) when an operand is not 16-byte aligned: the caller then takes the
@@ -169,6 +170,9 @@ bool skinny_usable(int64_t R, int64_t Kc, int64_t N);
 int64_t skinny_bwd_workspace_elems(int64_t R, int64_t Kc, int64_t N);
 int launch_skinny_nn(int64_t R, int64_t N, int64_t Kc, const float* A, const float* Bm, const float* bias,
                      int64_t bias_mod, int act, float* C, cudaStream_t st);
+// dz = dy * act'(y) and dbias = colsum(dz) in one sweep; workspace: colsum_workspace_elems(F) floats
+int launch_act_backward_colsum(int64_t R, int64_t F, const float* y, const float* dy, int act, float* dz, float* dbias,
+                               float* workspace, cudaStream_t st);
 int launch_skinny_pconv_bwd(int64_t R, int64_t N, int64_t Kc, const float* X, const float* y, const float* dy, int act,
                             float* dz_out, float* dw, float* dbias, float* partial, cudaStream_t st);
 

@@ -351,6 +351,13 @@ int launch_act_backward(int64_t R, int64_t Ncols, int64_t F, const float* y, con
   return 0;
 }
 
+// out[f] = sum over `nblk` block partials [nblk, Ncols] (and folded columns c = f, f + F, ...)
+int launch_colsum_final(int64_t Ncols, int64_t F, int nblk, const float* partial, float* out, cudaStream_t st) {
+  colsum_final_kernel<<<(unsigned)cdiv(F, 32), 256, 0, st>>>(Ncols, F, nblk, partial, out);
+  DS_LAUNCHED();
+  return 0;
+}
+
 int launch_colsum(int64_t R, int64_t Ncols, int64_t F, const float* Z, float* out, float* workspace, cudaStream_t st) {
   const int nblk = (int)std::max<int64_t>(1, std::min<int64_t>(COLSUM_BLOCKS, cdiv(R, 64)));
   colsum_partial_kernel<<<nblk, 256, 0, st>>>(R, Ncols, Z, workspace);

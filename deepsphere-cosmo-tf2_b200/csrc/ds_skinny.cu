@@ -133,6 +133,41 @@ __global__ void skinny_bwd_final_kernel(int N, int KC, int nblk, const float* __
   }
 }
 
+// dz = dy * act'(y) and the column sums of dz in ONE sweep (act_backward_kernel + colsum_partial_kernel read dz a second
+// time).  Thread = (row slot, column group of 4); a block owns a contiguous row range; partial[block][F] feeds the
+// existing deterministic final reduction (colsum_final_kernel's layout).  F / 4 must divide 256.
+__global__ void __launch_bounds__(SK_THREADS) act_backward_colsum_kernel(int64_t R, int F, const float* __restrict__ y,
+                                                                         const float* __restrict__ dy, int act,
+                                                                         float* __restrict__ dz,
+                                                                         float* __restrict__ partial) {
+  __shared__ __align__(16) float4 red4[SK_THREADS];
+  const int cg = F >> 2, tid = threadIdx.x;
+  const int g = tid % cg, slot = tid / cg, slots = SK_THREADS / cg;
+  const int64_t rows_per_block = (R + gridDim.x - 1) / gridDim.x;
+  const int64_t rb = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t re = rb + rows_per_block < R ? rb + rows_per_block : R;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t r = rb + slot; r < re; r += slots) {
+    float4 d = ldg4(dy + r * F + 4 * g);
+    const float4 yv = ldg4(y + r * F + 4 * g);
+    d.x *= act_grad_from_y(yv.x, act); d.y *= act_grad_from_y(yv.y, act);
+    d.z *= act_grad_from_y(yv.z, act); d.w *= act_grad_from_y(yv.w, act);
+    reinterpret_cast<float4*>(dz + r * F)[g] = d;
+    acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+  }
+  red4[tid] = acc;
+  __syncthreads();
+  if (tid < F) {
+    const int gg = tid >> 2, j = tid & 3;
+    float s = 0.f;
+    for (int q = 0; q < slots; ++q) {
+      const float4 v = red4[q * cg + gg];
+      s += j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w));
+    }
+    partial[(int64_t)blockIdx.x * F + tid] = s;
+  }
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 inline bool enabled() {
@@ -202,6 +237,18 @@ int launch_skinny_pconv_bwd(int64_t R, int64_t N, int64_t Kc, const float* X, co
   skinny_bwd_final_kernel<<<(total + 127) / 128, 128, 0, st>>>((int)N, (int)Kc, nblk, partial, dw, dbias);
   DS_LAUNCHED();
   return 0;
+}
+
+int launch_act_backward_colsum(int64_t R, int64_t F, const float* y, const float* dy, int act, float* dz, float* dbias,
+                               float* workspace, cudaStream_t st) {
+  if (!enabled() || act == DS_ACT_LINEAR || dbias == nullptr || R < 1) return -1;
+  if (F < 4 || F > SK_THREADS || (F & (F - 1)) != 0) return -1;  // F/4 must divide 256 and F <= 256 threads
+  if (!aligned16(y) || !aligned16(dy) || !aligned16(dz)) return -1;
+  const int64_t max_blocks = colsum_workspace_elems(F) / F;
+  const int nblk = (int)std::max<int64_t>(1, std::min<int64_t>(max_blocks, (R + 63) / 64));
+  act_backward_colsum_kernel<<<nblk, SK_THREADS, 0, st>>>(R, (int)F, y, dy, act, dz, workspace);
+  DS_LAUNCHED();
+  return launch_colsum_final(F, F, nblk, workspace, dbias, st);
 }
 
 #endif  // DS_EMULATE

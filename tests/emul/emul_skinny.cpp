@@ -63,8 +63,45 @@ static int run_case(int64_t R, int N, int act, unsigned grid, bool with_bias, bo
   return 0;
 }
 
+// act_backward_colsum_kernel: dz bit-exact, block partials [nblk][F] summing to the column sums
+static int run_act_colsum(int64_t R, int F, int act, unsigned grid, unsigned seed) {
+  std::mt19937 rng(seed);
+  std::normal_distribution<float> nd(0.f, 1.f);
+  std::vector<float> Ys(R * F + 4), dYs(R * F + 4), dZs(R * F + 4, -777.f), partial((size_t)grid * F, -555.f);
+  auto aligned = [](std::vector<float>& v) { return reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(v.data()) + 15) & ~uintptr_t(15)); };
+  for (auto& e : Ys) e = nd(rng);
+  for (auto& e : dYs) e = nd(rng);
+  float *Y = aligned(Ys), *dY = aligned(dYs), *dZ = aligned(dZs);
+  emul::launch(grid, 256, [&] { ds::act_backward_colsum_kernel(R, F, Y, dY, act, dZ, partial.data()); });
+  double e_dz = 0, e_cs = 0, scale = 1;
+  std::vector<double> cs(F, 0.0);
+  for (int64_t r = 0; r < R; ++r)
+    for (int f = 0; f < F; ++f) {
+      const float dz = dY[r * F + f] * ds::act_grad_from_y(Y[r * F + f], act);
+      e_dz = std::max(e_dz, (double)std::fabs(dz - dZ[r * F + f]));
+      cs[f] += dz;
+    }
+  for (int f = 0; f < F; ++f) {
+    double s = 0;
+    for (unsigned b = 0; b < grid; ++b) s += partial[(size_t)b * F + f];
+    e_cs = std::max(e_cs, std::fabs(s - cs[f]));
+    scale = std::max(scale, std::fabs(cs[f]));
+  }
+  if (e_dz != 0 || e_cs > 2e-5 * scale) {
+    std::printf("FAIL act_backward_colsum R=%lld F=%d act=%d grid=%u: dz %g colsum %g\n", (long long)R, F, act, grid, e_dz, e_cs);
+    return 1;
+  }
+  std::printf("ok act_backward_colsum R=%lld F=%d act=%d grid=%u: dz bit-exact, colsum err %.2e\n", (long long)R, F, act, grid, e_cs);
+  return 0;
+}
+
 int main() {
   int bad = 0;
+  bad += run_act_colsum(1000, 32, DS_ACT_RELU, 3, 11);    // the HealpyGCNN layers: 32 / 64 channels
+  bad += run_act_colsum(777, 64, DS_ACT_ELU, 4, 12);
+  bad += run_act_colsum(5, 4, DS_ACT_TANH, 2, 13);        // cg = 1; second block has rows, later ones none
+  bad += run_act_colsum(130, 256, DS_ACT_SIGMOID, 5, 14); // widest: 256 columns = 256 threads
+  bad += run_act_colsum(64, 16, DS_ACT_SOFTPLUS, 7, 15);  // more blocks than row chunks
   bad += run_case<4>(1000, 16, DS_ACT_RELU, 3, true, false, 1);    // the HealpyGCNN head: 1 -> 16 channels, p = 1
   bad += run_case<4>(37, 4, DS_ACT_LINEAR, 2, false, false, 2);    // cg = 1, fewer rows than threads
   bad += run_case<8>(513, 8, DS_ACT_ELU, 1, true, true, 3);        // cg = 2, single block, dz requested

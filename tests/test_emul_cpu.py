@@ -25,7 +25,7 @@ def _build_and_run(tmp_path, extra):
 def test_skinny_kernels_on_the_host_emulator(tmp_path):
     res = _build_and_run(str(tmp_path), [])
     assert res.returncode == 0, res.stdout + res.stderr
-    assert res.stdout.count("ok ") == 6 and "FAIL" not in res.stdout
+    assert res.stdout.count("ok ") == 11 and "FAIL" not in res.stdout
 
 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")

@@ -191,14 +191,39 @@ for (p, Fin, Fout, act, need_dx) in [(1, 1, 16, "relu", False), (1, 2, 8, "elu",
     if need_dx:
         e = max(e, rel(xt.grad.cpu().numpy(), xr.grad.numpy()))
     worst = max(worst, e)
+# graph convolution with bias + activation: dz and dbias come from the fused act-backward/column-sum sweep
+from deepsphere import gnn_layers
+from deepsphere.graph import SphereHealpix
+sphere = SphereHealpix(4, k=8)
+Lt, _ = orc.prepare_laplacian(sphere.L, 0.75)
+for (Fin, Fout, act) in [(3, 32, "elu"), (4, 64, "tanh"), (2, 4, "sigmoid")]:
+    x = rng.standard_normal((2, 192, Fin)).astype(np.float32)
+    layer = gnn_layers.Chebyshev(L=sphere.L, K=3, Fout=Fout, use_bias=True, activation=act, mode="fp32")
+    layer.build_from_shape(x.shape)
+    with torch.no_grad():
+        layer.bias.normal_()
+    xt = torch.tensor(x, device="cuda", requires_grad=True)
+    y = layer(xt)
+    dy = rng.standard_normal(tuple(y.shape)).astype(np.float32)
+    y.backward(torch.tensor(dy, device="cuda"))
+    xr = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    wr = layer.kernel.detach().cpu().double().requires_grad_(True)
+    br = layer.bias.detach().cpu().double().requires_grad_(True)
+    z = orc.torch_cpu_graph_conv(xr, Lt, wr, 3, "chebyshev") + br
+    yr = {"elu": torch.nn.functional.elu, "tanh": torch.tanh, "sigmoid": torch.sigmoid}[act](z)
+    yr.backward(torch.tensor(dy, dtype=torch.float64))
+    rel = lambda a, c: float(np.abs(a - c).max() / max(np.abs(c).max(), 1e-300))
+    worst = max(worst, rel(y.detach().cpu().numpy(), yr.detach().numpy()), rel(xt.grad.cpu().numpy(), xr.grad.numpy()),
+                rel(layer.kernel.grad.cpu().numpy(), wr.grad.numpy()),
+                rel(layer.bias.grad.cpu().numpy().ravel(), br.grad.numpy().ravel()))
 print("SKINNY_WORST", worst)
 """
 
 
 def test_streaming_pseudo_conv_kernels_opt_in(tmp_path):
     """csrc/ds_skinny.cu (DEEPSPHERE_SKINNY=1, read once per process -> child process): forward, weight, bias and
-    input gradients of HealpyPseudoConv on the shapes the streaming kernels serve, against the oracle / float64
-    autograd at the fp32 bar."""
+    input gradients of HealpyPseudoConv on the shapes the streaming kernels serve, and a Chebyshev layer with bias +
+    activation (fused act-backward / column-sum sweep), against the oracle / float64 autograd at the fp32 bar."""
     import subprocess
     import sys
 
