@@ -55,7 +55,13 @@ class LatticePlan:
         return np.sort(rows[rows >= 0])
 
 
-def graph_is_healpix8(Lt, nside, indices):
+def neighbour_table(nside):
+    """The 8 NESTED neighbours of every pixel of the sphere, [npix, 8] (one vectorised pass; the plan builder looks
+    pixels up in it ~7 times per pixel, which used to be 60 % of its run time)."""
+    return hpx.neighbours(nside, np.arange(hpx.nside2npix(nside), dtype=np.int64))
+
+
+def graph_is_healpix8(Lt, nside, indices, nb_table=None):
     """True if every off-diagonal non-zero of Lt connects HEALPix 8-neighbours (within `indices`)."""
     npix = hpx.nside2npix(nside)
     indices = np.asarray(indices, dtype=np.int64)
@@ -64,7 +70,7 @@ def graph_is_healpix8(Lt, nside, indices):
         return False
     lut = np.full(npix + 1, -1, dtype=np.int64)
     lut[indices] = np.arange(M)
-    nb = hpx.neighbours(nside, indices)
+    nb = hpx.neighbours(nside, indices) if nb_table is None else nb_table[indices]
     nbrow = lut[nb]  # -1 (missing) indexes the sentinel slot -> -1
     coo = sparse.coo_matrix(Lt)
     off = coo.row != coo.col
@@ -83,7 +89,8 @@ def build_lattice_plan(Lt, nside, indices, H, tile_order=4):
     indices = np.asarray(indices, dtype=np.int64)
     if np.any(np.diff(indices) <= 0):
         return None
-    if not graph_is_healpix8(Lt, nside, indices):
+    NB = neighbour_table(nside)
+    if not graph_is_healpix8(Lt, nside, indices, NB):
         return None
     npix = hpx.nside2npix(nside)
     M = len(indices)
@@ -103,9 +110,8 @@ def build_lattice_plan(Lt, nside, indices, H, tile_order=4):
     own_pix = hpx.xyf2nest(nside, tx[:, None, None] + ii[None], ty[:, None, None] + jj[None], tf[:, None, None])
     pixel[:, H : H + T, H : H + T] = own_pix
 
-    # neighbour table of every pixel of the sphere (chunked lookup keeps this vectorised)
     def nbr_of(p):
-        return hpx.neighbours(nside, p)
+        return NB[p]
 
     # grow ring by ring: position P at ring r is reached from Q = P clamped one step towards the box
     for r in range(1, H + 1):
@@ -140,7 +146,7 @@ def build_lattice_plan(Lt, nside, indices, H, tile_order=4):
     csr = sparse.csr_matrix(Lt)
     csr.sort_indices()
     keys = np.repeat(np.arange(M, dtype=np.int64), np.diff(csr.indptr)) * M + csr.indices.astype(np.int64)
-    nbrow = lut[hpx.neighbours(nside, indices)]  # [M, 8]
+    nbrow = lut[NB[indices]]  # [M, 8]
     cols = np.concatenate([nbrow, np.arange(M)[:, None]], axis=1)  # [M, 9]
     q = np.arange(M, dtype=np.int64)[:, None] * M + np.where(cols >= 0, cols, 0)
     loc = np.searchsorted(keys, q)
@@ -161,7 +167,7 @@ def build_lattice_plan(Lt, nside, indices, H, tile_order=4):
     pos_j, pos_i = np.divmod(np.arange(LW * LW), LW)
     inner = (pos_j >= 1) & (pos_j <= LW - 2) & (pos_i >= 1) & (pos_i <= LW - 2)
     regular = np.ones(nt, dtype=bool)
-    nbr_true_all = hpx.neighbours(nside, np.where(pixel >= 0, pixel, 0))  # [nt, P, 8] face-frame order
+    nbr_true_all = NB[np.where(pixel >= 0, pixel, 0)]  # [nt, P, 8] face-frame order
     for d in range(8):
         tgt = (pos_j + DJ[d]) * LW + (pos_i + DI[d])
         tgt = np.where(inner, tgt, 0)

@@ -231,9 +231,8 @@ class PartitionedHealpyGCNN(torch.nn.Module):
         super().__init__()
         import copy
 
-        from scipy.sparse.linalg import eigsh
-
         from . import healpix as hpx
+        from . import utils
         from . import healpy_layers as hp_nn
         from .graph import SphereHealpix
 
@@ -270,8 +269,7 @@ class PartitionedHealpyGCNN(torch.nn.Module):
                 sphere = SphereHealpix(subdivisions=cur_nside, indexes=cur_idx, nest=True, k=n_neighbors,
                                        lap_type="normalized")
                 L = sphere.L
-                lmax = 1.02 * eigsh(sparse.csr_matrix(L, dtype=np.float64), k=1, which="LM",
-                                    return_eigenvectors=False)[0]
+                lmax = 1.02 * utils.largest_eigenvalue(sparse.csr_matrix(L, dtype=np.float64))
 
                 def make(L_ext, rows, layer=layer, lmax=lmax, nside_l=cur_nside, idx_l=cur_idx):
                     f = copy.copy(layer)

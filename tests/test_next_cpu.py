@@ -246,3 +246,31 @@ def test_get_gsp_filters_weight_view():
     ref = orc.graph_conv_forward(x, Lt, kern.astype(np.float64), 4, "chebyshev", dtype=np.float64)
     spec = np.einsum("mj,ofj,jf->mo", V, resp, V.T @ x[0])
     assert rel_err(spec, ref[0]) < 1e-9
+
+
+# ------------------------------------------------------------------------------------- Laplacian prep: lmax
+def test_largest_eigenvalue_matches_the_reference_arpack_call():
+    """utils.largest_eigenvalue replaces `eigsh(L, k=1, which="LM")` (gnn_layers.py:66) for large symmetric L by an
+    un-restarted Lanczos: same value to fp64 round-off on full-sphere, k-NN and masked graphs, on a matrix whose
+    largest-magnitude eigenvalue is negative, and on the identity (Krylov breakdown at step 0)."""
+    from scipy.sparse.linalg import eigsh
+
+    from deepsphere import utils
+
+    disc = hpx.query_disc(64, [1, 0, 0], 1.0)
+    ext = orc.extend_indices(disc, 64, 8)
+    cases = [SphereHealpix(32, k=8).L, SphereHealpix(32, k=20).L, SphereHealpix(64, indexes=ext, k=8).L,
+             sparse.identity(5000, format="csr"), sparse.diags(np.linspace(-3, 2, 6000)).tocsr()]
+    for L in cases:
+        L = sparse.csr_matrix(L, dtype=np.float64)
+        ref = float(eigsh(L, k=1, which="LM", return_eigenvectors=False)[0])
+        assert abs(utils.largest_eigenvalue(L) - ref) <= 1e-11 * abs(ref)
+    # small or unsymmetric matrices take the reference call itself
+    A = sparse.random(6000, 6000, density=0.001, random_state=1, format="csr")
+    assert utils.largest_eigenvalue(sparse.identity(10, format="csr")) == 1.0
+    assert np.isfinite(utils.largest_eigenvalue(A + sparse.identity(6000)))
+    # and the layer's lmax is the reference recipe's 1.02 * lambda_max
+    L = SphereHealpix(32, k=8).L
+    layer = gnn_layers.Chebyshev(L=L, K=3)
+    _, lmax = orc.prepare_laplacian(L, 0.75)
+    assert abs(layer.lmax - lmax) <= 1e-11 * lmax
