@@ -38,21 +38,21 @@ def rescale_L(L, lmax=2, scale=1):
     return sparse.csr_matrix(L)
 
 
-def largest_eigenvalue(L, tol=1e-10, maxit=20000, min_size=4096):
+def largest_eigenvalue(L, tol=1e-9, maxit=20000, min_size=4096):
     """``eigsh(L, k=1, which="LM", return_eigenvectors=False)[0]`` — the eigenvalue of largest magnitude that the
     reference takes from ARPACK at machine tolerance (gnn_layers.py:66) — for a symmetric sparse L.
 
     ARPACK's restarted Lanczos with its default 20 basis vectors needs ~1 400 products with L at nside 256 and
     ~3 000 at nside 512 (33 s and 217 s on 8 cores, per layer, before the first batch can run); an un-restarted
-    three-term Lanczos reaches the same Ritz value in ~230 steps.  The stopping rule is the residual bound of the
-    extreme Ritz pair, ``|beta_j s_j| <= tol |theta|``, which bounds the eigenvalue error by ``tol |theta|`` and in
-    practice (the error is quadratic in the residual for a symmetric matrix) reproduces ARPACK's value to ~1e-15;
-    the rescaled Laplacian needs it to ~1e-8 for fp32 parity.  Falls back to ARPACK for small or unsymmetric
+    three-term Lanczos reaches the same Ritz value in ~230 steps (k = 20 graphs have a clustered top of the spectrum:
+    ARPACK 8 700 products / 98 s at nside 128, here 7 s).  The stopping rule is the residual bound of the extreme Ritz
+    pair, ``|beta_j s_j| <= tol |theta|``, which bounds the eigenvalue error by ``tol |theta|`` and in practice (the
+    error is quadratic in the residual for a symmetric matrix) reproduces ARPACK's value to 1e-11 .. 1e-15; the
+    rescaled Laplacian needs it to ~1e-8 for fp32 parity.  Falls back to ARPACK for small or unsymmetric
     matrices (where `which="LM"` semantics of the reference are whatever ARPACK does) and on non-convergence;
     ``DEEPSPHERE_LMAX=arpack`` forces the reference call."""
     import os
 
-    from scipy.linalg import eigh_tridiagonal
     from scipy.sparse.linalg import eigsh
 
     def arpack():
@@ -67,14 +67,23 @@ def largest_eigenvalue(L, tol=1e-10, maxit=20000, min_size=4096):
     asym = abs(L - L.T)
     if asym.nnz and asym.max() > 1e-12 * max(abs(L).max(), 1e-300):
         return arpack()
+    theta = _lanczos_extreme(lambda v: L @ v, M, tol, min(maxit, M))
+    return arpack() if theta is None else theta
+
+
+def _lanczos_extreme(matvec, M, tol, maxit):
+    """Ritz value of largest magnitude of the symmetric operator `matvec`, or None if `maxit` steps do not bring
+    its residual bound below ``tol * |theta|``."""
+    from scipy.linalg import eigh_tridiagonal
+
     rng = np.random.default_rng(0)
     q = rng.standard_normal(M)
     q /= np.linalg.norm(q)
     q_prev = np.zeros(M)
     beta = 0.0
     alphas, betas = [], []
-    for j in range(min(maxit, M)):
-        w = L @ q
+    for j in range(maxit):
+        w = matvec(q)
         a = float(q @ w)
         w -= a * q
         w -= beta * q_prev
@@ -91,7 +100,7 @@ def largest_eigenvalue(L, tol=1e-10, maxit=20000, min_size=4096):
                 return float(theta)
         q_prev, q = q, w / b
         beta = b
-    return arpack()
+    return None
 
 
 def plan_from_sparse(L_tilde, ell_width=0):
