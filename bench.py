@@ -434,7 +434,8 @@ def main():
 
     # ---- the same training step with the opt-in streaming pseudo-convolution kernels (ds_skinny.cu, written after
     # this round's GPU budget was spent: host-emulated only, hence not the default).  Separate process so that a fault
-    # there cannot touch this measurement; "validated" = its loss after the same 13 seeded steps equals ours.
+    # there cannot touch this measurement; "validated" = its first-step loss and per-parameter gradient norms (same
+    # seeds, before any update) equal the default path's to 1e-4.
     model_train_experimental = None
     if model_train is not None and "error" not in model_train and not args.no_experimental and world == 1:
         model_train_experimental = experimental_model_run(args, model_train)

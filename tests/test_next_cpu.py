@@ -274,3 +274,43 @@ def test_largest_eigenvalue_matches_the_reference_arpack_call():
     layer = gnn_layers.Chebyshev(L=L, K=3)
     _, lmax = orc.prepare_laplacian(L, 0.75)
     assert abs(layer.lmax - lmax) <= 1e-11 * lmax
+
+
+# ------------------------------------------------------------------------------------- bench.py host logic
+def test_bench_experimental_child_validation(monkeypatch):
+    """bench.py runs the opt-in kernels in a child process and accepts its number only if the first training step
+    (loss, per-parameter gradient norms) reproduces the default path's; a crash or a mismatch is reported, never
+    raised into the parent's measurement."""
+    import argparse
+    import json
+    import subprocess
+    import types
+
+    import bench
+
+    args = argparse.Namespace(mode="tf32", model_nside=256, model_batch=16)
+    base = {"ms_per_step": 8.0, "final_loss": 0.7, "first_step": {"loss": 1.25, "grad_norms": [0.5, 2.0, 1e-3]}}
+
+    def fake_run(out_obj=None, rc=0, stderr=""):
+        def run(cmd, env=None, **kw):
+            assert env["DEEPSPHERE_SKINNY"] == "1" and "--model-only" in cmd and "RANK" not in env
+            stdout = "log line\n" + (json.dumps(out_obj) + "\n" if out_obj is not None else "")
+            return types.SimpleNamespace(returncode=rc, stdout=stdout, stderr=stderr)
+        return run
+
+    good = {"ms_per_step": 6.4, "final_loss": 0.7, "first_step": {"loss": 1.25 * (1 + 2e-6), "grad_norms": [0.5, 2.0, 1e-3]}}
+    monkeypatch.setattr(subprocess, "run", fake_run(good))
+    r = bench.experimental_model_run(args, base)
+    assert r["validated"] is True and abs(r["speedup_vs_default"] - 1.25) < 1e-12 and r["switch"] == "DEEPSPHERE_SKINNY=1"
+    bad = {"ms_per_step": 6.4, "final_loss": 0.7, "first_step": {"loss": 1.25, "grad_norms": [0.5, 2.1, 1e-3]}}
+    monkeypatch.setattr(subprocess, "run", fake_run(bad))
+    assert bench.experimental_model_run(args, base)["validated"] is False
+    monkeypatch.setattr(subprocess, "run", fake_run(None, rc=-11, stderr="CUDA error: an illegal memory access"))
+    r = bench.experimental_model_run(args, base)
+    assert "error" in r and "illegal" in r["error"]
+
+    def boom(*a, **k):
+        raise subprocess.TimeoutExpired("bench", 600)
+
+    monkeypatch.setattr(subprocess, "run", boom)
+    assert "error" in bench.experimental_model_run(args, base)
