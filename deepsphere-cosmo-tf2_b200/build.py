@@ -1,8 +1,12 @@
 """Build libdeepsphere_b200.so (sm_100a only) in-tree with nvcc.
 
-Usage: python build.py [--force]
+Usage: python build.py [--force] [-v] [--variant NAME -DMACRO=VALUE ...]
 The shared library is a plain C-ABI library (include/deepsphere_b200.h); it links only
 against the CUDA runtime (static) — no torch, no Python.
+
+`--variant NAME -D...` builds lib/libdeepsphere_b200_NAME.so from the same sources with extra preprocessor
+definitions (kernel experiment switches such as -DC2_FENCE_BY_ISSUER=1): load it with DEEPSPHERE_LIB=<path> for an
+A/B run against the default build on one GPU box.
 """
 import os
 import subprocess
@@ -39,16 +43,18 @@ def up_to_date():
     return all(os.path.getmtime(p) <= t for p in deps())
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
+def build(force=False, verbose=False, variant=None, defines=()):
+    lib = LIB if variant is None else os.path.join(LIBDIR, f"libdeepsphere_b200_{variant}.so")
+    if variant is None and not force and up_to_date():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     objs = []
     procs = []
+    tag = "" if variant is None else f".{variant}"
     for src in sources():
-        obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + tag + ".o")
         objs.append(obj)
-        cmd = [NVCC, *[f for f in FLAGS if not f.startswith("--use_fast_math")], "-c", src, "-o", obj]
+        cmd = [NVCC, *[f for f in FLAGS if not f.startswith("--use_fast_math")], *defines, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -62,11 +68,13 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
+    cmd = [NVCC, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
            "-lcuda"]
     subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    name = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=name,
+                defines=[a for a in sys.argv[1:] if a.startswith("-D")]))

@@ -83,6 +83,13 @@ struct Conv2Ctl {
 #ifndef C2_FFMA2
 #define C2_FFMA2 1
 #endif
+// Experiment switch (round 2, A/B through DEEPSPHERE_LIB): 1 = the generic->async proxy fence that orders the hop's
+// exchange stores before the UMMA reads is executed ONCE by the issuing lane after it has observed hop_full, instead of
+// by each of the 128 compute threads before its arrive (~300 clk on every hop's dependency chain).  Whether the
+// consumer-side fence is sufficient is exactly what the parity tests of the variant build have to show; default 0.
+#ifndef C2_FENCE_BY_ISSUER
+#define C2_FENCE_BY_ISSUER 0
+#endif
 // ROT = 0: `x` natural channel order, `acc` rotated by one (x.x <-> acc.w, x.y <-> acc.x, ...); ROT = 1: `x` rotated,
 // `acc` natural; ROT = 2: both natural (used with FFMA2).
 __host__ __device__ constexpr int rot_of_hop(int s) { return C2_FFMA2 ? 2 : ((s - 1) & 1); }
@@ -371,7 +378,9 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
             for (int r = 0; r < 3; ++r)
 #pragma unroll
               for (int cc = 0; cc < 3; ++cc) dst[r * C2_LW + cc * 8] = acc[r][cc];
+#if !C2_FENCE_BY_ISSUER
             ptx::fence_proxy_async_smem();
+#endif
             ptx::mbar_arrive(&ctl->hop_full[p]);
             if (probe) pd[3] = clock64();
             float* outp = a.out[s - 1];
@@ -488,6 +497,9 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
               long long* pd = a.dbg + ((size_t)(it & 15) * 5 + s) * 8;
               if (probe) pd[5] = clock64();
               ch[p]++;
+#if C2_FENCE_BY_ISSUER
+              ptx::fence_proxy_async_smem();
+#endif
               ptx::tc_fence_after_sync();
               issue(buf_u32 + (uint32_t)(2 + p) * (uint32_t)(C2_BUF * 16), w_u32, s, false);
               ptx::umma_commit(&ctl->mma_done[p]);
