@@ -264,6 +264,12 @@ def main():
             return
         from deepsphere.graph import SphereHealpix
 
+        # torchrun exports OMP_NUM_THREADS=1 for its workers; the reference arm is rank 0 alone on the box's host
+        # cores and may use all of them
+        try:
+            torch.set_num_threads(max(torch.get_num_threads(), len(os.sched_getaffinity(0))))
+        except (AttributeError, RuntimeError):
+            pass
         g = SphereHealpix(args.nside, k=8)
         steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
         t, nbytes = cpu_reference_time(g.L, args, args.cpu_sample_batch, steps, warmup)
