@@ -46,6 +46,8 @@ def parse():
                     help="only the HealpyGCNN training-step measurement; prints its JSON object (used for the "
                          "experimental-kernel child process)")
     ap.add_argument("--no-experimental", action="store_true")
+    ap.add_argument("--model-graph", action="store_true",
+                    help="with --model-only: capture the training step in a CUDA graph and time graph replays")
     ap.add_argument("--model-nside", type=int, default=256)
     ap.add_argument("--model-batch", type=int, default=16)
     ap.add_argument("--nside", type=int, default=256)
@@ -182,7 +184,8 @@ def model_train_bench(args, mode, device, world):
     model.build(input_shape=(None, npix, 1))
     dsd.broadcast_parameters(model)
     params = model.trainable_variables
-    opt = torch.optim.Adam(params, lr=1e-3)
+    use_graph = bool(getattr(args, "model_graph", False))
+    opt = torch.optim.Adam(params, lr=1e-3, capturable=use_graph)
     gen = torch.Generator(device=device).manual_seed(11 + int(os.environ.get("RANK", "0")))
     x = torch.randn(Bm, npix, 1, device=device, generator=gen)
     t = torch.randn(Bm, 2, device=device, generator=gen)
@@ -201,8 +204,26 @@ def model_train_bench(args, mode, device, world):
     loss0 = ((model(x, training=True) - t) ** 2).mean()
     loss0.backward()
     first_step = {"loss": float(loss0.detach()), "grad_norms": [float(p.grad.norm()) for p in params]}
-    for _ in range(3):
-        train_step()
+    graph = None
+    if use_graph:
+        # whole-step capture (forward, backward, Adam): the C-ABI calls only enqueue work on the current stream and take
+        # their scratch memory from cudaMallocAsync, so the step is capturable; replays remove the host launch path
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                train_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            static_loss = train_step()
+        run_step = lambda: (graph.replay(), static_loss)[1]  # noqa: E731
+    else:
+        run_step = train_step
+        for _ in range(3):
+            train_step()
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
@@ -211,12 +232,12 @@ def model_train_bench(args, mode, device, world):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(n):
-        loss = train_step()
+        loss = run_step()
     b.record()
     torch.cuda.synchronize()
     ms = dsd.allreduce_max(a.elapsed_time(b) / n, device)
     n_params = int(sum(p.numel() for p in params))
-    del model, opt, x, t
+    del graph, model, opt, x, t
     torch.cuda.empty_cache()
     return {"metric": "HealpyGCNN train maps/s", "value": world * Bm / (ms * 1e-3), "unit": "maps/s",
             "ms_per_step": ms, "batch_per_gpu": Bm, "n_gpus": world, "parameters": n_params, "final_loss": float(loss.detach()),
@@ -225,32 +246,40 @@ def model_train_bench(args, mode, device, world):
                       f"Chebyshev K5 F64 -> AVG pool -> mean -> Dense(2); MSE, Adam, fwd+bwd+all-reduce+step, mode {mode}"}
 
 
-def experimental_model_run(args, baseline):
-    """`bench.py --model-only` in a child process with DEEPSPHERE_SKINNY=1 (bounded: 10 minutes)."""
+def experimental_model_run(args, baseline, switch_env=None, extra_args=()):
+    """`bench.py --model-only` in a child process (bounded: 10 minutes) with an opt-in switch: `switch_env` (e.g.
+    DEEPSPHERE_SKINNY=1) and / or extra flags (--model-graph).  The child's number only counts as validated if its
+    first training step reproduces the default path's loss and per-parameter gradient norms."""
     import subprocess
 
-    env = dict(os.environ, DEEPSPHERE_SKINNY="1", CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0"))
+    switch_env = dict(switch_env or {})
+    label = " ".join([f"{k}={v}" for k, v in switch_env.items()] + list(extra_args))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0"), **switch_env)
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
     cmd = [sys.executable, os.path.abspath(__file__), "--model-only", "--mode", args.mode,
-           "--model-nside", str(args.model_nside), "--model-batch", str(args.model_batch)]
+           "--model-nside", str(args.model_nside), "--model-batch", str(args.model_batch), *extra_args]
     try:
         res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
         lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
         if res.returncode != 0 or not lines:
-            return {"switch": "DEEPSPHERE_SKINNY=1", "error": (res.stderr or res.stdout)[-300:]}
+            return {"switch": label, "error": (res.stderr or res.stdout)[-300:]}
         out = json.loads(lines[-1])
-        out["switch"] = "DEEPSPHERE_SKINNY=1"
+        out["switch"] = label
         a, b = baseline["first_step"], out["first_step"]
         rel = [abs(a["loss"] - b["loss"]) / max(abs(a["loss"]), 1e-12)]
         rel += [abs(u - v) / max(abs(u), 1e-12) for u, v in zip(a["grad_norms"], b["grad_norms"])]
         out["first_step_max_rel_diff"] = max(rel)
-        # same forward, same gradients (fp32 summation order differs in the fused weight-gradient sweep)
-        out["validated"] = bool(max(rel) <= 1e-4 and len(a["grad_norms"]) == len(b["grad_norms"]))
+        # same forward, same gradients (fp32 summation order differs in the fused weight-gradient sweep); a graph
+        # replay must also land on the same loss after the same number of steps
+        ok = max(rel) <= 1e-4 and len(a["grad_norms"]) == len(b["grad_norms"])
+        if "--model-graph" in extra_args:
+            ok = ok and abs(out["final_loss"] - baseline["final_loss"]) <= 1e-3 * max(abs(baseline["final_loss"]), 1e-12)
+        out["validated"] = bool(ok)
         out["speedup_vs_default"] = baseline["ms_per_step"] / out["ms_per_step"]
         return out
     except Exception as exc:
-        return {"switch": "DEEPSPHERE_SKINNY=1", "error": str(exc)[:300]}
+        return {"switch": label, "error": str(exc)[:300]}
 
 
 def main():
@@ -444,7 +473,11 @@ def main():
     # seeds, before any update) equal the default path's to 1e-4.
     model_train_experimental = None
     if model_train is not None and "error" not in model_train and not args.no_experimental and world == 1:
-        model_train_experimental = experimental_model_run(args, model_train)
+        model_train_experimental = {
+            "streaming_kernels": experimental_model_run(args, model_train, {"DEEPSPHERE_SKINNY": "1"}),
+            "cuda_graph": experimental_model_run(args, model_train, None, ("--model-graph",)),
+            "both": experimental_model_run(args, model_train, {"DEEPSPHERE_SKINNY": "1"}, ("--model-graph",)),
+        }
 
     # ---- e2e: public layer API, pinned host buffers, H2D + D2H inside the timed region ------------
     e2e = None

@@ -291,6 +291,8 @@ def test_bench_experimental_child_validation(monkeypatch):
     args = argparse.Namespace(mode="tf32", model_nside=256, model_batch=16)
     base = {"ms_per_step": 8.0, "final_loss": 0.7, "first_step": {"loss": 1.25, "grad_norms": [0.5, 2.0, 1e-3]}}
 
+    monkeypatch.setenv("RANK", "0")
+
     def fake_run(out_obj=None, rc=0, stderr=""):
         def run(cmd, env=None, **kw):
             assert env["DEEPSPHERE_SKINNY"] == "1" and "--model-only" in cmd and "RANK" not in env
@@ -300,17 +302,24 @@ def test_bench_experimental_child_validation(monkeypatch):
 
     good = {"ms_per_step": 6.4, "final_loss": 0.7, "first_step": {"loss": 1.25 * (1 + 2e-6), "grad_norms": [0.5, 2.0, 1e-3]}}
     monkeypatch.setattr(subprocess, "run", fake_run(good))
-    r = bench.experimental_model_run(args, base)
+    sw = {"DEEPSPHERE_SKINNY": "1"}
+    r = bench.experimental_model_run(args, base, sw)
     assert r["validated"] is True and abs(r["speedup_vs_default"] - 1.25) < 1e-12 and r["switch"] == "DEEPSPHERE_SKINNY=1"
+    # a graph replay must also reproduce the final loss
+    r = bench.experimental_model_run(args, base, sw, ("--model-graph",))
+    assert r["validated"] is True and r["switch"] == "DEEPSPHERE_SKINNY=1 --model-graph"
+    drift = dict(good, final_loss=0.71)
+    monkeypatch.setattr(subprocess, "run", fake_run(drift))
+    assert bench.experimental_model_run(args, base, sw, ("--model-graph",))["validated"] is False
     bad = {"ms_per_step": 6.4, "final_loss": 0.7, "first_step": {"loss": 1.25, "grad_norms": [0.5, 2.1, 1e-3]}}
     monkeypatch.setattr(subprocess, "run", fake_run(bad))
-    assert bench.experimental_model_run(args, base)["validated"] is False
+    assert bench.experimental_model_run(args, base, sw)["validated"] is False
     monkeypatch.setattr(subprocess, "run", fake_run(None, rc=-11, stderr="CUDA error: an illegal memory access"))
-    r = bench.experimental_model_run(args, base)
+    r = bench.experimental_model_run(args, base, sw)
     assert "error" in r and "illegal" in r["error"]
 
     def boom(*a, **k):
         raise subprocess.TimeoutExpired("bench", 600)
 
     monkeypatch.setattr(subprocess, "run", boom)
-    assert "error" in bench.experimental_model_run(args, base)
+    assert "error" in bench.experimental_model_run(args, base, sw)
