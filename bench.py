@@ -203,7 +203,7 @@ def model_train_bench(args, mode, device, world):
     opt.zero_grad(set_to_none=True)
     loss0 = ((model(x, training=True) - t) ** 2).mean()
     loss0.backward()
-    first_step = {"loss": float(loss0.detach()), "grad_norms": [float(p.grad.norm()) for p in params]}
+    first_step = {"loss": float(loss0.detach()), "grad_norms": [float(p.grad.norm()) if p.grad is not None else 0.0 for p in params]}
     graph = None
     if use_graph:
         # whole-step capture (forward, backward, Adam): the C-ABI calls only enqueue work on the current stream and take
