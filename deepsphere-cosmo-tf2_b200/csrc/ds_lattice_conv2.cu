@@ -136,11 +136,28 @@ __device__ __forceinline__ float4 f4_scale(float w, const float4& x) {
 __device__ __noinline__ float4 act4(float4 v, int act) {
   return make_float4(act_apply(v.x, act), act_apply(v.y, act), act_apply(v.z, act), act_apply(v.w, act));
 }
+#ifndef DS_EMULATE
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ptx::smem_u32(dst)), "l"(src), "r"(src_bytes)
                : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#define C2_SETMAXNREG_INC(n) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(n))
+#define C2_SETMAXNREG_DEC(n) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(n))
+#define C2_DYNAMIC_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
+// volatile: keeps the scaled weight in its register (ptxas otherwise re-multiplies at every use)
+#define C2_SCALED_WEIGHT(dst, v, scale) asm volatile("mul.rn.f32 %0, %1, %2;" : "=f"(dst) : "f"(v), "f"(scale))
+#else  // host emulation (tests/emul): same semantics with plain C++
+inline void cp_async16(void* dst, const void* src, uint32_t src_bytes) {
+  std::memset(dst, 0, 16);
+  std::memcpy(dst, src, src_bytes);
+}
+inline void cp_async_wait_all() {}
+#define C2_SETMAXNREG_INC(n) ((void)0)
+#define C2_SETMAXNREG_DEC(n) ((void)0)
+#define C2_DYNAMIC_SMEM(name) uint8_t* const name = emul::dynamic_smem()
+#define C2_SCALED_WEIGHT(dst, v, scale) (dst) = (v) * (scale)
+#endif
 
 // stencil direction index of the plan's weight table for (drow, dcol) (lattice.py: SW, W, NW, N, NE, E, SE, S, centre)
 __device__ __forceinline__ constexpr int dir_of(int dr, int dc) {
@@ -217,7 +234,7 @@ __device__ __forceinline__ void hop_perimeter(float4 (&acc)[3][3], const float (
 
 template <bool CHEB>
 __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv2Args a) {
-  extern __shared__ __align__(128) uint8_t c2_smem[];
+  C2_DYNAMIC_SMEM(c2_smem);
   float4* const bufs = reinterpret_cast<float4*>(c2_smem);  // S0, S1 (input staging), X0, X1 (hop results)
   const int N = a.N, nsteps = a.nsteps;
   const uint32_t img_bytes = (uint32_t)N * C2_FC * 4;                 // one (chunk, hop) weight image
@@ -252,7 +269,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
 
   if (warp < 4) {
     // ================================ compute warps ================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C2_REG_COMPUTE));
+    C2_SETMAXNREG_INC(C2_REG_COMPUTE);
     // (skipping the block rows that lie outside the valid region of hops 3, 4 was measured: no gain, the kernel is
     // bound by the per-hop dependency chain, not by issue slots)
     const int R = 2 * warp + (lane >> 4), q = (lane >> 3) & 1, cb = lane & 7;
@@ -325,10 +342,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
         for (int cc = 0; cc < 3; ++cc) {
           const float* wp = a.w + ((size_t)tile * C2_P + (size_t)(3 * R + r) * C2_LW + 3 * cb + cc) * 9;
 #pragma unroll
-          for (int d = 0; d < 9; ++d) {
-            // volatile: keeps the scaled weight in its register (ptxas otherwise re-multiplies at every use)
-            asm volatile("mul.rn.f32 %0, %1, %2;" : "=f"(w[r][cc][d]) : "f"(__ldg(wp + d)), "f"(a.wscale));
-          }
+          for (int d = 0; d < 9; ++d) C2_SCALED_WEIGHT(w[r][cc][d], __ldg(wp + d), a.wscale);
         }
 #pragma unroll
       for (int mt = 0; mt < 3; ++mt) {  // accumulator row (mt, TMEM lane) -> lattice position -> row of y
@@ -441,7 +455,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
     if (pend) epilogue();
   } else if (warp == 4) {
     // ================================ UMMA issuer / weight streamer ================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REG_IO));
+    C2_SETMAXNREG_DEC(C2_REG_IO);
     if (lane == 0) {
       uint32_t total_items = 0;
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -523,7 +537,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
     __syncwarp();
   } else {
     // ================================ input gather warps ================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C2_REG_IO));
+    C2_SETMAXNREG_DEC(C2_REG_IO);
     const int t = tid - 5 * 32;           // 0..95
     const int q = t & 1, pl0 = t >> 1;    // channel quad; position within a pair of lattice rows (0..47)
     const int inpos = pl0 % C2_LW, r0 = pl0 / C2_LW;
@@ -593,6 +607,8 @@ size_t conv2_smem_bytes(int N, int nsteps) {
 }
 
 }  // namespace
+
+#ifndef DS_EMULATE  // tests/emul runs the kernels above on the host; the launchers below need nvcc
 
 // Is the register-resident fused kernel available for this call?
 bool lattice_conv2_usable(const LatticeDev& L, int nsteps, int F, int N, int mode) {
@@ -682,5 +698,7 @@ int launch_lattice_conv2(const LatticeDev& L, int nsteps, int64_t B, int64_t M, 
   if (e != cudaSuccess) return fail("lattice_conv2_kernel launch failed: %s", cudaGetErrorString(e));
   return 0;
 }
+
+#endif  // DS_EMULATE
 
 }  // namespace ds

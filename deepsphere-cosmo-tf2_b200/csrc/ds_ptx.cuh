@@ -3,6 +3,10 @@
 // Every wait is bounded: a protocol bug traps (launch error) instead of hanging the GPU.
 #pragma once
 
+#ifdef DS_EMULATE  // host emulation of this header (tests/emul/ds_ptx_emul.h, on the include path of the emulator build)
+#include "ds_ptx_emul.h"
+#else
+
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -184,3 +188,5 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 }  // namespace ptx
 }  // namespace ds
+
+#endif  // DS_EMULATE

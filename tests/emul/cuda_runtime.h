@@ -4,11 +4,17 @@
 // emulated sources (csrc/ds_common.cuh, csrc/ds_skinny.cu) use is provided.
 #pragma once
 #include <barrier>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <functional>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -20,6 +26,7 @@
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
 #define __launch_bounds__(...)
+#define __noinline__
 
 struct float4 { float x, y, z, w; };
 struct float2 { float x, y; };
@@ -27,6 +34,21 @@ struct int4 { int x, y, z, w; };
 struct uint3 { unsigned x, y, z; };
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
+// packed fp32 FMA: two IEEE fused multiply-adds
+inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)}; }
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+inline long long clock64() { return (long long)std::chrono::steady_clock::now().time_since_epoch().count(); }
+inline void __trap() { std::fprintf(stderr, "emul: __trap()\n"); std::abort(); }
+inline void __nanosleep(unsigned) { std::this_thread::yield(); }
+inline long long min(long long a, long long b) { return a < b ? a : b; }
+inline long min(long a, long b) { return a < b ? a : b; }
+inline int min(int a, int b) { return a < b ? a : b; }
+inline long long max(long long a, long long b) { return a > b ? a : b; }
+inline long max(long a, long b) { return a > b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+using std::isfinite;
 
 typedef int cudaError_t;
 typedef void* cudaStream_t;
@@ -38,10 +60,19 @@ inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 148; return cudaSuccess; }
 
 namespace emul {
+struct MbarState { uint32_t expected = 0; int32_t pending = 0; int64_t tx = 0; uint32_t phase = 0; };
 struct BlockState {
   std::unique_ptr<std::barrier<>> block_bar;
   std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
   std::vector<float> shfl;  // [warps][32]
+  // dynamic shared memory, tensor memory (128 lanes x 512 columns), mbarriers and named barriers of the block
+  std::vector<uint8_t> dyn_smem_storage;
+  uint8_t* dyn_smem = nullptr;
+  std::vector<uint32_t> tmem;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::map<const void*, MbarState> mbar;
+  std::map<int, std::unique_ptr<std::barrier<>>> named;
 };
 inline BlockState*& state() { static BlockState* s = nullptr; return s; }
 }  // namespace emul
@@ -51,7 +82,13 @@ inline thread_local uint3 blockIdx{0, 0, 0};
 inline thread_local dim3 blockDim;
 inline thread_local dim3 gridDim;
 
+namespace emul {
+inline uint8_t* dynamic_smem() { return state()->dyn_smem; }
+}  // namespace emul
 inline void __syncthreads() { emul::state()->block_bar->arrive_and_wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emul::state()->warp_bar[threadIdx.x >> 5]->arrive_and_wait(); }
+template <class T>
+inline void __stcs(T* p, const T& v) { *p = v; }
 inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
   emul::BlockState* s = emul::state();
   const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -66,10 +103,13 @@ inline T __ldg(const T* p) { return *p; }
 
 namespace emul {
 // run `kernel()` for every thread of a grid x block launch (1-D), blocks one after the other
-inline void launch(unsigned grid, unsigned block, const std::function<void()>& kernel) {
+inline void launch(unsigned grid, unsigned block, const std::function<void()>& kernel, size_t dyn_smem_bytes = 0) {
   if (block % 32 != 0) { std::fprintf(stderr, "emul: block size must be a multiple of 32\n"); std::abort(); }
   for (unsigned b = 0; b < grid; ++b) {
     BlockState st;
+    st.dyn_smem_storage.assign(dyn_smem_bytes + 1024, 0xCD);  // poisoned: reads of unwritten smem show up
+    st.dyn_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(st.dyn_smem_storage.data()) + 1023) & ~uintptr_t(1023));
+    st.tmem.assign(128 * 512, 0xCDCDCDCDu);
     st.block_bar = std::make_unique<std::barrier<>>(block);
     for (unsigned w = 0; w < block / 32; ++w) st.warp_bar.push_back(std::make_unique<std::barrier<>>(32));
     st.shfl.assign(block, 0.f);
