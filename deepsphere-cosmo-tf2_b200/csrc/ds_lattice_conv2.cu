@@ -46,8 +46,25 @@ constexpr int C2_FC = 8;               // channels per work item = one UMMA K st
 constexpr int C2_NQ = C2_FC / 4;       // float4 planes per buffer
 constexpr int C2_PL = 26 * C2_LW + 4;  // float4 per plane (+4: the two planes start on complementary bank groups)
 constexpr int C2_BUF = C2_NQ * C2_PL;  // float4 per exchange buffer
-constexpr int C2_THREADS = 256, C2_NCOMP = 128, C2_NLOAD = 96;
-constexpr int C2_REG_COMPUTE = 208, C2_REG_IO = 48;  // 128 * 208 + 128 * 48 = 256 * 128 registers per CTA
+// Rows of the pixel block a compute thread owns (3 columns wide).  3 (default, the measured kernel): 64 blocks x 2
+// channel quads = 4 compute warps, 81 weights + 72 basis values per thread.  2 (experiment, -DC2_BR=2): 96 blocks =
+// 6 compute warps, 54 weights + 48 basis values per thread -> 136 registers, i.e. 12 instead of 8 compute warps per
+// SM to hide the per-hop dependency chain, for 14 instead of 16 perimeter loads per 54 instead of 81 FMAs.
+#ifndef C2_BR
+#define C2_BR 3
+#endif
+static_assert(C2_BR == 3 || C2_BR == 2, "block rows");
+constexpr int C2_NCW = (C2_LW / C2_BR) / 2;  // compute warps: a warp covers two block rows x 8 column blocks x 2 quads
+constexpr int C2_NCOMP = 32 * C2_NCW, C2_NLOAD = 96, C2_THREADS = C2_NCOMP + 32 + C2_NLOAD;
+// registers per CTA: C2_NCOMP * compute + 128 * io <= 32768 (two CTAs per SM); overridable for the variant builds
+#ifndef C2_REGS_COMPUTE
+#define C2_REGS_COMPUTE (C2_BR == 3 ? 208 : 136)
+#endif
+#ifndef C2_REGS_IO
+#define C2_REGS_IO 48
+#endif
+constexpr int C2_REG_COMPUTE = C2_REGS_COMPUTE, C2_REG_IO = C2_REGS_IO;
+static_assert(C2_NCOMP * C2_REG_COMPUTE + 128 * C2_REG_IO <= 32768, "register budget of two CTAs per SM");
 constexpr int C2_TMEM_COLS = 256;
 
 struct Conv2Args {
@@ -170,9 +187,10 @@ __device__ __forceinline__ constexpr int dir_of(int dr, int dc) {
 //   hop_perimeter: acc += taps whose source is one of the 16 perimeter pixels (loaded from `src`, which points at the
 //                  thread's own (r = 0, cc = 0) position of the buffer holding `in` of all threads); halved if HALVE
 template <bool HAS_OLD, int ROT>
-__device__ __forceinline__ void hop_inside(const float4 (&in)[3][3], float4 (&acc)[3][3], const float (&w)[3][3][9]) {
+__device__ __forceinline__ void hop_inside(const float4 (&in)[C2_BR][3], float4 (&acc)[C2_BR][3],
+                                           const float (&w)[C2_BR][3][9]) {
 #pragma unroll
-  for (int r = 0; r < 3; ++r)
+  for (int r = 0; r < C2_BR; ++r)
 #pragma unroll
     for (int cc = 0; cc < 3; ++cc) {
       if (HAS_OLD) f4_fms<ROT>(w[r][cc][8], in[r][cc], acc[r][cc]);
@@ -183,50 +201,50 @@ __device__ __forceinline__ void hop_inside(const float4 (&in)[3][3], float4 (&ac
 #pragma unroll
     for (int dc = -1; dc <= 1; ++dc)
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+      for (int r = 0; r < C2_BR; ++r)
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
           if (dr == 0 && dc == 0) continue;
           const int sr = r + dr, sc = cc + dc;
-          if (!(sr >= 0 && sr < 3 && sc >= 0 && sc < 3)) continue;
+          if (!(sr >= 0 && sr < C2_BR && sc >= 0 && sc < 3)) continue;
           f4_fma<ROT>(w[r][cc][dir_of(dr, dc)], in[sr][sc], acc[r][cc]);
         }
 }
 template <bool HALVE, int ROT>
-__device__ __forceinline__ void hop_perimeter(float4 (&acc)[3][3], const float (&w)[3][3][9],
+__device__ __forceinline__ void hop_perimeter(float4 (&acc)[C2_BR][3], const float (&w)[C2_BR][3][9],
                                               const float4* __restrict__ src) {
   // position offsets of columns -1, 0, 1, 2, 3 relative to the own column-0 position
   constexpr int CO[5] = {15, 0, 8, 16, 1};
-  float4 top[5], bot[5], lft[3], rgt[3];
+  float4 top[5], bot[5], lft[C2_BR], rgt[C2_BR];
 #pragma unroll
   for (int k = 0; k < 5; ++k) top[k] = src[-C2_LW + CO[k]];
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
+  for (int r = 0; r < C2_BR; ++r) {
     lft[r] = src[r * C2_LW + 15];
     rgt[r] = src[r * C2_LW + 1];
   }
 #pragma unroll
-  for (int k = 0; k < 5; ++k) bot[k] = src[3 * C2_LW + CO[k]];
+  for (int k = 0; k < 5; ++k) bot[k] = src[C2_BR * C2_LW + CO[k]];
 #pragma unroll
   for (int dr = -1; dr <= 1; ++dr)
 #pragma unroll
     for (int dc = -1; dc <= 1; ++dc)
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+      for (int r = 0; r < C2_BR; ++r)
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
           if (dr == 0 && dc == 0) continue;
           const int sr = r + dr, sc = cc + dc;
-          if (sr >= 0 && sr < 3 && sc >= 0 && sc < 3) continue;
+          if (sr >= 0 && sr < C2_BR && sc >= 0 && sc < 3) continue;
           const float wv = w[r][cc][dir_of(dr, dc)];
           if (sr < 0) f4_fma<ROT>(wv, top[sc + 1], acc[r][cc]);
-          else if (sr > 2) f4_fma<ROT>(wv, bot[sc + 1], acc[r][cc]);
+          else if (sr > C2_BR - 1) f4_fma<ROT>(wv, bot[sc + 1], acc[r][cc]);
           else if (sc < 0) f4_fma<ROT>(wv, lft[sr], acc[r][cc]);
           else f4_fma<ROT>(wv, rgt[sr], acc[r][cc]);
         }
   if (HALVE) {
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+    for (int r = 0; r < C2_BR; ++r)
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc) acc[r][cc] = f4_scale(0.5f, acc[r][cc]);
   }
@@ -261,23 +279,23 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
     ptx::mbar_init(&ctl->acc_empty, 4);
     ptx::fence_mbar_init();
   }
-  if (warp == 4) ptx::tmem_alloc(&ctl->tmem_base, C2_TMEM_COLS);
+  if (warp == C2_NCW) ptx::tmem_alloc(&ctl->tmem_base, C2_TMEM_COLS);
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = ctl->tmem_base;
 
-  if (warp < 4) {
+  if (warp < C2_NCW) {
     // ================================ compute warps ================================
     C2_SETMAXNREG_INC(C2_REG_COMPUTE);
     // (skipping the block rows that lie outside the valid region of hops 3, 4 was measured: no gain, the kernel is
     // bound by the per-hop dependency chain, not by issue slots)
     const int R = 2 * warp + (lane >> 4), q = (lane >> 3) & 1, cb = lane & 7;
-    const int own0 = q * C2_PL + (3 * R + 1) * C2_LW + cb;  // float4 index of the own (0, 0) position
+    const int own0 = q * C2_PL + (C2_BR * R + 1) * C2_LW + cb;  // float4 index of the own (0, 0) position
     const int FV = a.F / 4, NV16 = N / 16;
     const bool has_out = a.out[0] != nullptr || a.out[1] != nullptr || a.out[2] != nullptr || a.out[3] != nullptr;
-    float w[3][3][9];
-    float4 A[3][3], Bv[3][3];
+    float w[C2_BR][3][9];
+    float4 A[C2_BR][3], Bv[C2_BR][3];
     uint32_t it = 0, g = 0;
     uint32_t cnt_done[2] = {0, 0}, par[2] = {0, 0};
     int last_bar = -1;
@@ -337,10 +355,10 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
         ptx::named_bar_sync(1, C2_NCOMP);
       }
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+      for (int r = 0; r < C2_BR; ++r)
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
-          const float* wp = a.w + ((size_t)tile * C2_P + (size_t)(3 * R + r) * C2_LW + 3 * cb + cc) * 9;
+          const float* wp = a.w + ((size_t)tile * C2_P + (size_t)(C2_BR * R + r) * C2_LW + 3 * cb + cc) * 9;
 #pragma unroll
           for (int d = 0; d < 9; ++d) C2_SCALED_WEIGHT(w[r][cc][d], __ldg(wp + d), a.wscale);
         }
@@ -360,7 +378,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
           ptx::mbar_wait(&ctl->in_full[st], (it >> 1) & 1);
           if (a.dbg != nullptr && blockIdx.x == 0 && it < 16 && tid == 0) a.dbg[((size_t)(it & 15) * 5) * 8 + 1] = clock64();
 #pragma unroll
-          for (int r = 0; r < 3; ++r)
+          for (int r = 0; r < C2_BR; ++r)
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc) A[r][cc] = S[own0 + r * C2_LW + cc * 8];
 
@@ -371,7 +389,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
           // hop: positions outside the shrinking valid region hold don't-care values that never reach a valid
           // output (a valid output only reads valid inputs).
           // (st.async + complete_tx instead of STS + proxy fence was measured: ~20 B/clk, 3x slower.)
-          auto finish_hop = [&](auto s_tag, float4(&acc)[3][3], const float4* src) {
+          auto finish_hop = [&](auto s_tag, float4(&acc)[C2_BR][3], const float4* src) {
             constexpr int s = decltype(s_tag)::value;
             constexpr int p = (s - 1) & 1;
             const bool probe = a.dbg != nullptr && blockIdx.x == 0 && it < 16 && tid == 0;
@@ -389,7 +407,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
             if (probe) pd[2] = clock64();
             float4* dst = X[p] + own0;
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
+            for (int r = 0; r < C2_BR; ++r)
 #pragma unroll
               for (int cc = 0; cc < 3; ++cc) dst[r * C2_LW + cc * 8] = acc[r][cc];
 #if !C2_FENCE_BY_ISSUER
@@ -401,10 +419,10 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
             if (outp != nullptr) {
               float4* ob = reinterpret_cast<float4*>(outp + (b * a.M * a.F + c * C2_FC)) + q;
 #pragma unroll
-              for (int r = 0; r < 3; ++r)
+              for (int r = 0; r < C2_BR; ++r)
 #pragma unroll
                 for (int cc = 0; cc < 3; ++cc) {
-                  const int row = s_pix[(3 * R + r) * C2_LW + 3 * cb + cc];
+                  const int row = s_pix[(C2_BR * R + r) * C2_LW + 3 * cb + cc];
                   const float4 v = hop_is_rotated(s) ? make_float4(acc[r][cc].w, acc[r][cc].x, acc[r][cc].y, acc[r][cc].z) : acc[r][cc];
                   if (row >= 0) __stcs(ob + (int64_t)row * FV, v);
                 }
@@ -442,7 +460,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
           last_par = par[last];
 
           if (c == n_chunks - 1) {
-            pend = true;
+            pend = C2_NCW <= 4 || warp < 4;  // TMEM lanes 32 (w % 4) .. + 31 belong to warp w: warps 0-3 drain
             pend_g = g;
             pend_b = b;
             pend_rows[0] = erow[0]; pend_rows[1] = erow[1]; pend_rows[2] = erow[2];
@@ -453,7 +471,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
       }
     }
     if (pend) epilogue();
-  } else if (warp == 4) {
+  } else if (warp == C2_NCW) {
     // ================================ UMMA issuer / weight streamer ================================
     C2_SETMAXNREG_DEC(C2_REG_IO);
     if (lane == 0) {
@@ -538,7 +556,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
   } else {
     // ================================ input gather warps ================================
     C2_SETMAXNREG_DEC(C2_REG_IO);
-    const int t = tid - 5 * 32;           // 0..95
+    const int t = tid - (C2_NCW + 1) * 32;  // 0..95
     const int q = t & 1, pl0 = t >> 1;    // channel quad; position within a pair of lattice rows (0..47)
     const int inpos = pl0 % C2_LW, r0 = pl0 / C2_LW;
     const int col = 3 * (inpos & 7) + (inpos >> 3);
@@ -574,7 +592,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == C2_NCW) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, C2_TMEM_COLS);
   }

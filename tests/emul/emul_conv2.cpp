@@ -68,8 +68,8 @@ int main(int argc, char** argv) {
   for (int s = 0; s < C2_H; ++s) a.out[s] = u[s];
   a.b_img = img; a.bias = bias; a.act = (int)act; a.y = y;
   const size_t smem = conv2_smem_bytes((int)N, (int)nsteps);
-  std::printf("emul_conv2: %ld tiles, B %ld, F %ld -> N %ld, %ld hops, grid %ld x 256 threads, %zu bytes smem\n", n_tiles, B, F, N,
-              nsteps, grid, smem);
+  std::printf("emul_conv2: %ld tiles, B %ld, F %ld -> N %ld, %ld hops, grid %ld x %d threads, %zu bytes smem\n", n_tiles, B, F, N,
+              nsteps, grid, C2_THREADS, smem);
   if (cheb) emul::launch((unsigned)grid, C2_THREADS, [&] { lattice_conv2_kernel<true>(a); }, smem);
   else emul::launch((unsigned)grid, C2_THREADS, [&] { lattice_conv2_kernel<false>(a); }, smem);
   store(dir + "/y.bin", y, ny);

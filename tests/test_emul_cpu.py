@@ -34,3 +34,92 @@ def test_skinny_kernels_have_no_shared_memory_race(tmp_path):
     if "FATAL: ThreadSanitizer" in res.stderr and "unexpected memory mapping" in res.stderr:
         pytest.skip("ThreadSanitizer cannot run in this container (ASLR settings)")
     assert res.returncode == 0 and "WARNING: ThreadSanitizer" not in res.stderr, res.stdout + res.stderr[-2000:]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The fused lattice convolution kernel (csrc/ds_lattice_conv2.cu) on the host emulator: warp-specialised roles, mbarrier
+# protocol, cp.async gathers, UMMA shared-memory descriptors, tensor-memory epilogue — the unchanged source, default build
+# and the experiment variants (tools/build_variants.sh), against the oracle.
+def _build_conv2(tmp_path, name, defines):
+    exe = os.path.join(tmp_path, name)
+    cmd = ["g++", "-std=c++20", "-O1", "-pthread", "-DDS_EMULATE", *defines, "-I", os.path.join(HERE, "emul"),
+           os.path.join(HERE, "emul", "emul_conv2.cpp"), "-o", exe]
+    subprocess.run(cmd, check=True, cwd=ROOT, capture_output=True, text=True)
+    return exe
+
+
+def _conv2_problem():
+    import numpy as np
+    from deepsphere import gnn_layers
+    from deepsphere.graph import SphereHealpix
+
+    g = SphereHealpix(32, k=8)
+    out = {}
+    for cls, K in ((gnn_layers.Chebyshev, 5), (gnn_layers.Monomial, 4)):
+        layer = cls(L=g.L, K=K, Fout=16)
+        out[cls.__name__] = (layer, layer._lattice_payload())
+    return g, out
+
+
+@pytest.fixture(scope="module")
+def conv2_problem():
+    return _conv2_problem()
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+@pytest.mark.parametrize("variant,defines", [
+    ("default", []),
+    ("fence", ["-DC2_FENCE_BY_ISSUER=1"]),
+    ("br2", ["-DC2_BR=2"]),
+    ("br2r144", ["-DC2_BR=2", "-DC2_REGS_COMPUTE=144", "-DC2_REGS_IO=40"]),
+])
+def test_fused_lattice_kernel_on_the_host_emulator(tmp_path, conv2_problem, variant, defines):
+    import numpy as np
+    from scipy import sparse
+
+    from helpers import orc
+
+    exe = _build_conv2(str(tmp_path), "emul_conv2_" + variant, defines)
+    g, layers = conv2_problem
+    M = g.L.shape[0]
+    rng = np.random.default_rng(7)
+    cases = [  # (layer class, B, F, N, activation id, bias, b_split, grid, basis wanted)
+        ("Chebyshev", 1, 8, 16, 0, True, 1, 2, True),
+        ("Monomial", 2, 16, 32, 1, False, 2, 3, False),
+    ]
+    for name, B, F, N, act, has_bias, b_split, grid, want_basis in cases:
+        layer, pay = layers[name]
+        K = layer.K
+        assert pay is not None and pay["n_tiles"] == 24 and pay["LW"] == 24 and pay["H"] == 4
+        d = os.path.join(str(tmp_path), f"{variant}_{name}")
+        os.makedirs(d)
+        x = rng.standard_normal((B, M, F)).astype(np.float32)
+        W = (rng.standard_normal((F * K, N)) * 0.2).astype(np.float32)
+        bias = rng.standard_normal(N).astype(np.float32)
+        for arr, fn in ((pay["pix"], "pix"), (pay["w"], "w"), (x, "x"), (W, "W"), (bias, "bias")):
+            arr.tofile(os.path.join(d, fn + ".bin"))
+        cheb = int(name == "Chebyshev")
+        with open(os.path.join(d, "meta.txt"), "w") as f:
+            f.write(f"{pay['n_tiles']} {B} {M} {F} {N} {K - 1} {cheb} {act} {int(has_bias)} {grid} {b_split} "
+                    f"{int(want_basis)}\n")
+        res = subprocess.run([exe, d], capture_output=True, text=True, timeout=900)
+        assert res.returncode == 0, res.stdout + res.stderr[-2000:]
+        y = np.fromfile(os.path.join(d, "y.bin"), dtype=np.float32).reshape(B, M, N)
+        Lt = sparse.csr_matrix((layer._L_values.astype(np.float64), (layer._L_indices[:, 0], layer._L_indices[:, 1])),
+                               shape=(M, M))
+        ref = orc.graph_conv_forward(x.astype(np.float64), Lt, W.astype(np.float64), K, name.lower(),
+                                     bias=bias.reshape(1, 1, -1).astype(np.float64) if has_bias else None,
+                                     activation="relu" if act == 1 else None, dtype=np.float64)
+        own = pay["pix"].reshape(pay["n_tiles"], 24, 24)[:, 4:20, 4:20].ravel()
+        own = np.sort(own[own >= 0])
+        assert len(own) == 24 * 256
+        other = np.setdiff1d(np.arange(M), own)
+        assert np.isnan(y[:, other]).all()  # rows of the irregular tiles belong to the generic path: untouched
+        err = np.abs(y[:, own] - ref[:, own]).max() / np.abs(ref).max()
+        assert err <= 1e-3, (variant, name, err)  # TF32 contraction (the GPU measures 5e-4)
+        if want_basis:  # fp32 recursion: T_1..T_{K-1} on the own pixels
+            t_prev, t_cur = x.astype(np.float64), np.stack([Lt @ x[b].astype(np.float64) for b in range(B)])
+            for s in range(1, K):
+                u = np.fromfile(os.path.join(d, f"u{s}.bin"), dtype=np.float32).reshape(B, M, F)
+                assert np.abs(u[:, own] - t_cur[:, own]).max() <= 1e-5 * np.abs(t_cur).max(), (variant, s)
+                t_prev, t_cur = t_cur, 2 * np.stack([Lt @ t_cur[b] for b in range(B)]) - t_prev

@@ -1,0 +1,11 @@
+#!/usr/bin/env bash
+# Builds the A/B libraries of the fused-kernel experiments (run HERE before a gpurun call: the .so files travel with the
+# snapshot).  Each is the same source with preprocessor switches; load one with DEEPSPHERE_LIB=<path>.
+set -e
+B=deepsphere-cosmo-tf2_b200/build.py
+python $B                                                          # default
+python $B --variant fence   -DC2_FENCE_BY_ISSUER=1                 # proxy fence by the UMMA-issuing lane
+python $B --variant br2     -DC2_BR=2                              # 2x3 pixel blocks, 6 compute warps, 136 / 48 registers
+python $B --variant br2r144 -DC2_BR=2 -DC2_REGS_COMPUTE=144 -DC2_REGS_IO=40
+python $B --variant br2fence -DC2_BR=2 -DC2_REGS_COMPUTE=144 -DC2_REGS_IO=40 -DC2_FENCE_BY_ISSUER=1
+ls -la deepsphere-cosmo-tf2_b200/lib/*.so

@@ -19,17 +19,18 @@ for sk in 0 1; do
   DEEPSPHERE_SKINNY=$sk ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
     --log-file gpurun_out/r2_launches_model_skinny$sk.csv python tools/profile_model.py > gpurun_out/r2_model_prof_skinny$sk.log 2>&1
 done
-# 6. fused-kernel experiment: proxy fence by the issuing lane (build it HERE first, the .so travels with the snapshot:
-#    python deepsphere-cosmo-tf2_b200/build.py --variant fence -DC2_FENCE_BY_ISSUER=1)
-V=deepsphere-cosmo-tf2_b200/lib/libdeepsphere_b200_fence.so
-if [ -f "$V" ]; then
+# 6. fused-kernel experiments (build them HERE first: bash tools/build_variants.sh; the .so files travel with the
+#    snapshot).  Every variant has run on the host emulator (tests/test_emul_cpu.py); this decides parity and speed.
+for V in deepsphere-cosmo-tf2_b200/lib/libdeepsphere_b200_*.so; do
+  [ -f "$V" ] || continue
+  name=$(basename "$V" .so)
   {
-    echo "== fence variant: parity of the fused kernel =="
-    DEEPSPHERE_LIB=$PWD/$V python -m pytest tests/test_gpu_lattice.py tests/test_gpu_tensor_core.py -q -m gpu 2>&1 | tail -5
-    echo "== fence variant: layer bench =="
-    DEEPSPHERE_LIB=$PWD/$V python bench.py --no-model --no-e2e --no-cpu-baseline --no-other-modes 2>&1 | tail -1
-  } > gpurun_out/r2_variant_fence.log 2>&1
-  tail -c 900 gpurun_out/r2_variant_fence.log
-fi
+    echo "== $name: parity of the fused kernel =="
+    DEEPSPHERE_LIB=$PWD/$V timeout 600 python -m pytest tests/test_gpu_lattice.py tests/test_gpu_tensor_core.py -q -m gpu 2>&1 | tail -5
+    echo "== $name: layer bench =="
+    DEEPSPHERE_LIB=$PWD/$V timeout 600 python bench.py --no-model --no-e2e --no-cpu-baseline --no-other-modes 2>&1 | tail -1
+  } > gpurun_out/r2_variant_$name.log 2>&1
+  tail -c 700 gpurun_out/r2_variant_$name.log
+done
 tail -c 600 gpurun_out/r2_tests.log
 tail -c 1500 gpurun_out/r2_bench_default.log
