@@ -5,6 +5,7 @@ set -e
 B=deepsphere-cosmo-tf2_b200/build.py
 python $B                                                          # default
 python $B --variant fence   -DC2_FENCE_BY_ISSUER=1                 # proxy fence by the UMMA-issuing lane
+python $B --variant r216    -DC2_REGS_COMPUTE=216 -DC2_REGS_IO=40   # default blocks, 8 more registers for the compute warps
 python $B --variant br2     -DC2_BR=2                              # 2x3 pixel blocks, 6 compute warps, 136 / 48 registers
 python $B --variant br2r144 -DC2_BR=2 -DC2_REGS_COMPUTE=144 -DC2_REGS_IO=40
 python $B --variant br2fence -DC2_BR=2 -DC2_REGS_COMPUTE=144 -DC2_REGS_IO=40 -DC2_FENCE_BY_ISSUER=1
