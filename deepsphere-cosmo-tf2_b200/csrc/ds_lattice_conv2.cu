@@ -181,6 +181,18 @@ __device__ __forceinline__ constexpr int dir_of(int dr, int dc) {
   return dr == 0 ? (dc < 0 ? 0 : (dc > 0 ? 4 : 8)) : (dr > 0 ? (dc < 0 ? 1 : (dc == 0 ? 2 : 3)) : (dc > 0 ? 5 : (dc == 0 ? 6 : 7)));
 }
 
+// Experiment switch: 1 = exploit L~_pq = L~_qp for the links BETWEEN two pixels of the thread's own block: the weight is
+// kept once (by the pixel that comes first in the block), 20 of the 81 weight registers of a 3x3 block and 11 of the 54
+// of a 2x3 block disappear.  L~ is symmetric up to fp32 rounding of the two stored copies (1e-6 relative, the tolerance
+// the plan already accepts for using the same stencil in the backward pass), so results move at that level.
+#ifndef C2_SYMW
+#define C2_SYMW 0
+#endif
+#if C2_SYMW
+// the weight of the tap (r, cc) <- (sr, sc), both inside the block, is read from the OTHER pixel's table entry
+__host__ __device__ constexpr bool sym_other(int r, int cc, int sr, int sc) { return (sr * 3 + sc) < (r * 3 + cc); }
+#endif
+
 // One hop on the thread's 3x3 block, in two parts so that the part that needs no other thread's data overlaps the
 // wait for the neighbours:
 //   hop_inside:    acc <- w_c * in - (HAS_OLD ? acc : 0) + taps whose source pixel lies inside the block (49 of 81)
@@ -207,7 +219,12 @@ __device__ __forceinline__ void hop_inside(const float4 (&in)[C2_BR][3], float4 
           if (dr == 0 && dc == 0) continue;
           const int sr = r + dr, sc = cc + dc;
           if (!(sr >= 0 && sr < C2_BR && sc >= 0 && sc < 3)) continue;
+#if C2_SYMW
+          f4_fma<ROT>(sym_other(r, cc, sr, sc) ? w[sr][sc][dir_of(-dr, -dc)] : w[r][cc][dir_of(dr, dc)], in[sr][sc],
+                      acc[r][cc]);
+#else
           f4_fma<ROT>(w[r][cc][dir_of(dr, dc)], in[sr][sc], acc[r][cc]);
+#endif
         }
 }
 template <bool HALVE, int ROT>
@@ -359,8 +376,20 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
           const float* wp = a.w + ((size_t)tile * C2_P + (size_t)(C2_BR * R + r) * C2_LW + 3 * cb + cc) * 9;
+#if C2_SYMW
+#pragma unroll
+          for (int dr = -1; dr <= 1; ++dr)
+#pragma unroll
+            for (int dc = -1; dc <= 1; ++dc) {
+              const int sr = r + dr, sc = cc + dc, d = dir_of(dr, dc);
+              const bool inside = sr >= 0 && sr < C2_BR && sc >= 0 && sc < 3 && d != 8;
+              if (inside && sym_other(r, cc, sr, sc)) continue;  // kept by the other pixel of the link
+              C2_SCALED_WEIGHT(w[r][cc][d], __ldg(wp + d), a.wscale);
+            }
+#else
 #pragma unroll
           for (int d = 0; d < 9; ++d) C2_SCALED_WEIGHT(w[r][cc][d], __ldg(wp + d), a.wscale);
+#endif
         }
 #pragma unroll
       for (int mt = 0; mt < 3; ++mt) {  // accumulator row (mt, TMEM lane) -> lattice position -> row of y

@@ -71,7 +71,8 @@ def conv2_problem():
     ("default", []),
     ("fence", ["-DC2_FENCE_BY_ISSUER=1"]),
     ("br2", ["-DC2_BR=2"]),
-    ("br2r144", ["-DC2_BR=2", "-DC2_REGS_COMPUTE=144", "-DC2_REGS_IO=40"]),
+    ("symw", ["-DC2_SYMW=1"]),
+    ("br2symw", ["-DC2_BR=2", "-DC2_SYMW=1", "-DC2_REGS_COMPUTE=144", "-DC2_REGS_IO=40"]),
 ])
 def test_fused_lattice_kernel_on_the_host_emulator(tmp_path, conv2_problem, variant, defines):
     import numpy as np
