@@ -188,6 +188,10 @@ __device__ __forceinline__ constexpr int dir_of(int dr, int dc) {
 #ifndef C2_SYMW
 #define C2_SYMW 0
 #endif
+// Experiment switch: 1 = software-pipelined accumulator drain (see the epilogue)
+#ifndef C2_EPI_PIPE
+#define C2_EPI_PIPE 0
+#endif
 #if C2_SYMW
 // the weight of the tap (r, cc) <- (sr, sc), both inside the block, is read from the OTHER pixel's table entry
 __host__ __device__ constexpr bool sym_other(int r, int cc, int sr, int sc) { return (sr * 3 + sc) < (r * 3 + cc); }
@@ -327,6 +331,46 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
     auto epilogue = [&]() {
       ptx::mbar_wait(&ctl->acc_full, pend_g & 1);
       ptx::tc_fence_after_sync();
+#if C2_EPI_PIPE
+      // one flat loop over the 3 * N / 16 accumulator slices with the tensor-memory load of slice i + 1 in flight while
+      // slice i is biased, activated and stored (the ncu source page shows the drain waiting on every tcgen05.ld)
+      {
+        const int n_slices = 3 * NV16;
+        const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16);
+        uint32_t rbuf[2][16];
+        ptx::tmem_ld_32x32b_x16(t0, rbuf[0]);
+        ptx::tmem_ld_wait();
+#pragma unroll 1
+        for (int i = 0; i < n_slices; i += 2) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int cur = i + h;
+            if (cur >= n_slices) break;
+            const int mt = cur / NV16, cc = cur - mt * NV16;
+            if (cur + 1 < n_slices) {
+              const int nmt = (cur + 1) / NV16, ncc = (cur + 1) - nmt * NV16;
+              ptx::tmem_ld_32x32b_x16(t0 + (uint32_t)(nmt * N + ncc * 16), rbuf[h ^ 1]);
+            }
+            const int row = pend_rows[mt];
+            if (row >= 0) {
+              float* yrow = a.y + (pend_b * a.M + row) * (int64_t)N;
+#pragma unroll
+              for (int v = 0; v < 4; ++v) {
+                float4 o = make_float4(__uint_as_float(rbuf[h][v * 4]), __uint_as_float(rbuf[h][v * 4 + 1]),
+                                       __uint_as_float(rbuf[h][v * 4 + 2]), __uint_as_float(rbuf[h][v * 4 + 3]));
+                if (a.bias != nullptr) {
+                  const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + cc * 16 + v * 4));
+                  o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                }
+                if (a.act != DS_ACT_LINEAR) o = act4(o, a.act);
+                __stcs(reinterpret_cast<float4*>(yrow + cc * 16 + v * 4), o);
+              }
+            }
+            ptx::tmem_ld_wait();
+          }
+        }
+      }
+#else
 #pragma unroll 1
       for (int mt = 0; mt < 3; ++mt) {
         const int row = pend_rows[mt];
@@ -351,6 +395,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
           }
         }
       }
+#endif
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&ctl->acc_empty);
