@@ -188,6 +188,11 @@ __device__ __forceinline__ constexpr int dir_of(int dr, int dc) {
 #ifndef C2_SYMW
 #define C2_SYMW 0
 #endif
+// 0 = compile the clock64 timeline probe (DEEPSPHERE_CONV2_DEBUG) out of the kernel: its predicates, branches and
+// constant loads are ~5 % of the instructions the compute warps issue (ncu source page, r1k capture)
+#ifndef C2_PROBE
+#define C2_PROBE 1
+#endif
 // Experiment switch: 1 = software-pipelined accumulator drain (see the epilogue)
 #ifndef C2_EPI_PIPE
 #define C2_EPI_PIPE 0
@@ -448,9 +453,9 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
           const uint32_t st = it & 1;
           const float4* S = bufs + (size_t)st * C2_BUF;
           float4* X[2] = {bufs + 2 * (size_t)C2_BUF, bufs + 3 * (size_t)C2_BUF};
-          if (a.dbg != nullptr && blockIdx.x == 0 && it < 16 && tid == 0) a.dbg[((size_t)(it & 15) * 5) * 8 + 0] = clock64();
+          if (C2_PROBE && a.dbg != nullptr && blockIdx.x == 0 && it < 16 && tid == 0) a.dbg[((size_t)(it & 15) * 5) * 8 + 0] = clock64();
           ptx::mbar_wait(&ctl->in_full[st], (it >> 1) & 1);
-          if (a.dbg != nullptr && blockIdx.x == 0 && it < 16 && tid == 0) a.dbg[((size_t)(it & 15) * 5) * 8 + 1] = clock64();
+          if (C2_PROBE && a.dbg != nullptr && blockIdx.x == 0 && it < 16 && tid == 0) a.dbg[((size_t)(it & 15) * 5) * 8 + 1] = clock64();
 #pragma unroll
           for (int r = 0; r < C2_BR; ++r)
 #pragma unroll
@@ -466,7 +471,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
           auto finish_hop = [&](auto s_tag, float4(&acc)[C2_BR][3], const float4* src) {
             constexpr int s = decltype(s_tag)::value;
             constexpr int p = (s - 1) & 1;
-            const bool probe = a.dbg != nullptr && blockIdx.x == 0 && it < 16 && tid == 0;
+            const bool probe = C2_PROBE && a.dbg != nullptr && blockIdx.x == 0 && it < 16 && tid == 0;
             long long* pd = a.dbg + ((size_t)(it & 15) * 5 + s) * 8;
             if (probe) pd[0] = clock64();
             // the UMMAs that read X[p] two hops ago: probe now, consume after the arithmetic (hides the round trip)
@@ -599,7 +604,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
             for (int s = 1; s <= nsteps; ++s) {
               const int p = (s - 1) & 1;
               ptx::mbar_wait_backoff(&ctl->hop_full[p], ch[p] & 1, (uint32_t)a.sleep_mma);
-              const bool probe = a.dbg != nullptr && blockIdx.x == 0 && it < 16;
+              const bool probe = C2_PROBE && a.dbg != nullptr && blockIdx.x == 0 && it < 16;
               long long* pd = a.dbg + ((size_t)(it & 15) * 5 + s) * 8;
               if (probe) pd[5] = clock64();
               ch[p]++;

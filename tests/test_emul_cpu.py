@@ -73,7 +73,9 @@ def conv2_problem():
     ("br2", ["-DC2_BR=2"]),
     ("epipipe", ["-DC2_EPI_PIPE=1"]),
     ("symw", ["-DC2_SYMW=1"]),
-    ("br2symwepi", ["-DC2_BR=2", "-DC2_SYMW=1", "-DC2_EPI_PIPE=1", "-DC2_REGS_COMPUTE=144", "-DC2_REGS_IO=40"]),
+    ("br3all", ["-DC2_SYMW=1", "-DC2_EPI_PIPE=1", "-DC2_PROBE=0"]),
+    ("all", ["-DC2_BR=2", "-DC2_SYMW=1", "-DC2_EPI_PIPE=1", "-DC2_PROBE=0", "-DC2_REGS_COMPUTE=144", "-DC2_REGS_IO=40",
+             "-DC2_FENCE_BY_ISSUER=1"]),
 ])
 def test_fused_lattice_kernel_on_the_host_emulator(tmp_path, conv2_problem, variant, defines):
     import numpy as np
