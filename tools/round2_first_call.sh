@@ -21,16 +21,17 @@ for sk in 0 1; do
 done
 # 6. fused-kernel experiments (build them HERE first: bash tools/build_variants.sh; the .so files travel with the
 #    snapshot).  Every variant has run on the host emulator (tests/test_emul_cpu.py); this decides parity and speed.
-for V in deepsphere-cosmo-tf2_b200/lib/libdeepsphere_b200_*.so; do
+# VARIANTS="fence all" bash tools/round2_first_call.sh   restricts the list (about 2 GPU-minutes per variant)
+for name in ${VARIANTS:-fence noprobe epipipe symw br3all br2r144 br2symwepi all}; do
+  V=deepsphere-cosmo-tf2_b200/lib/libdeepsphere_b200_$name.so
   [ -f "$V" ] || continue
-  name=$(basename "$V" .so)
   {
     echo "== $name: parity of the fused kernel =="
-    DEEPSPHERE_LIB=$PWD/$V timeout 600 python -m pytest tests/test_gpu_lattice.py tests/test_gpu_tensor_core.py -q -m gpu 2>&1 | tail -5
+    DEEPSPHERE_LIB=$PWD/$V timeout 600 python -m pytest tests/test_gpu_lattice.py -q -m gpu -k "fused or conv2" 2>&1 | tail -4
     echo "== $name: layer bench =="
-    DEEPSPHERE_LIB=$PWD/$V timeout 600 python bench.py --no-model --no-e2e --no-cpu-baseline --no-other-modes 2>&1 | tail -1
+    DEEPSPHERE_LIB=$PWD/$V timeout 600 python bench.py --steps 5 --warmup 3 --no-model --no-e2e --no-cpu-baseline --no-other-modes 2>&1 | tail -1 | cut -c1-1400
   } > gpurun_out/r2_variant_$name.log 2>&1
-  tail -c 700 gpurun_out/r2_variant_$name.log
+  tail -c 500 gpurun_out/r2_variant_$name.log
 done
 tail -c 600 gpurun_out/r2_tests.log
 tail -c 1500 gpurun_out/r2_bench_default.log
