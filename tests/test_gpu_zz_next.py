@@ -63,15 +63,16 @@ def test_bernstein_bias_activation_and_textbook_last_term():
 
 
 def test_bernstein_on_the_fused_tensor_core_kernel():
-    """nside 16 full sphere, order 4 = 5 Chebyshev terms: tf32 mode runs the register-resident fused kernel.  It
+    """nside 32 full sphere (the smallest with regular 16 x 16 tiles), order 4 = 5 Chebyshev terms: tf32 mode runs the
+    register-resident fused kernel.  It
     must equal the Chebyshev layer fed with the basis-changed weights (same launch), and the literal Bernstein
     loops within the TF32 bar scaled by the basis change: the TF32 rounding (1e-3) acts on W' = C W and on the
     Chebyshev basis, and sum_j |C[i, j]| reaches 6 at K = 4 -> 4e-3 forward (a CPU emulation of the truncation
     gives 1.6e-3), 1e-2 for the gradients, which pass through C a second time."""
-    sphere = SphereHealpix(16, k=8)
+    sphere = SphereHealpix(32, k=8)
     rng = np.random.default_rng(9)
     K, Fin, Fout = 4, 8, 16
-    x = rng.standard_normal((2, 12 * 16 * 16, Fin)).astype(np.float32)
+    x = rng.standard_normal((2, 12 * 32 * 32, Fin)).astype(np.float32)
     W = (rng.standard_normal(((K + 1) * Fin, Fout)) * 0.2).astype(np.float32)
     bern = gnn_layers.Bernstein(L=sphere.L, K=K, Fout=Fout, mode="tf32")
     bern.build_from_shape(x.shape)
