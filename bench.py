@@ -247,7 +247,7 @@ def model_train_bench(args, mode, device, world):
 
 
 def experimental_model_run(args, baseline, switch_env=None, extra_args=()):
-    """`bench.py --model-only` in a child process (bounded: 10 minutes) with an opt-in switch: `switch_env` (e.g.
+    """`bench.py --model-only` in a child process (bounded: 4 minutes) with an opt-in switch: `switch_env` (e.g.
     DEEPSPHERE_SKINNY=1) and / or extra flags (--model-graph).  The child's number only counts as validated if its
     first training step reproduces the default path's loss and per-parameter gradient norms."""
     import subprocess
@@ -260,7 +260,7 @@ def experimental_model_run(args, baseline, switch_env=None, extra_args=()):
     cmd = [sys.executable, os.path.abspath(__file__), "--model-only", "--mode", args.mode,
            "--model-nside", str(args.model_nside), "--model-batch", str(args.model_batch), *extra_args]
     try:
-        res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+        res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
         lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
         if res.returncode != 0 or not lines:
             return {"switch": label, "error": (res.stderr or res.stdout)[-300:]}
@@ -473,11 +473,13 @@ def main():
     # seeds, before any update) equal the default path's to 1e-4.
     model_train_experimental = None
     if model_train is not None and "error" not in model_train and not args.no_experimental and world == 1:
-        model_train_experimental = {
-            "streaming_kernels": experimental_model_run(args, model_train, {"DEEPSPHERE_SKINNY": "1"}),
-            "cuda_graph": experimental_model_run(args, model_train, None, ("--model-graph",)),
-            "both": experimental_model_run(args, model_train, {"DEEPSPHERE_SKINNY": "1"}, ("--model-graph",)),
-        }
+        model_train_experimental = {}
+        for key, env_sw, flags in (("streaming_kernels", {"DEEPSPHERE_SKINNY": "1"}, ()),
+                                   ("cuda_graph", None, ("--model-graph",)),
+                                   ("both", {"DEEPSPHERE_SKINNY": "1"}, ("--model-graph",))):
+            model_train_experimental[key] = experimental_model_run(args, model_train, env_sw, flags)
+            if "timed out" in str(model_train_experimental[key].get("error", "")):
+                break  # do not spend more of the bench's minutes on a child that hangs
 
     # ---- e2e: public layer API, pinned host buffers, H2D + D2H inside the timed region ------------
     e2e = None
