@@ -88,6 +88,9 @@ struct Conv2Args {
 
 struct Conv2Ctl {
   uint64_t in_full[2], in_empty[2], w_full[2], item_done[2], hop_full[2], mma_done[2], acc_full, acc_empty;
+#if C2_SPLIT_BAR
+  uint64_t hop_ready[2];
+#endif
   uint32_t tmem_base;
 };
 
@@ -192,6 +195,15 @@ __device__ __forceinline__ constexpr int dir_of(int dr, int dc) {
 // constant loads are ~5 % of the instructions the compute warps issue (ncu source page, r1k capture)
 #ifndef C2_PROBE
 #define C2_PROBE 1
+#endif
+// Experiment switch: 1 = two barriers per hop.  hop_ready: every compute thread arrives right after its exchange stores
+// (generic proxy; mbarrier arrive / wait are release / acquire) and it is what the NEXT hop's perimeter loads wait for;
+// the generic->async proxy fence and the arrive on hop_full (what the UMMA issuer waits for) move behind the next hop's
+// own-register taps, where the stores have long landed: the ~300 clk of FENCE.VIEW.ASYNC leave the hop-to-hop
+// dependency chain without touching the ordering the UMMA reads rely on (each thread still fences its own stores
+// before it arrives on hop_full).
+#ifndef C2_SPLIT_BAR
+#define C2_SPLIT_BAR 0
 #endif
 // Experiment switch: 1 = software-pipelined accumulator drain (see the epilogue)
 #ifndef C2_EPI_PIPE
@@ -299,6 +311,9 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
       ptx::mbar_init(&ctl->w_full[i], 1);
       ptx::mbar_init(&ctl->item_done[i], 1);
       ptx::mbar_init(&ctl->hop_full[i], C2_NCOMP);
+#if C2_SPLIT_BAR
+      ptx::mbar_init(&ctl->hop_ready[i], C2_NCOMP);
+#endif
       ptx::mbar_init(&ctl->mma_done[i], 1);
     }
     ptx::mbar_init(&ctl->acc_full, 1);
@@ -480,7 +495,11 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
             if (probe) pd[1] = clock64();
             if (!mma_ok) ptx::mbar_wait(&ctl->mma_done[p], (cnt_done[p] - 1) & 1);
             if (s == 1 && last_bar >= 0) {  // previous item's last phase: everybody has finished reading X[0]
+#if C2_SPLIT_BAR
+              ptx::mbar_wait(&ctl->hop_ready[last_bar], last_par);
+#else
               ptx::mbar_wait(&ctl->hop_full[last_bar], last_par);
+#endif
               last_bar = -1;
             }
             if (probe) pd[2] = clock64();
@@ -489,10 +508,14 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
             for (int r = 0; r < C2_BR; ++r)
 #pragma unroll
               for (int cc = 0; cc < 3; ++cc) dst[r * C2_LW + cc * 8] = acc[r][cc];
+#if C2_SPLIT_BAR
+            ptx::mbar_arrive(&ctl->hop_ready[p]);  // fence + hop_full arrive: publish(p), after the next inside taps
+#else
 #if !C2_FENCE_BY_ISSUER
             ptx::fence_proxy_async_smem();
 #endif
             ptx::mbar_arrive(&ctl->hop_full[p]);
+#endif
             if (probe) pd[3] = clock64();
             float* outp = a.out[s - 1];
             if (outp != nullptr) {
@@ -511,6 +534,51 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
             if (probe) pd[4] = clock64();
           };
           // wait until hop s has been published by everybody (its phase on hop_full[(s-1)&1])
+#if C2_SPLIT_BAR
+          auto wait_hop = [&](int pp) { ptx::mbar_wait(&ctl->hop_ready[pp], par[pp]); };
+          // hand the hop in X[pp] to the UMMA issuer: this thread's stores -> async proxy, then hop_full
+          auto publish = [&](int pp) {
+#if !C2_FENCE_BY_ISSUER
+            ptx::fence_proxy_async_smem();
+#endif
+            ptx::mbar_arrive(&ctl->hop_full[pp]);
+          };
+          hop_inside<false, rot_of_hop(1)>(A, Bv, w);
+          finish_hop(std::integral_constant<int, 1>{}, Bv, S);
+          bool pub = false;
+          if (pend) {  // the drain is long: do not hold hop 1 back behind it
+            publish(0);
+            pub = true;
+            epilogue();
+          }
+          int last = 0;
+          if (nsteps >= 2) {
+            hop_inside<CHEB, rot_of_hop(2)>(Bv, A, w);
+            if (!pub) publish(0);
+            wait_hop(0);
+            finish_hop(std::integral_constant<int, 2>{}, A, X[0]);
+            last = 1;
+            if (nsteps == 2) publish(1);
+          } else if (!pub) {
+            publish(0);
+          }
+          if (nsteps >= 3) {
+            hop_inside<CHEB, rot_of_hop(3)>(A, Bv, w);
+            publish(1);
+            wait_hop(1);
+            finish_hop(std::integral_constant<int, 3>{}, Bv, X[1]);
+            last = 0;
+            if (nsteps == 3) publish(0);
+          }
+          if (nsteps >= 4) {
+            hop_inside<CHEB, rot_of_hop(4)>(Bv, A, w);
+            publish(0);
+            wait_hop(0);
+            finish_hop(std::integral_constant<int, 4>{}, A, X[0]);
+            last = 1;
+            publish(1);
+          }
+#else
           auto wait_hop = [&](int pp) { ptx::mbar_wait(&ctl->hop_full[pp], par[pp]); };
 
           hop_inside<false, rot_of_hop(1)>(A, Bv, w);
@@ -535,6 +603,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
             finish_hop(std::integral_constant<int, 4>{}, A, X[0]);
             last = 1;
           }
+#endif
           last_bar = last;
           last_par = par[last];
 

@@ -71,11 +71,14 @@ def conv2_problem():
     ("default", []),
     ("fence", ["-DC2_FENCE_BY_ISSUER=1"]),
     ("br2", ["-DC2_BR=2"]),
+    ("split", ["-DC2_SPLIT_BAR=1"]),
     ("epipipe", ["-DC2_EPI_PIPE=1"]),
     ("symw", ["-DC2_SYMW=1"]),
-    ("br3all", ["-DC2_SYMW=1", "-DC2_EPI_PIPE=1", "-DC2_PROBE=0"]),
-    ("all", ["-DC2_BR=2", "-DC2_SYMW=1", "-DC2_EPI_PIPE=1", "-DC2_PROBE=0", "-DC2_REGS_COMPUTE=144", "-DC2_REGS_IO=40",
-             "-DC2_FENCE_BY_ISSUER=1"]),
+    ("br3all", ["-DC2_SYMW=1", "-DC2_EPI_PIPE=1", "-DC2_PROBE=0", "-DC2_SPLIT_BAR=1"]),
+    ("br2all", ["-DC2_BR=2", "-DC2_SYMW=1", "-DC2_EPI_PIPE=1", "-DC2_PROBE=0", "-DC2_SPLIT_BAR=1",
+                "-DC2_REGS_COMPUTE=144", "-DC2_REGS_IO=40"]),
+    ("br2allfence", ["-DC2_BR=2", "-DC2_SYMW=1", "-DC2_EPI_PIPE=1", "-DC2_PROBE=0", "-DC2_SPLIT_BAR=1",
+                     "-DC2_REGS_COMPUTE=144", "-DC2_REGS_IO=40", "-DC2_FENCE_BY_ISSUER=1"]),
 ])
 def test_fused_lattice_kernel_on_the_host_emulator(tmp_path, conv2_problem, variant, defines):
     import numpy as np
@@ -87,15 +90,16 @@ def test_fused_lattice_kernel_on_the_host_emulator(tmp_path, conv2_problem, vari
     g, layers = conv2_problem
     M = g.L.shape[0]
     rng = np.random.default_rng(7)
-    cases = [  # (layer class, B, F, N, activation id, bias, b_split, grid, basis wanted)
-        ("Chebyshev", 1, 8, 16, 0, True, 1, 2, True),
-        ("Monomial", 2, 16, 32, 1, False, 2, 3, False),
+    cases = [  # (layer class, K, B, F, N, activation id, bias, b_split, grid, basis wanted)
+        ("Chebyshev", 5, 1, 8, 16, 0, True, 1, 2, True),
+        ("Monomial", 4, 2, 16, 32, 1, False, 2, 3, False),
+        ("Chebyshev", 3, 1, 16, 16, 0, False, 1, 2, True),   # 2 hops
+        ("Chebyshev", 2, 1, 8, 64, 1, True, 1, 1, False),    # 1 hop, widest accumulator (3 x 64 TMEM columns)
     ]
-    for name, B, F, N, act, has_bias, b_split, grid, want_basis in cases:
-        layer, pay = layers[name]
-        K = layer.K
+    for ci, (name, K, B, F, N, act, has_bias, b_split, grid, want_basis) in enumerate(cases):
+        layer, pay = layers[name]  # the tile tables do not depend on K (4-ring halo for every K <= 5)
         assert pay is not None and pay["n_tiles"] == 24 and pay["LW"] == 24 and pay["H"] == 4
-        d = os.path.join(str(tmp_path), f"{variant}_{name}")
+        d = os.path.join(str(tmp_path), f"{variant}_{ci}_{name}")
         os.makedirs(d)
         x = rng.standard_normal((B, M, F)).astype(np.float32)
         W = (rng.standard_normal((F * K, N)) * 0.2).astype(np.float32)

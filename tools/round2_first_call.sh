@@ -22,7 +22,7 @@ done
 # 6. fused-kernel experiments (build them HERE first: bash tools/build_variants.sh; the .so files travel with the
 #    snapshot).  Every variant has run on the host emulator (tests/test_emul_cpu.py); this decides parity and speed.
 # VARIANTS="fence all" bash tools/round2_first_call.sh   restricts the list (about 2 GPU-minutes per variant)
-for name in ${VARIANTS:-fence noprobe epipipe symw br3all br2r144 br2symwepi all}; do
+for name in ${VARIANTS:-split fence noprobe epipipe symw br3all br2r144 br2all br2allfence}; do
   V=deepsphere-cosmo-tf2_b200/lib/libdeepsphere_b200_$name.so
   [ -f "$V" ] || continue
   {
