@@ -34,10 +34,10 @@ static void store(const std::string& path, const float* p, size_t n) {
 int main(int argc, char** argv) {
   if (argc < 2) return 2;
   const std::string dir = argv[1];
-  long n_tiles, B, M, F, N, nsteps, cheb, act, has_bias, grid, b_split, want_basis;
+  long n_tiles, B, M, F, N, nsteps, cheb, act, has_bias, grid, b_split, want_basis, bwd = 0;
   {
     std::ifstream m(dir + "/meta.txt");
-    m >> n_tiles >> B >> M >> F >> N >> nsteps >> cheb >> act >> has_bias >> grid >> b_split >> want_basis;
+    m >> n_tiles >> B >> M >> F >> N >> nsteps >> cheb >> act >> has_bias >> grid >> b_split >> want_basis >> bwd;
   }
   using namespace ds;
   const int K = (int)nsteps + 1, n_chunks = (int)(F / C2_FC);
@@ -54,10 +54,13 @@ int main(int argc, char** argv) {
     u[s] = static_cast<float*>(std::aligned_alloc(64, nu * 4 + 64));
     for (size_t i = 0; i < nu; ++i) u[s][i] = NAN;
   }
-  // weight images (conv2_prep_b_kernel), forward addressing: W[(f*K + k)*N + n]
+  // weight images (conv2_prep_b_kernel).  Forward launch: B_k(f, n) = W[(f*K + k)*N + n] (ds_graph_conv_forward);
+  // backward-data launch on dz (F = the layer's Fout, N = its Fin): B_k(o, f) = kernel[(f*K + k)*F + o]
+  // (ds_graph_conv_backward: strides 1, F, K*F)
   const size_t img_elems = (size_t)n_chunks * K * N * C2_FC;
   float* img = static_cast<float*>(std::aligned_alloc(64, img_elems * 4 + 64));
-  emul::launch(2, 256, [&] { conv2_prep_b_kernel(W, (int64_t)K * N, N, 1, n_chunks, K, (int)N, img); });
+  const int64_t s_f = bwd ? 1 : (int64_t)K * N, s_k = bwd ? F : N, s_n = bwd ? (int64_t)K * F : 1;
+  emul::launch(2, 256, [&] { conv2_prep_b_kernel(W, s_f, s_k, s_n, n_chunks, K, (int)N, img); });
 
   Conv2Args a;
   a.n_tiles = (int)n_tiles; a.pix = pix; a.w = w;

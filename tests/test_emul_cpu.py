@@ -95,29 +95,36 @@ def test_fused_lattice_kernel_on_the_host_emulator(tmp_path, conv2_problem, vari
         ("Monomial", 4, 2, 16, 32, 1, False, 2, 3, False),
         ("Chebyshev", 3, 1, 16, 16, 0, False, 1, 2, True),   # 2 hops
         ("Chebyshev", 2, 1, 8, 64, 1, True, 1, 1, False),    # 1 hop, widest accumulator (3 x 64 TMEM columns)
+        ("Chebyshev-bwd", 5, 1, 16, 32, 0, False, 1, 2, True),  # backward-data launch: dx from dz, basis U_k out
     ]
     for ci, (name, K, B, F, N, act, has_bias, b_split, grid, want_basis) in enumerate(cases):
+        bwd = name.endswith("-bwd")
+        name = name.split("-")[0]
         layer, pay = layers[name]  # the tile tables do not depend on K (4-ring halo for every K <= 5)
         assert pay is not None and pay["n_tiles"] == 24 and pay["LW"] == 24 and pay["H"] == 4
         d = os.path.join(str(tmp_path), f"{variant}_{ci}_{name}")
         os.makedirs(d)
         x = rng.standard_normal((B, M, F)).astype(np.float32)
-        W = (rng.standard_normal((F * K, N)) * 0.2).astype(np.float32)
+        W = (rng.standard_normal((N * K, F) if bwd else (F * K, N)) * 0.2).astype(np.float32)
         bias = rng.standard_normal(N).astype(np.float32)
         for arr, fn in ((pay["pix"], "pix"), (pay["w"], "w"), (x, "x"), (W, "W"), (bias, "bias")):
             arr.tofile(os.path.join(d, fn + ".bin"))
         cheb = int(name == "Chebyshev")
         with open(os.path.join(d, "meta.txt"), "w") as f:
             f.write(f"{pay['n_tiles']} {B} {M} {F} {N} {K - 1} {cheb} {act} {int(has_bias)} {grid} {b_split} "
-                    f"{int(want_basis)}\n")
+                    f"{int(want_basis)} {int(bwd)}\n")
         res = subprocess.run([exe, d], capture_output=True, text=True, timeout=900)
         assert res.returncode == 0, res.stdout + res.stderr[-2000:]
         y = np.fromfile(os.path.join(d, "y.bin"), dtype=np.float32).reshape(B, M, N)
         Lt = sparse.csr_matrix((layer._L_values.astype(np.float64), (layer._L_indices[:, 0], layer._L_indices[:, 1])),
                                shape=(M, M))
-        ref = orc.graph_conv_forward(x.astype(np.float64), Lt, W.astype(np.float64), K, name.lower(),
-                                     bias=bias.reshape(1, 1, -1).astype(np.float64) if has_bias else None,
-                                     activation="relu" if act == 1 else None, dtype=np.float64)
+        if bwd:  # x plays dz [B, M, Fout = F]; the layer kernel is [(N*K), F]; the launch returns dx [B, M, Fin = N]
+            ref, _, _ = orc.graph_conv_backward(np.zeros((B, M, N)), Lt, W.astype(np.float64), K, x.astype(np.float64),
+                                                name.lower())
+        else:
+            ref = orc.graph_conv_forward(x.astype(np.float64), Lt, W.astype(np.float64), K, name.lower(),
+                                         bias=bias.reshape(1, 1, -1).astype(np.float64) if has_bias else None,
+                                         activation="relu" if act == 1 else None, dtype=np.float64)
         own = pay["pix"].reshape(pay["n_tiles"], 24, 24)[:, 4:20, 4:20].ravel()
         own = np.sort(own[own >= 0])
         assert len(own) == 24 * 256
