@@ -60,7 +60,18 @@ inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 148; return cudaSuccess; }
 
 namespace emul {
-struct MbarState { uint32_t expected = 0; int32_t pending = 0; int64_t tx = 0; uint32_t phase = 0; };
+// one synchronisation object PER mbarrier (not a global lock): ThreadSanitizer then only sees the happens-before edges
+// the barrier protocol really creates, so a missing wait between two roles shows up as a data race
+struct MbarState {
+  std::mutex mu;
+  std::condition_variable cv;
+  bool live = false;
+  uint32_t expected = 0;
+  int32_t pending = 0;
+  int64_t tx = 0;
+  uint32_t phase = 0;
+};
+constexpr size_t kSmemBytes = 232448;  // 227 KB
 struct BlockState {
   std::unique_ptr<std::barrier<>> block_bar;
   std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
@@ -69,9 +80,8 @@ struct BlockState {
   std::vector<uint8_t> dyn_smem_storage;
   uint8_t* dyn_smem = nullptr;
   std::vector<uint32_t> tmem;
-  std::mutex mu;
-  std::condition_variable cv;
-  std::map<const void*, MbarState> mbar;
+  std::unique_ptr<MbarState[]> mbar;  // indexed by the barrier's 8-byte slot in dynamic shared memory
+  std::mutex named_mu;
   std::map<int, std::unique_ptr<std::barrier<>>> named;
 };
 inline BlockState*& state() { static BlockState* s = nullptr; return s; }
@@ -110,6 +120,7 @@ inline void launch(unsigned grid, unsigned block, const std::function<void()>& k
     st.dyn_smem_storage.assign(dyn_smem_bytes + 1024, 0xCD);  // poisoned: reads of unwritten smem show up
     st.dyn_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(st.dyn_smem_storage.data()) + 1023) & ~uintptr_t(1023));
     st.tmem.assign(128 * 512, 0xCDCDCDCDu);
+    st.mbar = std::make_unique<MbarState[]>(kSmemBytes / 8);
     st.block_bar = std::make_unique<std::barrier<>>(block);
     for (unsigned w = 0; w < block / 32; ++w) st.warp_bar.push_back(std::make_unique<std::barrier<>>(32));
     st.shfl.assign(block, 0.f);

@@ -1,6 +1,6 @@
 // Host emulation of csrc/ds_ptx.cuh — TEST INFRASTRUCTURE (selected by -DDS_EMULATE).  Functional models of the sm_100a
 // features the kernels use, so that an UNCHANGED kernel source runs on CPU threads:
-//   * mbarrier: arrival count + transaction bytes + phase, behind the block's mutex / condition variable
+//   * mbarrier: arrival count + transaction bytes + phase, each barrier behind its own mutex / condition variable
 //   * cp.async.bulk (1-D): memcpy + complete_tx
 //   * tcgen05: tensor memory = 128 lanes x 512 columns of 32 bits per CTA; tcgen05.mma.kind::tf32 decodes the shared
 //     memory descriptors (no-swizzle K-major core matrices: 8 rows x 16 bytes; LBO = step between core matrices along
@@ -23,60 +23,61 @@ inline uint32_t smem_u32(const void* p) {
 inline uint8_t* smem_ptr(uint32_t addr) { return emul::state()->dyn_smem + addr; }
 
 // ---- mbarrier ---------------------------------------------------------------------------
-inline void mbar_check_locked(emul::BlockState* s, emul::MbarState& m) {
+inline emul::MbarState& mbar_slot(const void* bar) {
+  emul::BlockState* s = emul::state();
+  const size_t off = (size_t)(reinterpret_cast<const uint8_t*>(bar) - s->dyn_smem);
+  if (off % 8 != 0 || off >= emul::kSmemBytes) { std::fprintf(stderr, "emul: mbarrier outside dynamic shared memory\n"); std::abort(); }
+  return s->mbar[off / 8];
+}
+inline emul::MbarState& mbar_live(const void* bar) {
+  emul::MbarState& m = mbar_slot(bar);
+  if (!m.live) { std::fprintf(stderr, "emul: use of an uninitialised mbarrier\n"); std::abort(); }
+  return m;
+}
+// caller holds m.mu
+inline void mbar_check_locked(emul::MbarState& m) {
+  if (m.pending < 0) { std::fprintf(stderr, "emul: mbarrier over-arrived\n"); std::abort(); }
   if (m.pending == 0 && m.tx == 0) {
     m.phase++;
     m.pending = (int32_t)m.expected;
-    s->cv.notify_all();
+    m.cv.notify_all();
   }
-  if (m.pending < 0) { std::fprintf(stderr, "emul: mbarrier over-arrived\n"); std::abort(); }
 }
 inline void mbar_init(uint64_t* bar, uint32_t count) {
-  emul::BlockState* s = emul::state();
-  std::lock_guard<std::mutex> lk(s->mu);
-  emul::MbarState m;
-  m.expected = count; m.pending = (int32_t)count;
-  s->mbar[bar] = m;
+  emul::MbarState& m = mbar_slot(bar);
+  std::lock_guard<std::mutex> lk(m.mu);
+  m.live = true; m.expected = count; m.pending = (int32_t)count; m.tx = 0; m.phase = 0;
 }
 inline void fence_mbar_init() {}
-inline emul::MbarState& mbar_get(emul::BlockState* s, const void* bar) {
-  auto it = s->mbar.find(bar);
-  if (it == s->mbar.end()) { std::fprintf(stderr, "emul: use of an uninitialised mbarrier\n"); std::abort(); }
-  return it->second;
-}
 inline void mbar_arrive(uint64_t* bar) {
-  emul::BlockState* s = emul::state();
-  std::lock_guard<std::mutex> lk(s->mu);
-  emul::MbarState& m = mbar_get(s, bar);
+  emul::MbarState& m = mbar_live(bar);
+  std::lock_guard<std::mutex> lk(m.mu);
   m.pending -= 1;
-  mbar_check_locked(s, m);
+  mbar_check_locked(m);
 }
 inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  emul::BlockState* s = emul::state();
-  std::lock_guard<std::mutex> lk(s->mu);
-  emul::MbarState& m = mbar_get(s, bar);
+  emul::MbarState& m = mbar_live(bar);
+  std::lock_guard<std::mutex> lk(m.mu);
   m.tx += bytes;
   m.pending -= 1;
-  mbar_check_locked(s, m);
+  mbar_check_locked(m);
 }
 inline void mbar_complete_tx(uint64_t* bar, uint32_t bytes) {
-  emul::BlockState* s = emul::state();
-  std::lock_guard<std::mutex> lk(s->mu);
-  emul::MbarState& m = mbar_get(s, bar);
+  emul::MbarState& m = mbar_live(bar);
+  std::lock_guard<std::mutex> lk(m.mu);
   m.tx -= bytes;
-  mbar_check_locked(s, m);
+  mbar_check_locked(m);
 }
 // the phase with parity `parity` has completed <=> the barrier's current phase has the other parity
 inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  emul::BlockState* s = emul::state();
-  std::unique_lock<std::mutex> lk(s->mu);
-  emul::MbarState& m = mbar_get(s, bar);
-  return s->cv.wait_for(lk, std::chrono::milliseconds(2), [&] { return (m.phase & 1u) != parity; });
+  emul::MbarState& m = mbar_live(bar);
+  std::unique_lock<std::mutex> lk(m.mu);
+  return m.cv.wait_for(lk, std::chrono::milliseconds(2), [&] { return (m.phase & 1u) != parity; });
 }
 inline bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
-  emul::BlockState* s = emul::state();
-  std::lock_guard<std::mutex> lk(s->mu);
-  return (mbar_get(s, bar).phase & 1u) != parity;
+  emul::MbarState& m = mbar_live(bar);
+  std::lock_guard<std::mutex> lk(m.mu);
+  return (m.phase & 1u) != parity;
 }
 inline void mbar_wait(uint64_t* bar, uint32_t parity) {
   const auto t0 = std::chrono::steady_clock::now();
@@ -102,7 +103,7 @@ inline void named_bar_sync(int id, int nthreads) {
   emul::BlockState* s = emul::state();
   std::barrier<>* b;
   {
-    std::lock_guard<std::mutex> lk(s->mu);
+    std::lock_guard<std::mutex> lk(s->named_mu);
     auto& slot = s->named[id];
     if (!slot) slot = std::make_unique<std::barrier<>>(nthreads);
     b = slot.get();
@@ -115,7 +116,9 @@ inline void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* b
 }
 
 // ---- tensor memory --------------------------------------------------------------------------
-inline void tmem_alloc(uint32_t* smem_dst, uint32_t) { *smem_dst = 0; }
+inline void tmem_alloc(uint32_t* smem_dst, uint32_t) {  // warp-collective: one write
+  if ((threadIdx.x & 31) == 0) *smem_dst = 0;
+}
 inline void tmem_dealloc(uint32_t, uint32_t) {}
 
 constexpr uint64_t LAYOUT_SWIZZLE_NONE = 0, LAYOUT_SWIZZLE_128B_BASE32B = 1, LAYOUT_SWIZZLE_128B = 2, LAYOUT_SWIZZLE_64B = 4, LAYOUT_SWIZZLE_32B = 6;

@@ -150,3 +150,35 @@ def test_fused_lattice_kernel_on_the_host_emulator(tmp_path, conv2_problem, vari
                 u = np.fromfile(os.path.join(d, f"u{s}.bin"), dtype=np.float32).reshape(B, M, F)
                 assert np.abs(u[:, own] - t_cur[:, own]).max() <= 1e-5 * np.abs(t_cur).max(), (variant, s)
                 t_prev, t_cur = t_cur, 2 * np.stack([Lt @ t_cur[b] for b in range(B)]) - t_prev
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+@pytest.mark.parametrize("variant,defines", [
+    ("default", []),
+    ("br2all", ["-DC2_BR=2", "-DC2_SYMW=1", "-DC2_EPI_PIPE=1", "-DC2_PROBE=0", "-DC2_SPLIT_BAR=1",
+                "-DC2_REGS_COMPUTE=144", "-DC2_REGS_IO=40"]),
+])
+def test_fused_lattice_kernel_protocol_under_thread_sanitizer(tmp_path, conv2_problem, variant, defines):
+    """The barrier protocol of the fused kernel under ThreadSanitizer: every emulated mbarrier is its own lock, so the
+    only happens-before edges are the ones the protocol creates; an exchange buffer written while a neighbour still reads
+    it, or read before it was published, is reported as a data race (removing the wait for the previous item's last
+    phase from the kernel is — checked by hand — caught this way)."""
+    import numpy as np
+
+    exe = _build_conv2(str(tmp_path), "emul_conv2_tsan_" + variant, ["-g", "-fsanitize=thread", *defines])
+    g, layers = conv2_problem
+    layer, pay = layers["Chebyshev"]
+    M, K, B, F, N = g.L.shape[0], 5, 1, 16, 16
+    d = os.path.join(str(tmp_path), "case")
+    os.makedirs(d)
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((B, M, F)).astype(np.float32)
+    W = (rng.standard_normal((F * K, N)) * 0.2).astype(np.float32)
+    for arr, fn in ((pay["pix"], "pix"), (pay["w"], "w"), (x, "x"), (W, "W")):
+        arr.tofile(os.path.join(d, fn + ".bin"))
+    with open(os.path.join(d, "meta.txt"), "w") as f:
+        f.write(f"{pay['n_tiles']} {B} {M} {F} {N} {K - 1} 1 0 0 2 1 1 0\n")
+    res = subprocess.run([exe, d], capture_output=True, text=True, timeout=900)
+    if "FATAL: ThreadSanitizer" in res.stderr and "unexpected memory mapping" in res.stderr:
+        pytest.skip("ThreadSanitizer cannot run in this container (ASLR settings)")
+    assert res.returncode == 0 and "WARNING: ThreadSanitizer" not in res.stderr, res.stderr[-3000:]
