@@ -802,6 +802,10 @@ int launch_lattice_conv2(const LatticeDev& L, int nsteps, int64_t B, int64_t M, 
   a.B = B; a.M = M; a.F = F; a.N = N; a.nsteps = nsteps;
   int split = 1;  // persistent CTAs, 2 per SM: enough units for a balanced tail
   while ((int64_t)L.n_tiles * split < (int64_t)32 * num_sms() && split < B) split *= 2;
+  // sweeps without a rebuild: DEEPSPHERE_CONV2_BSPLIT (work units per tile along the batch), DEEPSPHERE_CONV2_GRID (CTAs)
+  static const int env_split = [] { const char* e = getenv("DEEPSPHERE_CONV2_BSPLIT"); return e ? atoi(e) : 0; }();
+  static const int env_grid = [] { const char* e = getenv("DEEPSPHERE_CONV2_GRID"); return e ? atoi(e) : 0; }();
+  if (env_split > 0) split = env_split;
   a.b_split = (int)std::min<int64_t>(split, B);
   a.wscale = cheb ? 2.f : 1.f;
   static const int sleep_mma = [] { const char* e = getenv("DEEPSPHERE_CONV2_SLEEP_MMA"); return e ? atoi(e) : 0; }();
@@ -840,7 +844,7 @@ int launch_lattice_conv2(const LatticeDev& L, int nsteps, int64_t B, int64_t M, 
     return attr_rc;
   }
   const int n_units = a.n_tiles * a.b_split;
-  const int grid = std::min(n_units, 2 * num_sms());
+  const int grid = std::min(n_units, env_grid > 0 ? env_grid : 2 * num_sms());
   if (cheb) lattice_conv2_kernel<true><<<grid, C2_THREADS, smem, st>>>(a);
   else lattice_conv2_kernel<false><<<grid, C2_THREADS, smem, st>>>(a);
   cudaError_t e = cudaGetLastError();
