@@ -351,11 +351,18 @@ class HealpySmoothing(Model):
         if self.per_channel_repetitions is None:
             x = _ops.sparse_matmul(self.sparse_kernel, x)
         else:
-            reps = torch.as_tensor(self.per_channel_repetitions, device=x.device)
+            cache = self.__dict__.setdefault("_dev_cache", {})  # constants of the layer, uploaded once per device
+            reps = cache.get(("reps", x.device))
+            if reps is None:
+                reps = cache[("reps", x.device)] = torch.as_tensor(self.per_channel_repetitions, device=x.device)
             for r in range(1, int(self.per_channel_repetitions.max()) + 1):
                 x = torch.where((reps >= r)[None, None, :], _ops.sparse_matmul(self.sparse_kernel, x), x)
         if self.mask is not None:
-            x = x * self.mask.to(x.device)
+            cache = self.__dict__.setdefault("_dev_cache", {})
+            mask = cache.get(("mask", x.device))
+            if mask is None:
+                mask = cache[("mask", x.device)] = self.mask.to(x.device)
+            x = x * mask
         return x
 
     def _build_tree(self):
