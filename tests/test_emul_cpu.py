@@ -106,6 +106,7 @@ def test_fused_lattice_kernel_on_the_host_emulator(tmp_path, conv2_problem, vari
         ("Chebyshev", 2, 1, 8, 64, 1, True, 1, 1, False),    # 1 hop, widest accumulator (3 x 64 TMEM columns)
         ("Chebyshev-bwd", 5, 1, 16, 32, 0, False, 1, 2, True),  # backward-data launch: dx from dz, basis U_k out
         ("Masked", 5, 2, 8, 16, 0, True, 1, 2, True),           # partial sky: holes in the lattices
+        ("Chebyshev", 5, 1, 64, 64, 1, True, 1, 3, False),      # the bench layer's shape: 8 chunks, 192 TMEM columns
     ]
     for ci, (name, K, B, F, N, act, has_bias, b_split, grid, want_basis) in enumerate(cases):
         bwd = name.endswith("-bwd")
