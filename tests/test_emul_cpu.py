@@ -109,6 +109,8 @@ def test_fused_lattice_kernel_on_the_host_emulator(tmp_path, conv2_problem, vari
         ("Chebyshev", 5, 1, 64, 64, 1, True, 1, 3, False),      # the bench layer's shape: 8 chunks, 192 TMEM columns
     ]
     for ci, (name, K, B, F, N, act, has_bias, b_split, grid, want_basis) in enumerate(cases):
+        if F == 64 and variant not in ("default", "br2all"):
+            continue  # the large case only for the measured kernel and the most changed variant (CPU suite budget)
         bwd = name.endswith("-bwd")
         name = name.split("-")[0]
         layer, pay = layers[name]  # the tile tables do not depend on K (4-ring halo for every K <= 5)
