@@ -75,10 +75,10 @@ def conv2_problem():
     return _conv2_problem()
 
 
+# (the C2_FENCE_BY_ISSUER variants are not listed: proxy fences are no-ops on the emulator, they run like their base)
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
 @pytest.mark.parametrize("variant,defines", [
     ("default", []),
-    ("fence", ["-DC2_FENCE_BY_ISSUER=1"]),
     ("br2", ["-DC2_BR=2"]),
     ("split", ["-DC2_SPLIT_BAR=1"]),
     ("epipipe", ["-DC2_EPI_PIPE=1"]),
@@ -86,8 +86,6 @@ def conv2_problem():
     ("br3all", ["-DC2_SYMW=1", "-DC2_EPI_PIPE=1", "-DC2_PROBE=0", "-DC2_SPLIT_BAR=1"]),
     ("br2all", ["-DC2_BR=2", "-DC2_SYMW=1", "-DC2_EPI_PIPE=1", "-DC2_PROBE=0", "-DC2_SPLIT_BAR=1",
                 "-DC2_REGS_COMPUTE=144", "-DC2_REGS_IO=40"]),
-    ("br2allfence", ["-DC2_BR=2", "-DC2_SYMW=1", "-DC2_EPI_PIPE=1", "-DC2_PROBE=0", "-DC2_SPLIT_BAR=1",
-                     "-DC2_REGS_COMPUTE=144", "-DC2_REGS_IO=40", "-DC2_FENCE_BY_ISSUER=1"]),
 ])
 def test_fused_lattice_kernel_on_the_host_emulator(tmp_path, conv2_problem, variant, defines):
     import numpy as np
@@ -111,6 +109,8 @@ def test_fused_lattice_kernel_on_the_host_emulator(tmp_path, conv2_problem, vari
     for ci, (name, K, B, F, N, act, has_bias, b_split, grid, want_basis) in enumerate(cases):
         if F == 64 and variant not in ("default", "br2all"):
             continue  # the large case only for the measured kernel and the most changed variant (CPU suite budget)
+        if K <= 3 and variant not in ("default", "split", "br2all"):
+            continue  # 1- and 2-hop launches: only where the hop sequence itself differs
         bwd = name.endswith("-bwd")
         name = name.split("-")[0]
         layer, pay = layers[name]  # the tile tables do not depend on K (4-ring halo for every K <= 5)
