@@ -77,4 +77,5 @@ nat.launch_count = lambda: cnt[0]
 nat.GraphPlan.info = lambda self, d=0: {"lattice": 1, "tail_rows": 2, "symmetric": 0, "nnz": len(self.values), "M": self.shape[0]}
 torch.Tensor.cuda = lambda self, *a, **k: self
 torch.cuda.synchronize = lambda *a, **k: None
-sys.exit(pytest.main(sys.argv[1:] + ["-m", "gpu", "-q", "-p", "no:cacheprovider"]))
+if __name__ == "__main__":
+    sys.exit(pytest.main(sys.argv[1:] + ["-m", "gpu", "-q", "-p", "no:cacheprovider"]))
