@@ -1,0 +1,40 @@
+"""The device code of the fused lattice convolution kernel is pinned: the SASS of the DEFAULT build (all experiment switches
+off) must stay what was measured and parity-tested on the B200 in round 1 (commit e8f944c, profiles/r1k_*).  The kernel
+file carries compile-time variants and host-emulation seams; this test is what lets them be edited without a GPU — an edit
+that changes the default code generation fails here and has to be re-verified on the GPU before the pin moves.
+(Function names carry a hash of the source path; they are normalised away.)"""
+import hashlib
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "deepsphere-cosmo-tf2_b200", "csrc", "ds_lattice_conv2.cu")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+CUOBJDUMP = os.path.join(os.path.dirname(NVCC), "cuobjdump")
+PINNED = "5fcb63f4a8e384bf0202701e5a4e1069"
+
+
+def sass_digest(obj):
+    out = subprocess.run([CUOBJDUMP, "-sass", obj], check=True, capture_output=True, text=True).stdout
+    lines = []
+    for ln in out.splitlines():
+        if re.fullmatch(r"\s*/\*[0-9a-f]*\*/\s*", ln):  # second encoding word of an instruction
+            continue
+        ln = re.sub(r"/\* 0x[0-9a-f]* \*/", "", ln)      # first encoding word
+        ln = re.sub(r"_GLOBAL__N__[0-9a-f]+_", "_GLOBAL__N__", ln)
+        if ln.startswith("identifier ="):                # source path as given on the command line
+            continue
+        lines.append(ln.rstrip())
+    return hashlib.md5("\n".join(lines).encode()).hexdigest()
+
+
+@pytest.mark.skipif(not (os.path.exists(NVCC) and os.path.exists(CUOBJDUMP)), reason="needs nvcc and cuobjdump")
+def test_default_fused_kernel_sass_is_the_measured_one(tmp_path):
+    obj = os.path.join(str(tmp_path), "conv2.o")
+    subprocess.run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-c", SRC,
+                    "-o", obj], check=True, capture_output=True, text=True, cwd=os.path.dirname(SRC))
+    assert sass_digest(obj) == PINNED, "the default build of ds_lattice_conv2.cu no longer compiles to the measured code"
