@@ -48,6 +48,10 @@ def parse():
     ap.add_argument("--no-experimental", action="store_true")
     ap.add_argument("--model-graph", action="store_true",
                     help="with --model-only: capture the training step in a CUDA graph and time graph replays")
+    ap.add_argument("--no-partitioned", action="store_true",
+                    help="skip the nside-1024 sphere-partitioned HealpyGCNN (strong scaling over the ranks)")
+    ap.add_argument("--part-nside", type=int, default=1024)
+    ap.add_argument("--part-batch", type=int, default=8)
     ap.add_argument("--model-nside", type=int, default=256)
     ap.add_argument("--model-batch", type=int, default=16)
     ap.add_argument("--nside", type=int, default=256)
@@ -136,9 +140,16 @@ def build_layer(args, mode):
     return g, layer
 
 
-def cpu_reference_time(L, args, batch, steps, warmup, Lt=None):
+PARITY_TOL = {"fp32": 1e-5, "tf32": 1e-3, "tf32x3": 2e-5}  # north_star: rel <= 1e-5 fp32 path, stated <= 1e-3 for TF32
+
+
+def cpu_reference_time(L, args, batch, steps, warmup, Lt=None, sample=None):
     """The reference's op sequence (gnn_layers.py:131-150 + autodiff) with torch CPU ops on all
-    host threads — oracle/deepsphere_oracle.py:torch_cpu_graph_conv — fwd + bwd."""
+    host threads — oracle/deepsphere_oracle.py:torch_cpu_graph_conv — fwd + bwd.
+
+    `sample` = dict(x, kernel, dy, y, dx, dkernel) of CPU tensors taken from the GPU layer at the bench configuration
+    (the first `batch` maps of the workload): the CPU run then uses those inputs and the third return value is the
+    parity of the GPU results against it, max|err| / max|ref| per tensor."""
     from oracle import deepsphere_oracle as orc
 
     if Lt is None:
@@ -146,10 +157,17 @@ def cpu_reference_time(L, args, batch, steps, warmup, Lt=None):
     M = Lt.shape[0]
     F = args.features
     g = torch.Generator().manual_seed(0)
-    x = torch.randn(batch, M, F, generator=g, requires_grad=True)
-    w = (torch.randn(args.K * F, F, generator=g) * 0.075).requires_grad_(True)
-    dy = torch.randn(batch, M, F, generator=g)
+    if sample is not None:
+        x = sample["x"].clone().requires_grad_(True)
+        w = sample["kernel"].clone().requires_grad_(True)
+        dy = sample["dy"]
+        batch = x.shape[0]
+    else:
+        x = torch.randn(batch, M, F, generator=g, requires_grad=True)
+        w = (torch.randn(args.K * F, F, generator=g) * 0.075).requires_grad_(True)
+        dy = torch.randn(batch, M, F, generator=g)
     times = []
+    parity = None
     for i in range(warmup + steps):
         x.grad = w.grad = None
         t0 = time.perf_counter()
@@ -158,7 +176,13 @@ def cpu_reference_time(L, args, batch, steps, warmup, Lt=None):
         t1 = time.perf_counter()
         if i >= warmup:
             times.append(t1 - t0)
-    return float(np.mean(times)), algorithmic_bytes(batch, M, F, F)
+        if sample is not None and parity is None:
+            def rel(a, b):
+                return float((a - b).abs().max() / b.abs().max())
+
+            parity = {"y": rel(sample["y"], y.detach()), "dx": rel(sample["dx"], x.grad),
+                      "dkernel": rel(sample["dkernel"], w.grad)}
+    return float(np.mean(times)), algorithmic_bytes(batch, M, F, F), parity
 
 
 def model_train_bench(args, mode, device, world):
@@ -246,6 +270,148 @@ def model_train_bench(args, mode, device, world):
                       f"Chebyshev K5 F64 -> AVG pool -> mean -> Dense(2); MSE, Adam, fwd+bwd+all-reduce+step, mode {mode}"}
 
 
+def _c5_layers(mode, mean_layer):
+    """PseudoConv p1 F16 -> [Chebyshev K5 F32 + MAX pool] x 4 -> Chebyshev K5 F64 -> AVG pool ->
+    mean over pixels -> Dense(2)."""
+    from deepsphere import healpy_layers as hl, keras_compat as kc
+
+    kw = dict(use_bias=True, activation="relu", mode=mode)
+    layers = [hl.HealpyPseudoConv(p=1, Fout=16, activation="relu")]
+    for _ in range(4):
+        layers += [hl.HealpyChebyshev(K=5, Fout=32, **kw), hl.HealpyPool(p=1, pool_type="MAX")]
+    layers += [hl.HealpyChebyshev(K=5, Fout=64, **kw), hl.HealpyPool(p=1, pool_type="AVG"), mean_layer, kc.Dense(2)]
+    return layers
+
+
+def partition_parity_check(mode, device, rank, world, nside=64, batch=2):
+    """N ranks == 1 rank, on hardware and visible to the driver: the C5-pattern network on ONE nside-64
+    sphere partitioned over the ranks of this run, against the whole-sphere HealpyGCNN on rank 0 with the same weights
+    and input: output and every weight gradient (max|err| / max|ref|)."""
+    import deepsphere
+    from deepsphere import distributed as dsd, keras_compat as kc, partition
+
+    npix = 12 * nside * nside
+    torch.manual_seed(5)
+    part = partition.PartitionedHealpyGCNN(nside, np.arange(npix), _c5_layers(mode, partition.PartitionedMean()),
+                                           rank=rank, world=world)
+    gen = torch.Generator(device=device).manual_seed(7)
+    x = torch.randn(batch, npix, 1, device=device, generator=gen)
+    t = torch.randn(batch, 2, device=device, generator=gen)
+    b0, e0 = part.own_range
+    y = part(x[:, b0:e0].contiguous(), training=True)   # builds the lazily-shaped weights
+    dsd.broadcast_parameters(part)
+    params = [p for p in part.parameters() if p.requires_grad]
+    for p in params:
+        p.grad = None
+    y = part(x[:, b0:e0].contiguous(), training=True)
+    ((y - t) ** 2).mean().backward()
+    dsd.allreduce_gradients(params, average=False)
+    torch.cuda.synchronize()
+    out = None
+    if rank == 0:
+        torch.manual_seed(5)
+        whole = deepsphere.HealpyGCNN(nside=nside, indices=np.arange(npix),
+                                      layers=_c5_layers(mode, kc.Lambda(lambda v: v.mean(dim=1))))
+        whole.build(input_shape=(None, npix, 1))
+        wparams = whole.trainable_variables
+        assert len(wparams) == len(params), (len(wparams), len(params))
+        with torch.no_grad():
+            for a, b in zip(wparams, params):
+                a.copy_(b)
+        yw = whole(x, training=True)
+        ((yw - t) ** 2).mean().backward()
+
+        def rel(a, b):
+            return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+        errs = {"y": rel(y.detach(), yw.detach()), "grad_max": max(rel(b.grad, a.grad) for a, b in zip(wparams, params))}
+        tol = 2e-3 if mode == "tf32" else 1e-4
+        out = {"rel_err": errs, "tolerance": tol, "ok": bool(max(errs.values()) <= tol), "nside": nside, "batch": batch,
+               "ranks": world, "what": "sphere-partitioned C5-pattern network vs the whole-sphere HealpyGCNN on rank 0: "
+                                       "output and all weight gradients"}
+    return out
+
+
+def model_train_partitioned_bench(args, mode, device, rank, world):
+    """North-star scaling configuration (BASELINE.json configs[4]): the full-sphere regression
+    HealpyGCNN at nside 1024 (12.6 M pixels), ONE sphere per sample partitioned over the N ranks by quarter-face blocks
+    with a (K-1)-ring halo exchange per graph layer — strong scaling: the same global batch at every N, N = 1 is the
+    whole sphere on one GPU.  Step = forward + backward + weight-gradient all-reduce (sum of the ranks' partial sums) +
+    Adam.  Also reports the device time inside the halo exchanges and the all-reduce, and the halo volume."""
+    from deepsphere import distributed as dsd, partition
+
+    nside, Bm = args.part_nside, args.part_batch
+    npix = 12 * nside * nside
+    t0 = time.time()
+    torch.manual_seed(11)
+    model = partition.PartitionedHealpyGCNN(nside, np.arange(npix), _c5_layers(mode, partition.PartitionedMean()),
+                                            rank=rank, world=world)
+    b0, e0 = model.own_range
+    gen = torch.Generator(device=device).manual_seed(11 + rank)
+    x = torch.randn(Bm, e0 - b0, 1, device=device, generator=gen)
+    gt = torch.Generator(device=device).manual_seed(3)
+    t = torch.randn(Bm, 2, device=device, generator=gt)
+    model(x, training=True)  # builds the weights and the device plans
+    dsd.broadcast_parameters(model)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-3)
+    prep_s = time.time() - t0
+    ar_events = []
+
+    def train_step(timed=False):
+        opt.zero_grad(set_to_none=True)
+        loss = ((model(x, training=True) - t) ** 2).mean()
+        loss.backward()
+        if timed:
+            a = torch.cuda.Event(enable_timing=True); a.record()
+        dsd.allreduce_gradients(params, average=False)
+        if timed:
+            b = torch.cuda.Event(enable_timing=True); b.record()
+            ar_events.append((a, b))
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        train_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+    n = max(3, min(args.steps, 10))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        loss = train_step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = dsd.allreduce_max(a.elapsed_time(b) / n, device)
+    # time split (separate, instrumented steps: the event pairs serialise nothing but add host work)
+    partition._Timing.start()
+    for _ in range(2):
+        train_step(timed=True)
+    torch.cuda.synchronize()
+    ex_ms, ex_n = partition._Timing.stop()
+    ar_ms = sum(u.elapsed_time(v) for u, v in ar_events) / 2
+    ex_ms = dsd.allreduce_max(ex_ms / 2, device)
+    ar_ms = dsd.allreduce_max(ar_ms, device)
+    convs = [l for l in model.layers_use if isinstance(l, partition.PartitionedGraphConv)]
+    halo = [{"level_rows_own": int(c.plan.n_own), "halo_rows": int(c.plan.halo_rows), "hops": int(c.plan.n_hops),
+             "lattice": int(c.layer._plan.info(device.index or 0)["lattice"])} for c in convs]
+    n_params = int(sum(p.numel() for p in params))
+    out = {"metric": "HealpyGCNN train maps/s, nside %d, one sphere partitioned over the ranks" % nside,
+           "value": Bm / (ms * 1e-3), "unit": "maps/s", "ms_per_step": ms, "global_batch": Bm, "n_gpus": world,
+           "scaling": "strong", "parameters": n_params, "final_loss": float(loss.detach()),
+           "time_split_ms": {"halo_exchanges": ex_ms, "halo_exchanges_per_step": ex_n // 2, "grad_allreduce": ar_ms,
+                             "rest (kernels, optimizer, host launch gaps)": ms - ex_ms - ar_ms},
+           "limiting_collective": None if world == 1 else ("halo all_to_all" if ex_ms >= ar_ms else "gradient all-reduce"),
+           "halo": halo, "host_prep_s": prep_s,
+           "config": f"nside {nside} ({npix} px): PseudoConv p1 F16 -> [Chebyshev K5 F32 + MAX pool] x4 -> Chebyshev K5 F64 "
+                     f"-> AVG pool -> mean -> Dense(2); MSE, Adam; mode {mode}; rank r owns 48/{world} quarter-face blocks"}
+    del model, opt, x
+    torch.cuda.empty_cache()
+    return out
+
+
 def experimental_model_run(args, baseline, switch_env=None, extra_args=()):
     """`bench.py --model-only` in a child process (bounded: 4 minutes) with an opt-in switch: `switch_env` (e.g.
     DEEPSPHERE_SKINNY=1) and / or extra flags (--model-graph).  The child's number only counts as validated if its
@@ -301,7 +467,7 @@ def main():
             pass
         g = SphereHealpix(args.nside, k=8)
         steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
-        t, nbytes = cpu_reference_time(g.L, args, args.cpu_sample_batch, steps, warmup)
+        t, nbytes, _ = cpu_reference_time(g.L, args, args.cpu_sample_batch, steps, warmup)
         val = nbytes / t / 1e9
         sample = (f"batch {args.cpu_sample_batch} of the workload's {args.batch} (same nside/K/F), fwd+bwd, "
                   f"{steps} timed steps after {warmup} warm-up")
@@ -367,6 +533,21 @@ def main():
         sync_all()
     ms = e0.elapsed_time(e1) / args.steps
     launches = (nat.launch_count() - launches0)
+
+    # ---- parity sample at THIS configuration: the first cpu_sample_batch maps of the workload through the same layer
+    # (forward, dx, dkernel); compared further down with the CPU restatement of the reference on the same inputs
+    parity_sample = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        nb = max(1, min(args.cpu_sample_batch, B))
+        xs = x.detach()[:nb].clone().requires_grad_(True)
+        layer.kernel.grad = None
+        ys = layer(xs)
+        ys.backward(dy[:nb])
+        torch.cuda.synchronize()
+        parity_sample = {"x": xs.detach().cpu(), "dy": dy[:nb].cpu(), "kernel": layer.kernel.detach().cpu().clone(),
+                         "y": ys.detach().cpu(), "dx": xs.grad.cpu(), "dkernel": layer.kernel.grad.detach().cpu().clone()}
+        del xs, ys
+        layer.kernel.grad = None
     ms = dsd.allreduce_max(ms, device)
     value = world * nbytes / (ms * 1e-3) / 1e9
     hbm_peak, bf16_peak, peak_kind = peaks()
@@ -467,6 +648,19 @@ def main():
         except Exception as exc:
             model_train = {"error": str(exc)[:200]}
 
+    # ---- the north-star scaling configuration: nside 1024, one sphere partitioned over the ranks (strong scaling), and
+    # the N-rank == 1-rank parity of that path on a small sphere
+    model_train_partitioned = partition_parity = None
+    if not args.no_partitioned and not args.no_model:
+        try:
+            if world > 1:
+                partition_parity = partition_parity_check(mode, device, rank, world)
+            model_train_partitioned = model_train_partitioned_bench(args, mode, device, rank, world)
+        except Exception as exc:
+            import traceback
+
+            model_train_partitioned = {"error": str(exc)[:300], "trace": traceback.format_exc()[-600:]}
+
     # ---- the same training step with the opt-in streaming pseudo-convolution kernels (ds_skinny.cu, written after
     # this round's GPU budget was spent: host-emulated only, hence not the default).  Separate process so that a fault
     # there cannot touch this measurement; "validated" = its first-step loss and per-parameter gradient norms (same
@@ -564,15 +758,21 @@ def main():
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample -------------------
     cpu_baseline = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from scipy import sparse
 
         Lt = sparse.csr_matrix((layer._L_values.astype(np.float64), (layer._L_indices[:, 0], layer._L_indices[:, 1])),
                                shape=g.L.shape)  # the layer's own prepared L~ (skips a second ARPACK run)
-        t, nb = cpu_reference_time(g.L, args, args.cpu_sample_batch, 2, 1, Lt=Lt)
+        t, nb, par = cpu_reference_time(g.L, args, args.cpu_sample_batch, 2, 1, Lt=Lt, sample=parity_sample)
         cpu_baseline = {"value": nb / t / 1e9, "unit": "GB/s", "cores": torch.get_num_threads(), "kind": "port",
                         "sample": f"batch {args.cpu_sample_batch} of {B} (same nside/K/F), fwd+bwd, torch-CPU "
                                   f"restatement of gnn_layers.py:131-150, 2 timed steps", "ms_per_step": t * 1e3}
+        if par is not None:
+            tol = PARITY_TOL[mode]
+            parity = {"rel_err": par, "tolerance": tol, "ok": bool(max(par.values()) <= tol),
+                      "what": f"GPU y / dx / dkernel of the first {args.cpu_sample_batch} map(s) of this workload vs the "
+                              f"CPU restatement on the same inputs (max|err| / max|ref|), mode {mode}"}
 
     if rank == 0:
         line = {
@@ -586,9 +786,13 @@ def main():
                        "mode": mode, "parallelism": f"batch-sharded x{world}", "l2": "inputs (6.4 GB/tensor) >> L2"},
             "roofline": roofline, "layer_roofline": layer_roofline, "kernels": kernels, "other_modes": other_modes, "model_train": model_train,
             "model_train_experimental": model_train_experimental,
-            "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
+            "model_train_partitioned": model_train_partitioned, "partition_parity": partition_parity,
+            "cpu_baseline": cpu_baseline, "parity": parity, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
         }
         print(json.dumps(line))
+        if parity is not None and not parity["ok"]:
+            sys.stderr.write(f"bench.py: PARITY FAILED at the bench configuration: {parity}\n")
+            sys.exit(3)
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -13,6 +13,10 @@ struct LatticeDev {
   int LW = 0, H = 0, T = 0;
   int32_t* pix = nullptr;  // [n_tiles][LW*LW]
   float* w = nullptr;      // [n_tiles][LW*LW][9]
+  // centre weight (the diagonal of L~) of every lattice position that carries a pixel: ONE value when the plan comes from a
+  // normalised Laplacian (L~_ii = 2*scale/lmax - 1) - the round-2 fused kernel keeps it as a scalar
+  bool diag_const = false;
+  float diag = 0.f;
 };
 
 struct LatticeArgs {

@@ -220,6 +220,18 @@ extern "C" int ds_plan_attach_lattice(ds_plan_t* plan, int32_t n_tiles, int32_t 
   L->H = H;
   L->dev.n_tiles = n_tiles; L->dev.LW = LW; L->dev.H = H; L->dev.T = T;
   const size_t P = (size_t)LW * LW;
+  {  // is the diagonal of L~ one scalar on every position that carries a pixel?  (holes: all nine weights are zero)
+    bool first = true, same = true;
+    float d0 = 0.f;
+    for (size_t i = 0; i < (size_t)n_tiles * P && same; ++i) {
+      if (pix[i] < 0) continue;
+      const float d = w[i * 9 + 8];
+      if (first) { d0 = d; first = false; }
+      else if (d != d0) same = false;
+    }
+    L->dev.diag_const = same && !first;
+    L->dev.diag = d0;
+  }
   auto up = [&](const void* src, size_t bytes, void** dst) -> int {
     *dst = nullptr;
     DS_CUDA(cudaMalloc(dst, std::max<size_t>(bytes, 16)));

@@ -54,17 +54,49 @@ constexpr int C2_BUF = C2_NQ * C2_PL;  // float4 per exchange buffer
 #define C2_BR 3
 #endif
 static_assert(C2_BR == 3 || C2_BR == 2, "block rows");
-constexpr int C2_NCW = (C2_LW / C2_BR) / 2;  // compute warps: a warp covers two block rows x 8 column blocks x 2 quads
-constexpr int C2_NCOMP = 32 * C2_NCW, C2_NLOAD = 96, C2_THREADS = C2_NCOMP + 32 + C2_NLOAD;
-// registers per CTA: C2_NCOMP * compute + 128 * io <= 32768 (two CTAs per SM); overridable for the variant builds
-#ifndef C2_REGS_COMPUTE
-#define C2_REGS_COMPUTE (C2_BR == 3 ? 208 : 136)
+// Channels per compute thread.  4 (round 1): a thread owns a float4 of its block's pixels, 4 compute warps per CTA.
+// 2 (round 2): a thread owns HALF a float4 (one FFMA2 per tap), two neighbouring lanes share a position: 8 compute
+// warps per CTA = 16 per SM against the per-hop dependency chain (exchange -> barrier -> perimeter loads), half the
+// basis values and perimeter registers per thread (no spills), the same shared-memory bytes per FMA.
+#ifndef C2_CPT
+#define C2_CPT 4
 #endif
+static_assert(C2_CPT == 4 || (C2_CPT == 2 && C2_BR == 3), "channels per thread");
+// Columns of the pixel block (C2_BR rows).  3 (round 1).  6 (round 2, with C2_CPT = 2): 3 x 6 pixels x 2 channels per thread,
+// the same 72 basis registers and 4 compute warps as the 3 x 3 x 4 shape, but 22 perimeter positions per 18 pixels
+// instead of 16 per 9: the exchange loads - the largest share of the shared-memory wavefronts, which the ncu counters
+// show to be the kernel's ceiling (60 % busy at 31 % FMA) - drop by a third, and 112 of the 162 FFMA2 of a hop only
+// need the thread's own registers (they run before the wait for the neighbours).
+#ifndef C2_BC
+#define C2_BC 3
+#endif
+static_assert(C2_BC == 3 || (C2_BC == 6 && C2_CPT == 2 && C2_BR == 3), "block columns");
+constexpr int C2_NB = C2_LW / C2_BC;  // blocks per lattice row; the columns of a block are de-interleaved (see slot_of_col)
+constexpr int C2_VP = 4 / C2_CPT;  // vectors of a thread's width per 16-byte position
+constexpr int C2_NCW = (C2_LW / C2_BR) * C2_NB * 2 * C2_VP / 32;  // compute warps (one thread per block, quad and half)
+// position of lattice column c inside its row: the C2_NB blocks' columns cc sit next to each other, so that the lanes
+// of a quarter- / half-warp touch consecutive 16-byte positions; 8 consecutive positions are one UMMA core matrix
+__host__ __device__ constexpr int slot_of_col(int c) { return (c % C2_BC) * C2_NB + c / C2_BC; }
+__host__ __device__ constexpr int col_of_slot(int p) { return (p % C2_NB) * C2_BC + p / C2_NB; }
+#ifndef C2_NLOAD
+#define C2_NLOAD 96
+#endif
+static_assert(C2_NLOAD % 32 == 0 && (2 * C2_LW * C2_LW) % C2_NLOAD == 0, "gather threads");
+constexpr int C2_NCOMP = 32 * C2_NCW, C2_THREADS = C2_NCOMP + 32 + C2_NLOAD;
+constexpr int C2_NEPI = C2_NCW >= 8 ? 8 : 4;  // warps that drain the accumulators (TMEM lane quarter = warp % 4)
+// registers per CTA (two CTAs per SM): the pool is what the launch allocates, threads x (registers per thread of the
+// launch bound, a multiple of 8); setmaxnreg moves it between the roles.  Overridable for the variant builds.
+constexpr int C2_REG_POOL = (32768 / C2_THREADS / 8) * 8 * C2_THREADS;
 #ifndef C2_REGS_IO
-#define C2_REGS_IO 48
+#define C2_REGS_IO (C2_CPT == 2 ? 32 : 48)
+#endif
+#ifndef C2_REGS_COMPUTE
+#define C2_REGS_COMPUTE (((C2_REG_POOL - (C2_THREADS - C2_NCOMP) * C2_REGS_IO) / C2_NCOMP) / 8 * 8)
 #endif
 constexpr int C2_REG_COMPUTE = C2_REGS_COMPUTE, C2_REG_IO = C2_REGS_IO;
-static_assert(C2_NCOMP * C2_REG_COMPUTE + 128 * C2_REG_IO <= 32768, "register budget of two CTAs per SM");
+#ifndef C2_SKIP_REG_ASSERT
+static_assert(C2_NCOMP * C2_REG_COMPUTE + (C2_THREADS - C2_NCOMP) * C2_REG_IO <= C2_REG_POOL, "register budget of two CTAs per SM");
+#endif
 constexpr int C2_TMEM_COLS = 256;
 
 struct Conv2Args {
@@ -76,6 +108,7 @@ struct Conv2Args {
   int b_split;
   int nsteps;  // hops, 1..4
   float wscale;
+  float wdiag;              // C2_CDIAG: the (already scaled) centre weight of every pixel
   long long* dbg;           // optional timeline probe [item < 16][hop 0..4][8 slots] of clock64 (block 0)
   int sleep_mma, sleep_ld;  // ns of back-off between polls of the issuer / gather roles (0: plain spin)
   const float* in0;     // [B, M, F]
@@ -153,6 +186,26 @@ __device__ __forceinline__ void f4_mul(float w, const float4& x, float4& acc) { 
 __device__ __forceinline__ float4 f4_scale(float w, const float4& x) {
   return make_float4(w * x.x, w * x.y, w * x.z, w * x.w);
 }
+// two channels per thread (C2_CPT == 2): one packed FFMA2 per tap
+template <int ROT>
+__device__ __forceinline__ void f4_fma(float w, const float2& x, float2& acc) {
+  acc = __ffma2_rn(make_float2(w, w), x, acc);
+}
+template <int ROT>
+__device__ __forceinline__ void f4_fms(float w, const float2& x, float2& acc) {
+  acc = __ffma2_rn(make_float2(w, w), x, make_float2(-acc.x, -acc.y));
+}
+template <int ROT>
+__device__ __forceinline__ void f4_mul(float w, const float2& x, float2& acc) {
+  acc = make_float2(w * x.x, w * x.y);
+}
+__device__ __forceinline__ float2 f4_scale(float w, const float2& x) { return make_float2(w * x.x, w * x.y); }
+#if C2_CPT == 2
+typedef float2 cvec;
+static_assert(C2_FFMA2, "two channels per thread need the packed form");
+#else
+typedef float4 cvec;
+#endif
 __device__ __noinline__ float4 act4(float4 v, int act) {
   return make_float4(act_apply(v.x, act), act_apply(v.y, act), act_apply(v.z, act), act_apply(v.w, act));
 }
@@ -194,7 +247,7 @@ __device__ __forceinline__ constexpr int dir_of(int dr, int dc) {
 // 0 = compile the clock64 timeline probe (DEEPSPHERE_CONV2_DEBUG) out of the kernel: its predicates, branches and
 // constant loads are ~5 % of the instructions the compute warps issue (ncu source page, r1k capture)
 #ifndef C2_PROBE
-#define C2_PROBE 1
+#define C2_PROBE 0  // round 2 default (measured r2c: 15.5 -> 14.3 ms forward); build with -DC2_PROBE=1 for the timeline
 #endif
 // Experiment switch: 1 = two barriers per hop.  hop_ready: every compute thread arrives right after its exchange stores
 // (generic proxy; mbarrier arrive / wait are release / acquire) and it is what the NEXT hop's perimeter loads wait for;
@@ -209,9 +262,28 @@ __device__ __forceinline__ constexpr int dir_of(int dr, int dc) {
 #ifndef C2_EPI_PIPE
 #define C2_EPI_PIPE 0
 #endif
+// 1 = the centre weight (the diagonal of L~) is ONE scalar for the whole plan (normalised Laplacians: a - 1, SURVEY F8;
+// checked on the host when the lattice is attached, Conv2Args::wdiag): 9 (18) weight registers per thread less
+#ifndef C2_CDIAG
+#define C2_CDIAG (C2_BC == 6)
+#endif
+// 1 = the warp that owns the outermost block rows (lattice rows 0-2 and 21-23) sits out the hops whose valid region no
+// longer reaches them (the last two hops of an item): no loads, FMAs or stores, only the barrier arrivals
+#ifndef C2_SKIP_OUTER
+#define C2_SKIP_OUTER 0  // measured (r2b): 15.3 ms with, 14.6 ms without - the divergence costs more than the idle warp saves
+#endif
+// 1 = the hops of an item run as a LOOP over one code body per buffer parity instead of four unrolled, individually
+// specialised hops.  Why: the ncu captures show the GPC-level instruction cache at 84 - 90 % of its peak request rate
+// (gcc__cache_requests_type_instruction; the SM's own instruction cache misses 10 % of its requests, stall_no_inst 10 %):
+// the compute role's straight-line code is ~57 KB per item, more than the SM-level instruction cache holds, and the two
+// co-resident CTAs walk it out of phase.  The looped form is ~4x smaller.
+#ifndef C2_LOOP
+#define C2_LOOP 0
+#endif
+static_assert(!C2_LOOP || (C2_FFMA2 && !C2_SPLIT_BAR && !C2_SKIP_OUTER), "looped hops: packed arithmetic, one barrier per hop");
 #if C2_SYMW
 // the weight of the tap (r, cc) <- (sr, sc), both inside the block, is read from the OTHER pixel's table entry
-__host__ __device__ constexpr bool sym_other(int r, int cc, int sr, int sc) { return (sr * 3 + sc) < (r * 3 + cc); }
+__host__ __device__ constexpr bool sym_other(int r, int cc, int sr, int sc) { return (sr * C2_BC + sc) < (r * C2_BC + cc); }
 #endif
 
 // One hop on the thread's 3x3 block, in two parts so that the part that needs no other thread's data overlaps the
@@ -220,14 +292,15 @@ __host__ __device__ constexpr bool sym_other(int r, int cc, int sr, int sc) { re
 //   hop_perimeter: acc += taps whose source is one of the 16 perimeter pixels (loaded from `src`, which points at the
 //                  thread's own (r = 0, cc = 0) position of the buffer holding `in` of all threads); halved if HALVE
 template <bool HAS_OLD, int ROT>
-__device__ __forceinline__ void hop_inside(const float4 (&in)[C2_BR][3], float4 (&acc)[C2_BR][3],
-                                           const float (&w)[C2_BR][3][9]) {
+__device__ __forceinline__ void hop_inside(const cvec (&in)[C2_BR][C2_BC], cvec (&acc)[C2_BR][C2_BC],
+                                           const float (&w)[C2_BR][C2_BC][9], const float wdiag) {
 #pragma unroll
   for (int r = 0; r < C2_BR; ++r)
 #pragma unroll
-    for (int cc = 0; cc < 3; ++cc) {
-      if (HAS_OLD) f4_fms<ROT>(w[r][cc][8], in[r][cc], acc[r][cc]);
-      else f4_mul<ROT>(w[r][cc][8], in[r][cc], acc[r][cc]);
+    for (int cc = 0; cc < C2_BC; ++cc) {
+      const float wc = C2_CDIAG ? wdiag : w[r][cc][8];
+      if (HAS_OLD) f4_fms<ROT>(wc, in[r][cc], acc[r][cc]);
+      else f4_mul<ROT>(wc, in[r][cc], acc[r][cc]);
     }
 #pragma unroll
   for (int dr = -1; dr <= 1; ++dr)
@@ -236,10 +309,10 @@ __device__ __forceinline__ void hop_inside(const float4 (&in)[C2_BR][3], float4 
 #pragma unroll
       for (int r = 0; r < C2_BR; ++r)
 #pragma unroll
-        for (int cc = 0; cc < 3; ++cc) {
+        for (int cc = 0; cc < C2_BC; ++cc) {
           if (dr == 0 && dc == 0) continue;
           const int sr = r + dr, sc = cc + dc;
-          if (!(sr >= 0 && sr < C2_BR && sc >= 0 && sc < 3)) continue;
+          if (!(sr >= 0 && sr < C2_BR && sc >= 0 && sc < C2_BC)) continue;
 #if C2_SYMW
           f4_fma<ROT>(sym_other(r, cc, sr, sc) ? w[sr][sc][dir_of(-dr, -dc)] : w[r][cc][dir_of(dr, dc)], in[sr][sc],
                       acc[r][cc]);
@@ -249,20 +322,20 @@ __device__ __forceinline__ void hop_inside(const float4 (&in)[C2_BR][3], float4 
         }
 }
 template <bool HALVE, int ROT>
-__device__ __forceinline__ void hop_perimeter(float4 (&acc)[C2_BR][3], const float (&w)[C2_BR][3][9],
-                                              const float4* __restrict__ src) {
-  // position offsets of columns -1, 0, 1, 2, 3 relative to the own column-0 position
-  constexpr int CO[5] = {15, 0, 8, 16, 1};
-  float4 top[5], bot[5], lft[C2_BR], rgt[C2_BR];
+__device__ __forceinline__ void hop_perimeter(cvec (&acc)[C2_BR][C2_BC], const float (&w)[C2_BR][C2_BC][9],
+                                              const cvec* __restrict__ src) {
+  // position offsets of columns -1, 0, .., C2_BC relative to the own column-0 position (k = column + 1)
+  auto co = [](int k) constexpr { return k == 0 ? (C2_BC - 1) * C2_NB - 1 : (k == C2_BC + 1 ? 1 : (k - 1) * C2_NB); };
+  cvec top[C2_BC + 2], bot[C2_BC + 2], lft[C2_BR], rgt[C2_BR];
 #pragma unroll
-  for (int k = 0; k < 5; ++k) top[k] = src[-C2_LW + CO[k]];
+  for (int k = 0; k < C2_BC + 2; ++k) top[k] = src[(-C2_LW + co(k)) * C2_VP];
 #pragma unroll
   for (int r = 0; r < C2_BR; ++r) {
-    lft[r] = src[r * C2_LW + 15];
-    rgt[r] = src[r * C2_LW + 1];
+    lft[r] = src[(r * C2_LW + co(0)) * C2_VP];
+    rgt[r] = src[(r * C2_LW + 1) * C2_VP];
   }
 #pragma unroll
-  for (int k = 0; k < 5; ++k) bot[k] = src[C2_BR * C2_LW + CO[k]];
+  for (int k = 0; k < C2_BC + 2; ++k) bot[k] = src[(C2_BR * C2_LW + co(k)) * C2_VP];
 #pragma unroll
   for (int dr = -1; dr <= 1; ++dr)
 #pragma unroll
@@ -270,10 +343,10 @@ __device__ __forceinline__ void hop_perimeter(float4 (&acc)[C2_BR][3], const flo
 #pragma unroll
       for (int r = 0; r < C2_BR; ++r)
 #pragma unroll
-        for (int cc = 0; cc < 3; ++cc) {
+        for (int cc = 0; cc < C2_BC; ++cc) {
           if (dr == 0 && dc == 0) continue;
           const int sr = r + dr, sc = cc + dc;
-          if (sr >= 0 && sr < C2_BR && sc >= 0 && sc < 3) continue;
+          if (sr >= 0 && sr < C2_BR && sc >= 0 && sc < C2_BC) continue;
           const float wv = w[r][cc][dir_of(dr, dc)];
           if (sr < 0) f4_fma<ROT>(wv, top[sc + 1], acc[r][cc]);
           else if (sr > C2_BR - 1) f4_fma<ROT>(wv, bot[sc + 1], acc[r][cc]);
@@ -284,7 +357,7 @@ __device__ __forceinline__ void hop_perimeter(float4 (&acc)[C2_BR][3], const flo
 #pragma unroll
     for (int r = 0; r < C2_BR; ++r)
 #pragma unroll
-      for (int cc = 0; cc < 3; ++cc) acc[r][cc] = f4_scale(0.5f, acc[r][cc]);
+      for (int cc = 0; cc < C2_BC; ++cc) acc[r][cc] = f4_scale(0.5f, acc[r][cc]);
   }
 }
 
@@ -317,7 +390,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
       ptx::mbar_init(&ctl->mma_done[i], 1);
     }
     ptx::mbar_init(&ctl->acc_full, 1);
-    ptx::mbar_init(&ctl->acc_empty, 4);
+    ptx::mbar_init(&ctl->acc_empty, C2_NEPI);
     ptx::fence_mbar_init();
   }
   if (warp == C2_NCW) ptx::tmem_alloc(&ctl->tmem_base, C2_TMEM_COLS);
@@ -331,12 +404,23 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
     C2_SETMAXNREG_INC(C2_REG_COMPUTE);
     // (skipping the block rows that lie outside the valid region of hops 3, 4 was measured: no gain, the kernel is
     // bound by the per-hop dependency chain, not by issue slots)
-    const int R = 2 * warp + (lane >> 4), q = (lane >> 3) & 1, cb = lane & 7;
-    const int own0 = q * C2_PL + (C2_BR * R + 1) * C2_LW + cb;  // float4 index of the own (0, 0) position
-    const int FV = a.F / 4, NV16 = N / 16;
+#if C2_CPT == 2
+    // lane = (quad q, column block cb, half h): the 16 lanes of a half-warp touch 128 consecutive bytes (LDS.64 / STS.64)
+#if C2_BC == 6
+    // lane = (block-row half, quad q, column block cb (4), half h); warp 0 owns the outermost block rows 0 and 7
+    const int R = warp == 0 ? 7 * (lane >> 4) : 2 * warp - 1 + (lane >> 4), q = (lane >> 3) & 1, cb = (lane >> 1) & 3, h = lane & 1;
+#else
+    const int R = warp, q = lane >> 4, cb = (lane >> 1) & 7, h = lane & 1;
+#endif
+#else
+    const int R = 2 * warp + (lane >> 4), q = (lane >> 3) & 1, cb = lane & 7, h = 0;
+#endif
+    const int own0 = (q * C2_PL + (C2_BR * R + 1) * C2_LW + cb) * C2_VP + h;  // cvec index of the own (0, 0) position
+    const int FV = a.F / C2_CPT, NV16 = N / 16;
+    const int egrp = C2_NEPI == 8 ? (warp >> 2) : 0;  // which half of the accumulator slices this warp drains
     const bool has_out = a.out[0] != nullptr || a.out[1] != nullptr || a.out[2] != nullptr || a.out[3] != nullptr;
-    float w[C2_BR][3][9];
-    float4 A[C2_BR][3], Bv[C2_BR][3];
+    float w[C2_BR][C2_BC][9];
+    cvec A[C2_BR][C2_BC], Bv[C2_BR][C2_BC];
     uint32_t it = 0, g = 0;
     uint32_t cnt_done[2] = {0, 0}, par[2] = {0, 0};
     int last_bar = -1;
@@ -352,32 +436,36 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
       ptx::mbar_wait(&ctl->acc_full, pend_g & 1);
       ptx::tc_fence_after_sync();
 #if C2_EPI_PIPE
-      // one flat loop over the 3 * N / 16 accumulator slices with the tensor-memory load of slice i + 1 in flight while
-      // slice i is biased, activated and stored (the ncu source page shows the drain waiting on every tcgen05.ld)
+      // one flat loop over this warp's share of the 3 * N / 16 accumulator slices (slice = egrp + j * groups) with the
+      // tensor-memory load of the next slice in flight while the current one is biased, activated and stored (the ncu
+      // source page shows the drain waiting on every tcgen05.ld)
       {
+        constexpr int G = C2_NEPI / 4;
         const int n_slices = 3 * NV16;
-        const uint32_t t0 = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t t0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t rbuf[2][16];
-        ptx::tmem_ld_32x32b_x16(t0, rbuf[0]);
-        ptx::tmem_ld_wait();
+        if (egrp < n_slices) {
+          ptx::tmem_ld_32x32b_x16(t0 + (uint32_t)((egrp / NV16) * N + (egrp % NV16) * 16), rbuf[0]);
+          ptx::tmem_ld_wait();
+        }
 #pragma unroll 1
-        for (int i = 0; i < n_slices; i += 2) {
+        for (int i = egrp; i < n_slices; i += 2 * G) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int cur = i + h;
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int cur = i + h2 * G;
             if (cur >= n_slices) break;
             const int mt = cur / NV16, cc = cur - mt * NV16;
-            if (cur + 1 < n_slices) {
-              const int nmt = (cur + 1) / NV16, ncc = (cur + 1) - nmt * NV16;
-              ptx::tmem_ld_32x32b_x16(t0 + (uint32_t)(nmt * N + ncc * 16), rbuf[h ^ 1]);
+            if (cur + G < n_slices) {
+              const int nmt = (cur + G) / NV16, ncc = (cur + G) - nmt * NV16;
+              ptx::tmem_ld_32x32b_x16(t0 + (uint32_t)(nmt * N + ncc * 16), rbuf[h2 ^ 1]);
             }
             const int row = pend_rows[mt];
             if (row >= 0) {
               float* yrow = a.y + (pend_b * a.M + row) * (int64_t)N;
 #pragma unroll
               for (int v = 0; v < 4; ++v) {
-                float4 o = make_float4(__uint_as_float(rbuf[h][v * 4]), __uint_as_float(rbuf[h][v * 4 + 1]),
-                                       __uint_as_float(rbuf[h][v * 4 + 2]), __uint_as_float(rbuf[h][v * 4 + 3]));
+                float4 o = make_float4(__uint_as_float(rbuf[h2][v * 4]), __uint_as_float(rbuf[h2][v * 4 + 1]),
+                                       __uint_as_float(rbuf[h2][v * 4 + 2]), __uint_as_float(rbuf[h2][v * 4 + 3]));
                 if (a.bias != nullptr) {
                   const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + cc * 16 + v * 4));
                   o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
@@ -397,8 +485,9 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
         float* yrow = a.y + (pend_b * a.M + (row >= 0 ? row : 0)) * (int64_t)N;
 #pragma unroll 1
         for (int cc = 0; cc < NV16; ++cc) {
+          if (C2_NEPI == 8 && ((mt * NV16 + cc) & 1) != egrp) continue;
           uint32_t r[16];
-          ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * N + cc * 16), r);
+          ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * N + cc * 16), r);
           ptx::tmem_ld_wait();
           if (row >= 0) {
 #pragma unroll
@@ -439,43 +528,111 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
 #pragma unroll
       for (int r = 0; r < C2_BR; ++r)
 #pragma unroll
-        for (int cc = 0; cc < 3; ++cc) {
-          const float* wp = a.w + ((size_t)tile * C2_P + (size_t)(C2_BR * R + r) * C2_LW + 3 * cb + cc) * 9;
+        for (int cc = 0; cc < C2_BC; ++cc) {
+          const float* wp = a.w + ((size_t)tile * C2_P + (size_t)(C2_BR * R + r) * C2_LW + C2_BC * cb + cc) * 9;
 #if C2_SYMW
 #pragma unroll
           for (int dr = -1; dr <= 1; ++dr)
 #pragma unroll
             for (int dc = -1; dc <= 1; ++dc) {
               const int sr = r + dr, sc = cc + dc, d = dir_of(dr, dc);
-              const bool inside = sr >= 0 && sr < C2_BR && sc >= 0 && sc < 3 && d != 8;
+              const bool inside = sr >= 0 && sr < C2_BR && sc >= 0 && sc < C2_BC && d != 8;
               if (inside && sym_other(r, cc, sr, sc)) continue;  // kept by the other pixel of the link
+              if (C2_CDIAG && d == 8) continue;
               C2_SCALED_WEIGHT(w[r][cc][d], __ldg(wp + d), a.wscale);
             }
 #else
 #pragma unroll
-          for (int d = 0; d < 9; ++d) C2_SCALED_WEIGHT(w[r][cc][d], __ldg(wp + d), a.wscale);
+          for (int d = 0; d < (C2_CDIAG ? 8 : 9); ++d) C2_SCALED_WEIGHT(w[r][cc][d], __ldg(wp + d), a.wscale);
 #endif
         }
 #pragma unroll
       for (int mt = 0; mt < 3; ++mt) {  // accumulator row (mt, TMEM lane) -> lattice position -> row of y
-        const int m = mt * 128 + warp * 32 + lane;
-        const int j = C2_H + m / C2_LW, p = m % C2_LW, c = 3 * (p & 7) + (p >> 3);
+        const int m = mt * 128 + (warp & 3) * 32 + lane;
+        const int j = C2_H + m / C2_LW, p = m % C2_LW, c = col_of_slot(p);
         erow[mt] = (c >= C2_H && c < C2_H + C2_T) ? __ldg(tpix + j * C2_LW + c) : -1;
       }
 
       for (int64_t b = b_begin; b < b_end; ++b) {
         for (int c = 0; c < n_chunks; ++c) {
           const uint32_t st = it & 1;
-          const float4* S = bufs + (size_t)st * C2_BUF;
-          float4* X[2] = {bufs + 2 * (size_t)C2_BUF, bufs + 3 * (size_t)C2_BUF};
+          const cvec* S = reinterpret_cast<const cvec*>(bufs + (size_t)st * C2_BUF);
+          cvec* X[2] = {reinterpret_cast<cvec*>(bufs + 2 * (size_t)C2_BUF), reinterpret_cast<cvec*>(bufs + 3 * (size_t)C2_BUF)};
           if (C2_PROBE && a.dbg != nullptr && blockIdx.x == 0 && it < 16 && tid == 0) a.dbg[((size_t)(it & 15) * 5) * 8 + 0] = clock64();
           ptx::mbar_wait(&ctl->in_full[st], (it >> 1) & 1);
           if (C2_PROBE && a.dbg != nullptr && blockIdx.x == 0 && it < 16 && tid == 0) a.dbg[((size_t)(it & 15) * 5) * 8 + 1] = clock64();
 #pragma unroll
           for (int r = 0; r < C2_BR; ++r)
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc) A[r][cc] = S[own0 + r * C2_LW + cc * 8];
+            for (int cc = 0; cc < C2_BC; ++cc) A[r][cc] = S[own0 + (r * C2_LW + cc * C2_NB) * C2_VP];
 
+#if C2_LOOP
+          // Hop s: `in` (T_{s-1}) -> `acc` (T_{s-2} -> T_s); one body per buffer parity p = (s - 1) & 1 (the register
+          // arrays alternate), everything that depends on s is a run-time value.  Chebyshev: `acc` starts as zero, so
+          // hop 1 is the same "w * in - acc" as the others (T_1 = (2 L~ T_0) / 2: halved after the perimeter taps).
+          auto hop_body = [&](auto p_tag, const cvec(&in)[C2_BR][C2_BC], cvec(&acc)[C2_BR][C2_BC], const int s) {
+            constexpr int p = decltype(p_tag)::value;
+            hop_inside<CHEB, 2>(in, acc, w, a.wdiag);  // own registers only: runs before the wait for the neighbours
+            const cvec* src = S;
+            if (s > 1) {
+              ptx::mbar_wait(&ctl->hop_full[p ^ 1], par[p ^ 1]);  // hop s - 1 published by everybody
+              src = X[p ^ 1];
+            }
+            // the UMMAs that read X[p] two hops ago: probe now, consume after the arithmetic (hides the round trip)
+            const bool mma_ok = cnt_done[p] == 0 || ptx::mbar_test_wait(&ctl->mma_done[p], (cnt_done[p] - 1) & 1);
+            hop_perimeter<false, 2>(acc, w, src + own0);
+            if (CHEB && s == 1) {
+#pragma unroll
+              for (int r = 0; r < C2_BR; ++r)
+#pragma unroll
+                for (int cc = 0; cc < C2_BC; ++cc) acc[r][cc] = f4_scale(0.5f, acc[r][cc]);
+            }
+            if (!mma_ok) ptx::mbar_wait(&ctl->mma_done[p], (cnt_done[p] - 1) & 1);
+            if (s == 1 && last_bar >= 0) {  // previous item's last phase: everybody has finished reading X[0]
+              ptx::mbar_wait(&ctl->hop_full[last_bar], last_par);
+              last_bar = -1;
+            }
+            cvec* dst = X[p] + own0;
+#pragma unroll
+            for (int r = 0; r < C2_BR; ++r)
+#pragma unroll
+              for (int cc = 0; cc < C2_BC; ++cc) dst[(r * C2_LW + cc * C2_NB) * C2_VP] = acc[r][cc];
+            ptx::fence_proxy_async_smem();
+            ptx::mbar_arrive(&ctl->hop_full[p]);
+            if (has_out) {
+              float* outp = s == 1 ? a.out[0] : (s == 2 ? a.out[1] : (s == 3 ? a.out[2] : a.out[3]));
+              if (outp != nullptr) {
+                cvec* ob = reinterpret_cast<cvec*>(outp + (b * a.M * a.F + c * C2_FC)) + q * C2_VP + h;
+#pragma unroll
+                for (int r = 0; r < C2_BR; ++r)
+#pragma unroll
+                  for (int cc = 0; cc < C2_BC; ++cc) {
+                    const int row = s_pix[(C2_BR * R + r) * C2_LW + C2_BC * cb + cc];
+                    if (row >= 0) __stcs(ob + (int64_t)row * FV, acc[r][cc]);
+                  }
+              }
+            }
+            par[p] = cnt_done[p] & 1;  // parity of the phase this arrival belongs to
+            cnt_done[p]++;
+          };
+          if (CHEB) {
+#pragma unroll
+            for (int r = 0; r < C2_BR; ++r)
+#pragma unroll
+              for (int cc = 0; cc < C2_BC; ++cc) Bv[r][cc] = cvec{};
+          }
+          int last = 0;
+#pragma unroll 1
+          for (int s = 1; s <= nsteps; s += 2) {
+            hop_body(std::integral_constant<int, 0>{}, A, Bv, s);
+            last = 0;
+            if (s == 1 && pend) epilogue();
+            if (s + 1 <= nsteps) {
+              hop_body(std::integral_constant<int, 1>{}, Bv, A, s + 1);
+              last = 1;
+            }
+          }
+#else
           // Hop s: `in` (T_{s-1}) -> `acc` (T_{s-2} -> T_s), the register arrays alternate; results are published in
           // X[(s-1)&1].  There is no __syncthreads: every thread arrives on hop_full[p] (count 128) after its stores
           // and proxy fence, starts the inside part of the NEXT hop (own registers only, 60 % of the taps) and only
@@ -483,18 +640,22 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
           // hop: positions outside the shrinking valid region hold don't-care values that never reach a valid
           // output (a valid output only reads valid inputs).
           // (st.async + complete_tx instead of STS + proxy fence was measured: ~20 B/clk, 3x slower.)
-          auto finish_hop = [&](auto s_tag, float4(&acc)[C2_BR][3], const float4* src) {
+          // C2_SKIP_OUTER: hop s of an item with `nsteps` hops needs lattice rows 4 - (nsteps - s) .. 19 + (nsteps - s)
+          auto skip_hop = [&](int s) { return C2_SKIP_OUTER && C2_BC == 6 && warp == 0 && s > nsteps - 2; };
+          auto finish_hop = [&](auto s_tag, cvec(&acc)[C2_BR][C2_BC], const cvec* src) {
             constexpr int s = decltype(s_tag)::value;
             constexpr int p = (s - 1) & 1;
             const bool probe = C2_PROBE && a.dbg != nullptr && blockIdx.x == 0 && it < 16 && tid == 0;
             long long* pd = a.dbg + ((size_t)(it & 15) * 5 + s) * 8;
             if (probe) pd[0] = clock64();
             // the UMMAs that read X[p] two hops ago: probe now, consume after the arithmetic (hides the round trip)
-            const bool mma_ok = cnt_done[p] == 0 || ptx::mbar_test_wait(&ctl->mma_done[p], (cnt_done[p] - 1) & 1);
-            hop_perimeter<(CHEB && s == 1), rot_of_hop(s)>(acc, w, src + own0);
+            const bool skp = skip_hop(s);  // warp-uniform
+            const bool mma_ok = skp || cnt_done[p] == 0 || ptx::mbar_test_wait(&ctl->mma_done[p], (cnt_done[p] - 1) & 1);
+            if (!skp) hop_perimeter<(CHEB && s == 1), rot_of_hop(s)>(acc, w, src + own0);
             if (probe) pd[1] = clock64();
             if (!mma_ok) ptx::mbar_wait(&ctl->mma_done[p], (cnt_done[p] - 1) & 1);
-            if (s == 1 && last_bar >= 0) {  // previous item's last phase: everybody has finished reading X[0]
+            if (s == 1 && last_bar >= 0) {  // previous item's last phase: everybody has finished reading X[0] (a warp that
+                                            // sits this hop out waits too: its arrival must not land in that phase)
 #if C2_SPLIT_BAR
               ptx::mbar_wait(&ctl->hop_ready[last_bar], last_par);
 #else
@@ -503,11 +664,13 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
               last_bar = -1;
             }
             if (probe) pd[2] = clock64();
-            float4* dst = X[p] + own0;
+            cvec* dst = X[p] + own0;
+            if (!skp) {
 #pragma unroll
-            for (int r = 0; r < C2_BR; ++r)
+              for (int r = 0; r < C2_BR; ++r)
 #pragma unroll
-              for (int cc = 0; cc < 3; ++cc) dst[r * C2_LW + cc * 8] = acc[r][cc];
+                for (int cc = 0; cc < C2_BC; ++cc) dst[(r * C2_LW + cc * C2_NB) * C2_VP] = acc[r][cc];
+            }
 #if C2_SPLIT_BAR
             ptx::mbar_arrive(&ctl->hop_ready[p]);  // fence + hop_full arrive: publish(p), after the next inside taps
 #else
@@ -518,14 +681,18 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
 #endif
             if (probe) pd[3] = clock64();
             float* outp = a.out[s - 1];
-            if (outp != nullptr) {
-              float4* ob = reinterpret_cast<float4*>(outp + (b * a.M * a.F + c * C2_FC)) + q;
+            if (outp != nullptr && !skp) {
+              cvec* ob = reinterpret_cast<cvec*>(outp + (b * a.M * a.F + c * C2_FC)) + q * C2_VP + h;
 #pragma unroll
               for (int r = 0; r < C2_BR; ++r)
 #pragma unroll
-                for (int cc = 0; cc < 3; ++cc) {
-                  const int row = s_pix[(C2_BR * R + r) * C2_LW + 3 * cb + cc];
+                for (int cc = 0; cc < C2_BC; ++cc) {
+                  const int row = s_pix[(C2_BR * R + r) * C2_LW + C2_BC * cb + cc];
+#if C2_CPT == 4
                   const float4 v = hop_is_rotated(s) ? make_float4(acc[r][cc].w, acc[r][cc].x, acc[r][cc].y, acc[r][cc].z) : acc[r][cc];
+#else
+                  const cvec v = acc[r][cc];
+#endif
                   if (row >= 0) __stcs(ob + (int64_t)row * FV, v);
                 }
             }
@@ -543,7 +710,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
 #endif
             ptx::mbar_arrive(&ctl->hop_full[pp]);
           };
-          hop_inside<false, rot_of_hop(1)>(A, Bv, w);
+          if (!skip_hop(1)) hop_inside<false, rot_of_hop(1)>(A, Bv, w, a.wdiag);
           finish_hop(std::integral_constant<int, 1>{}, Bv, S);
           bool pub = false;
           if (pend) {  // the drain is long: do not hold hop 1 back behind it
@@ -553,7 +720,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
           }
           int last = 0;
           if (nsteps >= 2) {
-            hop_inside<CHEB, rot_of_hop(2)>(Bv, A, w);
+            if (!skip_hop(2)) hop_inside<CHEB, rot_of_hop(2)>(Bv, A, w, a.wdiag);
             if (!pub) publish(0);
             wait_hop(0);
             finish_hop(std::integral_constant<int, 2>{}, A, X[0]);
@@ -563,7 +730,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
             publish(0);
           }
           if (nsteps >= 3) {
-            hop_inside<CHEB, rot_of_hop(3)>(A, Bv, w);
+            if (!skip_hop(3)) hop_inside<CHEB, rot_of_hop(3)>(A, Bv, w, a.wdiag);
             publish(1);
             wait_hop(1);
             finish_hop(std::integral_constant<int, 3>{}, Bv, X[1]);
@@ -571,7 +738,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
             if (nsteps == 3) publish(0);
           }
           if (nsteps >= 4) {
-            hop_inside<CHEB, rot_of_hop(4)>(Bv, A, w);
+            if (!skip_hop(4)) hop_inside<CHEB, rot_of_hop(4)>(Bv, A, w, a.wdiag);
             publish(0);
             wait_hop(0);
             finish_hop(std::integral_constant<int, 4>{}, A, X[0]);
@@ -581,34 +748,35 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
 #else
           auto wait_hop = [&](int pp) { ptx::mbar_wait(&ctl->hop_full[pp], par[pp]); };
 
-          hop_inside<false, rot_of_hop(1)>(A, Bv, w);
+          if (!skip_hop(1)) hop_inside<false, rot_of_hop(1)>(A, Bv, w, a.wdiag);
           finish_hop(std::integral_constant<int, 1>{}, Bv, S);
           if (pend) epilogue();
           int last = 0;
           if (nsteps >= 2) {
-            hop_inside<CHEB, rot_of_hop(2)>(Bv, A, w);
+            if (!skip_hop(2)) hop_inside<CHEB, rot_of_hop(2)>(Bv, A, w, a.wdiag);
             wait_hop(0);
             finish_hop(std::integral_constant<int, 2>{}, A, X[0]);
             last = 1;
           }
           if (nsteps >= 3) {
-            hop_inside<CHEB, rot_of_hop(3)>(A, Bv, w);
+            if (!skip_hop(3)) hop_inside<CHEB, rot_of_hop(3)>(A, Bv, w, a.wdiag);
             wait_hop(1);
             finish_hop(std::integral_constant<int, 3>{}, Bv, X[1]);
             last = 0;
           }
           if (nsteps >= 4) {
-            hop_inside<CHEB, rot_of_hop(4)>(Bv, A, w);
+            if (!skip_hop(4)) hop_inside<CHEB, rot_of_hop(4)>(Bv, A, w, a.wdiag);
             wait_hop(0);
             finish_hop(std::integral_constant<int, 4>{}, A, X[0]);
             last = 1;
           }
 #endif
+#endif  // C2_LOOP
           last_bar = last;
           last_par = par[last];
 
           if (c == n_chunks - 1) {
-            pend = C2_NCW <= 4 || warp < 4;  // TMEM lanes 32 (w % 4) .. + 31 belong to warp w: warps 0-3 drain
+            pend = warp < C2_NEPI;  // TMEM lanes 32 (w % 4) .. + 31 belong to warp w: 4 (or 2 x 4, half the slices each) warps drain
             pend_g = g;
             pend_b = b;
             pend_rows[0] = erow[0]; pend_rows[1] = erow[1]; pend_rows[2] = erow[2];
@@ -707,7 +875,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
     const int t = tid - (C2_NCW + 1) * 32;  // 0..95
     const int q = t & 1, pl0 = t >> 1;    // channel quad; position within a pair of lattice rows (0..47)
     const int inpos = pl0 % C2_LW, r0 = pl0 / C2_LW;
-    const int col = 3 * (inpos & 7) + (inpos >> 3);
+    const int col = col_of_slot(inpos);
     const int FV = a.F / 4;
     uint32_t it = 0;
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -780,6 +948,7 @@ size_t conv2_smem_bytes(int N, int nsteps) {
 bool lattice_conv2_usable(const LatticeDev& L, int nsteps, int F, int N, int mode) {
   if (mode != DS_MODE_TF32 || L.n_tiles <= 0) return false;
   if (L.T != C2_T || L.H != C2_H || L.LW != C2_LW) return false;
+  if (C2_CDIAG && !L.diag_const) return false;  // this build keeps the diagonal of L~ as one scalar
   if (nsteps < 1 || nsteps > C2_H) return false;
   if (F % C2_FC != 0 || N % 16 != 0 || N < 16 || 3 * N > C2_TMEM_COLS) return false;
   static const bool disabled = [] { const char* e = getenv("DEEPSPHERE_FUSED_CONV2"); return e && atoi(e) == 0; }();
@@ -808,6 +977,7 @@ int launch_lattice_conv2(const LatticeDev& L, int nsteps, int64_t B, int64_t M, 
   if (env_split > 0) split = env_split;
   a.b_split = (int)std::min<int64_t>(split, B);
   a.wscale = cheb ? 2.f : 1.f;
+  a.wdiag = a.wscale * L.diag;
   static const int sleep_mma = [] { const char* e = getenv("DEEPSPHERE_CONV2_SLEEP_MMA"); return e ? atoi(e) : 0; }();
   static const int sleep_ld = [] { const char* e = getenv("DEEPSPHERE_CONV2_SLEEP_LD"); return e ? atoi(e) : 128; }();
   a.sleep_mma = sleep_mma; a.sleep_ld = sleep_ld;

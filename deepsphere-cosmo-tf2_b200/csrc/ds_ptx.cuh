@@ -65,12 +65,15 @@ __device__ __forceinline__ void st_async_v4(void* dst, const float4& v, uint64_t
                : "memory");
 }
 // bounded wait: 2^22 suspended try_waits (each returns after <= 20 us or the shorter system limit: 4 - 80 s), then trap (surfaces as a launch failure, never a hang)
+// (no printf here: its call sequence sat in every wait's code - ~12 % of the fused kernel's instruction footprint - and an
+// out-of-line reporter forces the ABI's register saves onto callers that hold 200 live registers; a timed-out wait
+// surfaces as a trapped launch)
+__device__ __forceinline__ void mbar_timeout() { __trap(); }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #pragma unroll 1
   for (uint32_t i = 0; i < (1u << 22); ++i)
     if (mbar_try_wait(bar, parity)) return;
-  printf("deepsphere_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-  __trap();
+  mbar_timeout();
 }
 
 // same, for the producer / issuer roles that must not steal issue slots from the math warps while they poll
@@ -80,8 +83,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
     if (mbar_try_wait(bar, parity)) return;
     if (ns) __nanosleep(ns);
   }
-  printf("deepsphere_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-  __trap();
+  mbar_timeout();
 }
 
 // ---- proxies / fences ------------------------------------------------------------------

@@ -60,6 +60,21 @@ SIGNATURES = {
         ctypes.c_int,
         [_i64, _i64, _i64, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _i32, _ptr, _ptr, _ptr, _ptr, _i32, _ptr],
     ),
+    "ds_bn_workspace_doubles": (_i64, [_i64, _i64, _i64]),
+    "ds_bn_stats": (ctypes.c_int, [_i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr]),
+    "ds_bn_bias_act_forward": (
+        ctypes.c_int,
+        [_i64, _i64, _i64, _ptr, _ptr, ctypes.c_double, _ptr, _f32, _f32, _i32, _ptr, _ptr, _ptr, _i32, _ptr, _ptr, _ptr,
+         _ptr],
+    ),
+    "ds_bn_backward_stats": (ctypes.c_int, [_i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _i32, _ptr, _ptr, _ptr]),
+    "ds_bn_backward_apply": (
+        ctypes.c_int,
+        [_i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, ctypes.c_double, _ptr, _i32, _i32, _ptr, _ptr, _ptr],
+    ),
+    "ds_halo_pack": (ctypes.c_int, [_i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr]),
+    "ds_halo_assemble": (ctypes.c_int, [_i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "ds_halo_reduce": (ctypes.c_int, [_i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "ds_pconvT_forward": (ctypes.c_int, [_i64, _i64, _i64, _i64, _i32, _ptr, _ptr, _ptr, _i32, _ptr, _i32, _ptr]),
     "ds_pconvT_backward_workspace_elems": (_i64, [_i64, _i64, _i64, _i64, _i32, _i32]),
     "ds_pconvT_backward": (
@@ -177,6 +192,15 @@ class GraphPlan:
         p = self._lattice_payload
         if not p:
             return
+        try:
+            self._attach_lattice_payload(h, device_index, p)
+        except NativeError as exc:  # the optional fast path must never break the layer: generic kernels serve it
+            import logging
+
+            logging.getLogger("deepsphere").warning(f"lattice plan not attached ({exc}); using the generic kernels")
+            self._lattice_payload = {}
+
+    def _attach_lattice_payload(self, h, device_index, p):
         import torch
 
         def cptr(a):

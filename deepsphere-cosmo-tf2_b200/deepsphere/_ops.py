@@ -132,6 +132,92 @@ class _BiasAct(torch.autograd.Function):
         return dz, None if db is None else db.reshape(bias_shape), None
 
 
+class _BnBiasAct(torch.autograd.Function):
+    """y = act(BatchNormalization(center=False, scale=False)(z) + bias)  (gnn_layers.py:152-159) through ds_bn_*.
+
+    `rows` = (r0, r1): the rows of every sample that contribute to the statistics (and carry gradient); `group` /
+    `sync`: with an initialised process group the 2F + 1 sums are all-reduced so that the statistics are those of the
+    global batch - one collective per direction, issued between the two C-ABI calls."""
+
+    @staticmethod
+    def forward(ctx, z, bias, moving_mean, moving_var, act, training, eps, momentum, rows, sync_group):
+        import torch.distributed as dist
+
+        _need_cuda(z, "BatchNormalization")
+        z = _f32c(z)
+        B, M, F = z.shape
+        r0, r1 = (0, M) if rows is None else (int(rows[0]), int(rows[1]))
+        bias_c = None if bias is None else _f32c(bias).reshape(-1)
+        dev = z.device
+        lib = nat.lib()
+        y = torch.empty_like(z)
+        mean_rstd = torch.empty(2 * F, device=dev, dtype=torch.float32)
+        scratch = torch.empty(2 * F, device=dev, dtype=torch.float32)
+        sums = count_dev = None
+        count = float(B * (r1 - r0))
+        do_sync = bool(training) and sync_group is not False and dist.is_initialized() and \
+            dist.get_world_size(None if sync_group is True else sync_group) > 1
+        group = None if sync_group in (True, False) else sync_group
+        with torch.cuda.device(dev.index):
+            st = nat.current_stream()
+            if training:
+                ws = torch.empty(int(lib.ds_bn_workspace_doubles(B, M, F)), device=dev, dtype=torch.float64)
+                sums = torch.empty(2 * F + 1, device=dev, dtype=torch.float64)
+                nat.check(lib.ds_bn_stats(B, M, F, r0, r1, nat.ptr(z), nat.ptr(sums), nat.ptr(ws), st), "ds_bn_stats")
+                if do_sync:  # the global row count travels with the sums and stays on the device (no host sync)
+                    sums[2 * F] = count
+                    dist.all_reduce(sums, group=group)
+                    count_dev = sums[2 * F:]
+            nat.check(
+                lib.ds_bn_bias_act_forward(B, M, F, nat.ptr(z), nat.ptr(sums), count, nat.ptr(count_dev), float(eps),
+                                           float(momentum),
+                                           int(bool(training)), nat.ptr(moving_mean), nat.ptr(moving_var), nat.ptr(bias_c),
+                                           act, nat.ptr(mean_rstd), nat.ptr(scratch), nat.ptr(y), st),
+                "ds_bn_bias_act_forward",
+            )
+        ctx.save_for_backward(z, y if act != nat.ACT_LINEAR else None, mean_rstd, count_dev)
+        ctx.meta = (act, bool(training), (r0, r1), count, do_sync, group, None if bias is None else bias.shape)
+        ctx.mark_non_differentiable(moving_mean, moving_var)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        import torch.distributed as dist
+
+        z, y, mean_rstd, count_dev = ctx.saved_tensors
+        act, training, (r0, r1), count, do_sync, group, bias_shape = ctx.meta
+        dy = _f32c(dy)
+        B, M, F = z.shape
+        dev = z.device
+        lib = nat.lib()
+        dz = torch.empty_like(z)
+        db = torch.empty(F, device=dev, dtype=torch.float32) if bias_shape is not None else None
+        with torch.cuda.device(dev.index):
+            st = nat.current_stream()
+            ws = torch.empty(int(lib.ds_bn_workspace_doubles(B, M, F)), device=dev, dtype=torch.float64)
+            sums = torch.empty(2 * F, device=dev, dtype=torch.float64)
+            nat.check(lib.ds_bn_backward_stats(B, M, F, r0, r1, nat.ptr(z), nat.ptr(y), nat.ptr(dy), nat.ptr(mean_rstd), act,
+                                               nat.ptr(sums), nat.ptr(ws), st), "ds_bn_backward_stats")
+            local_sums = sums
+            if do_sync:
+                local_sums = sums.clone()  # dbias stays this rank's partial sum (the gradient all-reduce adds the ranks)
+                dist.all_reduce(sums, group=group)
+            nat.check(lib.ds_bn_backward_apply(B, M, F, r0, r1, nat.ptr(z), nat.ptr(y), nat.ptr(dy), nat.ptr(mean_rstd),
+                                               nat.ptr(sums), count, nat.ptr(count_dev), act, int(training), nat.ptr(dz),
+                                               None, st),
+                      "ds_bn_backward_apply")
+            if db is not None:
+                db.copy_(local_sums[:F])
+        return dz, None if db is None else db.reshape(bias_shape), None, None, None, None, None, None, None, None
+
+
+def bn_bias_act(z, bias, bn, act, training, rows=None, sync_group=True):
+    """BatchNormalization(center=False, scale=False) + bias + activation in the C-ABI kernels; `bn` is the
+    keras_compat.BatchNormalization that owns the moving statistics."""
+    return _BnBiasAct.apply(z, bias, bn.moving_mean, bn.moving_variance, act, training, bn.epsilon, bn.momentum, rows,
+                            sync_group)
+
+
 def bias_act(z, bias, act):
     if bias is None and act == nat.ACT_LINEAR:
         return z

@@ -81,6 +81,11 @@ class _GraphConvBase(Model):
         # optional HEALPix geometry (nside, NESTED pixel ids of the rows of L): enables the fused lattice
         # kernel; HealpyGCNN provides it, and a full-sphere Laplacian is recognised automatically
         self._healpix = kwargs.pop("healpix", None)
+        # BatchNormalization statistics: rows of every sample that contribute (None = all; a sphere-partitioned layer
+        # sets its own rows, partition.PartitionedGraphConv) and the process group they are summed over (True = the
+        # default group when one is initialised, False = never, or a group)
+        self._bn_rows = None
+        self._bn_sync = True
         # largest eigenvalue of L supplied by the caller (skips ARPACK): the sphere-partitioned layer passes the
         # GLOBAL value so that every rank's restricted Laplacian is the restriction of the same L~
         lmax_given = kwargs.pop("lmax", None)
@@ -124,9 +129,11 @@ class _GraphConvBase(Model):
             return None
         Lt = sparse.csr_matrix((self._L_values, (self._L_indices[:, 0], self._L_indices[:, 1])), shape=(M, M))
         try:
-            # K <= 5: always a 4-ring halo (24 x 24 lattice) - the geometry of the register-resident fused kernel
-            # (ds_lattice_conv2.cu); the kernels run K - 1 <= 4 hops on it
-            return lattice.make_payload(Lt, nside, indices, max(self._n_terms - 1, 4))
+            # always the 4-ring halo (24 x 24 lattice): the geometry of the register-resident fused kernel
+            # (ds_lattice_conv2.cu) and of the fp32 lattice recursion; K - 1 <= 4 hops run in one pass on it, longer
+            # recursions are chained in passes of <= 4 hops by the C-ABI (ds_graph_conv_*), so the tables never grow
+            # with K (a (16 + 2 (K-1))^2 lattice would cost 40 B x positions per tile: 2.3 GB at nside 1024, K = 10)
+            return lattice.make_payload(Lt, nside, indices, 4)
         except Exception as exc:  # never let the optional fast path break the layer
             logger.warning(f"lattice plan construction failed ({exc!r}); using the generic kernels")
             return None
@@ -176,7 +183,15 @@ class _GraphConvBase(Model):
         )
         if fuse:
             return x
+        if self.use_bn and self._act_id is not None and x.is_cuda:
+            # BatchNormalization(center=False, scale=False) -> + bias -> activation as C-ABI kernels (ds_bn_*): one
+            # statistics pass and one normalise + bias + activation pass, no framework kernels in between; with a process
+            # group the 2F + 1 sums are all-reduced (statistics of the global batch / of the whole partitioned sphere)
+            return _ops.bn_bias_act(x, bias, self.bn, self._act_id, training, rows=self._bn_rows, sync_group=self._bn_sync)
         if self.use_bn:
+            if self._bn_rows is not None:
+                raise nat.NativeError("BatchNormalization over a row range (sphere-partitioned layer) runs in the CUDA "
+                                      "kernels only (ds_bn_*): CUDA tensors and a named activation are required")
             x = self.bn(x, training=training)
         if self._act_id is not None:
             return _ops.bias_act(x, bias, self._act_id)
@@ -338,11 +353,14 @@ class GCNN_ResidualLayer(Model):
             self.bn2.build_from_shape(shape)
 
     def call(self, input_tensor, training=False):
-        """gnn_layers.py:384-413 (the sub-layers are called without `training`, as there)."""
-        x = self.layer1(input_tensor)
+        """gnn_layers.py:384-413.  The reference calls its sub-layers without an explicit `training` (:391, :398); in
+        tf.keras a layer called inside another layer's `call` inherits the training flag of the enclosing call context,
+        so a sub-layer built with use_bn=True trains its BatchNormalization when the residual layer is trained — the
+        flag is passed on explicitly here."""
+        x = self.layer1(input_tensor, training=training)
         if self.use_bn:
             x = self._norm(self.bn1, x, training)
-        x = self.layer2(x)
+        x = self.layer2(x, training=training)
         if self.use_bn:
             x = self._norm(self.bn2, x, training)
         if self.activation is None:

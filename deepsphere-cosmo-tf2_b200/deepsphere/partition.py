@@ -24,6 +24,42 @@ from scipy import sparse
 from .distributed import shard_range
 
 
+class _Timing:
+    """Optional device-side timing of the exchanges (bench.py: time split of a partitioned training step).  When
+    `enabled`, every halo exchange (forward and transposed) is bracketed by CUDA events on the current stream."""
+
+    enabled = False
+    events = []
+
+    @classmethod
+    def start(cls):
+        cls.enabled, cls.events = True, []
+
+    @classmethod
+    def stop(cls):
+        """Total milliseconds spent between the recorded event pairs (call after a device synchronisation)."""
+        cls.enabled = False
+        ms = sum(a.elapsed_time(b) for a, b in cls.events)
+        n = len(cls.events)
+        cls.events = []
+        return ms, n
+
+
+class _timed:
+    def __enter__(self):
+        if _Timing.enabled and torch.cuda.is_available():
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        else:
+            self.a = None
+
+    def __exit__(self, *exc):
+        if self.a is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            _Timing.events.append((self.a, b))
+
+
 def _closure(pattern, rows, n_hops):
     """Rows within n_hops of `rows` in the graph of the (structurally symmetric) sparse `pattern`."""
     M = pattern.shape[0]
@@ -82,6 +118,16 @@ class HaloPlan:
         self.own_start = int(self.own_pos[0]) if self.n_own else 0
         assert self.n_own == 0 or np.array_equal(self.own_pos, self.own_start + np.arange(self.n_own))
         self._dev = {}
+        # the C-ABI kernels (ds_halo_pack / _assemble / _reduce) take the row lists of ALL peers concatenated, so that
+        # one launch serves every peer: the send buffer is [sum_q n_q, B, F] with peer q's block contiguous
+        self.send_cat = np.concatenate(self.send_rows).astype(np.int32)
+        self.recv_cat = np.concatenate(self.recv_pos).astype(np.int32)
+        # transposed exchange: own row r receives the slots of the returned buffer listed in slots[ptr[r]:ptr[r+1]]
+        # (ascending slot = ascending peer: a fixed summation order)
+        order = np.argsort(self.send_cat, kind="stable").astype(np.int32)
+        counts = np.bincount(self.send_cat, minlength=self.n_own) if len(self.send_cat) else np.zeros(self.n_own, np.int64)
+        self.reduce_ptr = np.concatenate(([0], np.cumsum(counts))).astype(np.int32)
+        self.reduce_slots = order
 
     def on(self, device):
         """Index tensors of the exchange, resident on `device` (uploaded once)."""
@@ -89,6 +135,14 @@ class HaloPlan:
         if key not in self._dev:
             self._dev[key] = ([torch.as_tensor(v, device=device) for v in self.send_rows],
                               [torch.as_tensor(v, device=device) for v in self.recv_pos])
+        return self._dev[key]
+
+    def native(self, device):
+        """int32 device tensors of the C-ABI halo kernels: (send_cat, recv_cat, reduce_ptr, reduce_slots)."""
+        key = "native:" + str(device)
+        if key not in self._dev:
+            self._dev[key] = tuple(torch.as_tensor(v, dtype=torch.int32, device=device)
+                                   for v in (self.send_cat, self.recv_cat, self.reduce_ptr, self.reduce_slots))
         return self._dev[key]
 
     def restrict(self, L):
@@ -109,8 +163,15 @@ class _HaloExchange(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_ext):
         plan, group = ctx.plan, ctx.group
+        with _timed():
+            return _HaloExchange._backward(g_ext, plan, group)
+
+    @staticmethod
+    def _backward(g_ext, plan, group):
         g_ext = g_ext.contiguous()
         B, _, F = g_ext.shape
+        if g_ext.is_cuda:  # C-ABI kernels: one pack launch, the all-to-all, one reduce launch
+            return _native_exchange_backward(g_ext, plan, group), None, None
         send_idx, recv_idx = plan.on(g_ext.device)
         g_own = g_ext[:, plan.own_start: plan.own_start + plan.n_own, :].clone()
         # send back what I received (halo positions), receive what I sent (own rows) and accumulate
@@ -138,10 +199,55 @@ def _all_to_all(flat, counts_out, counts_in, group):
 
 
 def _exchange(x_own, plan, group):
+    with _timed():
+        return _exchange_impl(x_own, plan, group)
+
+
+def _native_exchange(x_own, plan, group):
+    """The exchange on CUDA tensors through libdeepsphere_b200.so: ds_halo_pack -> all_to_all -> ds_halo_assemble."""
+    from . import _native as nat
+
+    B, n_own, F = x_own.shape
+    send_cat, recv_cat, _, _ = plan.native(x_own.device)
+    n_send, n_recv = len(plan.send_cat), len(plan.recv_cat)
+    st = nat.current_stream()
+    send = x_own.new_empty(n_send * B * F)
+    nat.check(nat.lib().ds_halo_pack(B, n_own, F, n_send, nat.ptr(send_cat), nat.ptr(x_own), nat.ptr(send), st), "ds_halo_pack")
+    counts_out = [len(plan.send_rows[q]) * B * F for q in range(plan.world)]
+    counts_in = [len(plan.recv_pos[q]) * B * F for q in range(plan.world)]
+    recv = _all_to_all(send, counts_out, counts_in, group)
+    x_ext = x_own.new_empty((B, plan.n_ext, F))
+    nat.check(nat.lib().ds_halo_assemble(B, n_own, plan.n_ext, plan.own_start, F, n_recv, nat.ptr(recv_cat), nat.ptr(x_own),
+                                         nat.ptr(recv), nat.ptr(x_ext), st), "ds_halo_assemble")
+    return x_ext
+
+
+def _native_exchange_backward(g_ext, plan, group):
+    from . import _native as nat
+
+    B, n_ext, F = g_ext.shape
+    _, recv_cat, red_ptr, red_slots = plan.native(g_ext.device)
+    n_send, n_recv = len(plan.send_cat), len(plan.recv_cat)
+    st = nat.current_stream()
+    back = g_ext.new_empty(n_recv * B * F)  # what I received in the forward goes back to its owners
+    nat.check(nat.lib().ds_halo_pack(B, n_ext, F, n_recv, nat.ptr(recv_cat), nat.ptr(g_ext), nat.ptr(back), st), "ds_halo_pack")
+    counts_out = [len(plan.recv_pos[q]) * B * F for q in range(plan.world)]
+    counts_in = [len(plan.send_rows[q]) * B * F for q in range(plan.world)]
+    got = _all_to_all(back, counts_out, counts_in, group)
+    g_own = g_ext.new_empty((B, plan.n_own, F))
+    nat.check(nat.lib().ds_halo_reduce(B, plan.n_own, n_ext, plan.own_start, F, nat.ptr(red_ptr) if n_send else None,
+                                       nat.ptr(red_slots) if n_send else None, nat.ptr(g_ext), nat.ptr(got),
+                                       nat.ptr(g_own), st), "ds_halo_reduce")
+    return g_own
+
+
+def _exchange_impl(x_own, plan, group):
     x_own = x_own.contiguous()
     B, n_own, F = x_own.shape
     if n_own != plan.n_own:
         raise ValueError(f"rank {plan.rank} owns {plan.n_own} rows, got a tensor with {n_own}")
+    if x_own.is_cuda:
+        return _native_exchange(x_own, plan, group)
     send_idx, recv_idx = plan.on(x_own.device)
     x_ext = x_own.new_empty((B, plan.n_ext, F))
     x_ext[:, plan.own_start: plan.own_start + n_own, :] = x_own
@@ -180,6 +286,11 @@ class PartitionedGraphConv(torch.nn.Module):
         self.group = group
         self.plan = HaloPlan(L, n_hops, rank, world, align)
         self.layer = make_layer(self.plan.restrict(L), self.plan.ext)
+        if getattr(self.layer, "use_bn", False):
+            # BatchNormalization inside the layer (gnn_layers.py:53,152-153): statistics over the OWN rows of every rank,
+            # summed over the group = the statistics of the whole sphere; halo rows carry no gradient (ds_bn_* row range)
+            self.layer._bn_rows = (self.plan.own_start, self.plan.own_start + self.plan.n_own)
+            self.layer._bn_sync = True if group is None else group
 
     def forward(self, x_own, *args, **kwargs):
         x_ext = halo_exchange(x_own, self.plan, self.group)
@@ -225,7 +336,8 @@ class PartitionedHealpyGCNN(torch.nn.Module):
     head; whatever follows it (Dense, ...) sees replicated tensors.  All ranks must construct the model with the same
     torch seed (or broadcast the parameters), feed the SAME batch restricted to their rows, and sum the weight
     gradients over the group after backward (`allreduce_gradients(params, average=False)`).
-    Not supported: use_bn inside graph layers (statistics would need the own-row mask), residual layers."""
+    use_bn inside graph layers: the statistics are those of the whole sphere (own rows of every rank, one all-reduce of
+    2F + 1 doubles per direction).  Not supported: residual layers."""
 
     def __init__(self, nside, indices, layers, n_neighbors=8, rank=None, world=None, group=None):
         super().__init__()
@@ -264,8 +376,6 @@ class PartitionedHealpyGCNN(torch.nn.Module):
         cur_nside, cur_idx, cur_align = int(nside), idx, align
         for layer in layers:
             if isinstance(layer, (hp_nn.HealpyChebyshev, hp_nn.HealpyMonomial, hp_nn.HealpyBernstein)):
-                if layer.use_bn:
-                    raise NotImplementedError("use_bn inside a partitioned graph layer")
                 sphere = SphereHealpix(subdivisions=cur_nside, indexes=cur_idx, nest=True, k=n_neighbors,
                                        lap_type="normalized")
                 L = sphere.L

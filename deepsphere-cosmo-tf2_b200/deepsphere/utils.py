@@ -55,8 +55,15 @@ def largest_eigenvalue(L, tol=1e-9, maxit=20000, min_size=4096):
 
     from scipy.sparse.linalg import eigsh
 
+    key = None
+    if L.shape[0] >= min_size and os.environ.get("DEEPSPHERE_LMAX", "").lower() not in ("arpack", "nocache"):
+        key = matrix_fingerprint(L)
+        hit = _lmax_lookup(key)
+        if hit is not None:
+            return hit
+
     def arpack():
-        return float(eigsh(L, k=1, which="LM", return_eigenvectors=False)[0])
+        return _lmax_store(key, float(eigsh(L, k=1, which="LM", return_eigenvectors=False)[0]))
 
     M = L.shape[0]
     if M < min_size or os.environ.get("DEEPSPHERE_LMAX", "").lower() == "arpack":
@@ -68,7 +75,85 @@ def largest_eigenvalue(L, tol=1e-9, maxit=20000, min_size=4096):
     if asym.nnz and asym.max() > 1e-12 * max(abs(L).max(), 1e-300):
         return arpack()
     theta = _lanczos_extreme(lambda v: L @ v, M, tol, min(maxit, M))
-    return arpack() if theta is None else theta
+    return arpack() if theta is None else _lmax_store(key, theta)
+
+
+# ---- memo of largest eigenvalues -----------------------------------------------------------------------------------
+# The same Laplacians come back again and again: every graph layer of a network level, every rank of a sphere-partitioned
+# model, every process of a benchmark.  Values are keyed by a fingerprint of the matrix CONTENT (never by nside / k), so
+# a changed graph builder simply misses.  Three tiers: in-process dict, the table shipped with the package
+# (_lmax_table.json: the full-sphere HEALPix graphs of graph.SphereHealpix, written by tools/make_lmax_table.py with
+# this very function), and an optional directory DEEPSPHERE_CACHE_DIR shared by the processes of one box.
+_LMAX_MEMO = {}
+_LMAX_TABLE = None
+
+
+def matrix_fingerprint(L):
+    """Content fingerprint of a sparse matrix: shape, nnz, sum of |values| and of squares (both well conditioned; 10
+    significant digits, so that a different summation order on another CPU gives the same key) and strided checksums
+    of the column indices and row pointers."""
+    L = sparse.csr_matrix(L)
+    if not L.has_canonical_format:
+        L = L.copy()
+        L.sum_duplicates()
+    d = np.asarray(L.data, dtype=np.float64)
+    step = max(1, L.nnz // 4096)
+    return (f"{L.shape[0]}x{L.shape[1]}:{L.nnz}:{float(np.abs(d).sum()):.9e}:{float((d * d).sum()):.9e}:"
+            f"{int(np.asarray(L.indices[::step], dtype=np.int64).sum())}:{int(L.indptr[:: max(1, L.shape[0] // 1024)].sum())}")
+
+
+def _lmax_lookup(key):
+    global _LMAX_TABLE
+    import json
+    import os
+
+    if key in _LMAX_MEMO:
+        return _LMAX_MEMO[key]
+    if _LMAX_TABLE is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lmax_table.json")
+        try:
+            with open(path) as f:
+                _LMAX_TABLE = json.load(f)
+        except (OSError, ValueError):
+            _LMAX_TABLE = {}
+    if key in _LMAX_TABLE:
+        _LMAX_MEMO[key] = float(_LMAX_TABLE[key])
+        return _LMAX_MEMO[key]
+    cdir = os.environ.get("DEEPSPHERE_CACHE_DIR")
+    if cdir:
+        import hashlib
+
+        path = os.path.join(cdir, "lmax_" + hashlib.sha1(key.encode()).hexdigest() + ".txt")
+        try:
+            with open(path) as f:
+                k2, v = f.read().split("\n")[:2]
+            if k2 == key:
+                _LMAX_MEMO[key] = float(v)
+                return _LMAX_MEMO[key]
+        except (OSError, ValueError):
+            pass
+    return None
+
+
+def _lmax_store(key, value):
+    import os
+
+    if key is not None:
+        _LMAX_MEMO[key] = float(value)
+        cdir = os.environ.get("DEEPSPHERE_CACHE_DIR")
+        if cdir:
+            import hashlib
+
+            try:
+                os.makedirs(cdir, exist_ok=True)
+                path = os.path.join(cdir, "lmax_" + hashlib.sha1(key.encode()).hexdigest() + ".txt")
+                tmp = f"{path}.{os.getpid()}"
+                with open(tmp, "w") as f:
+                    f.write(f"{key}\n{float(value)!r}\n")
+                os.replace(tmp, path)
+            except OSError:
+                pass
+    return float(value)
 
 
 def _lanczos_extreme(matvec, M, tol, maxit):

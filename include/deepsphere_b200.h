@@ -173,6 +173,48 @@ int ds_pconvT_backward(int64_t B, int64_t M, int64_t Fin, int64_t Fout, int32_t 
                        const float* y, const float* dy, int32_t act, float* dx, float* dw, float* dbias,
                        float* workspace, int32_t mode, void* stream);
 
+/* ---- BatchNormalization + bias + activation around the contraction (gnn_layers.py:53,152-159) --------------------
+ * tf.keras.layers.BatchNormalization(axis=-1, momentum, epsilon, center=False, scale=False) over the channel axis of
+ * z [B, M, F], then `+ bias`, then the activation.  Statistics over rows r0 <= m < r1 of every sample (the whole
+ * tensor: r0 = 0, r1 = M; a sphere-partitioned layer passes its OWN rows: the halo rows are normalised with the same
+ * statistics and receive no gradient).  `sums` = double[2F] (sum z | sum z^2, or sum g | sum g*zhat in the backward):
+ * a multi-GPU caller all-reduces them (and `count` = rows contributing) between the two calls of a direction, which is
+ * the whole of synchronised BatchNorm.  `workspace` = ds_bn_workspace_doubles(B, M, F) doubles.
+ *   forward   ds_bn_stats -> [all-reduce] -> ds_bn_bias_act_forward: updates moving_mean / moving_var [F] in place
+ *             (training), writes mean_rstd [2F] (saved for the backward), scale_shift [2F] (scratch) and
+ *             y = act((z - mean) * rstd + bias);  training == 0 uses the moving statistics (sums may be NULL).
+ *   backward  ds_bn_backward_stats -> [all-reduce] -> ds_bn_backward_apply: dz [B, M, F] and dbias [F] (nullable). */
+int64_t ds_bn_workspace_doubles(int64_t B, int64_t M, int64_t F);
+int ds_bn_stats(int64_t B, int64_t M, int64_t F, int64_t r0, int64_t r1, const float* z, double* sums, double* workspace,
+                void* stream);
+int ds_bn_bias_act_forward(int64_t B, int64_t M, int64_t F, const float* z, const double* sums, double count,
+                           const double* count_dev /* nullable: device scalar overriding `count` (after an all-reduce) */,
+                           float eps, float momentum, int32_t training, float* moving_mean, float* moving_var,
+                           const float* bias /* nullable */, int32_t act, float* mean_rstd, float* scale_shift, float* y,
+                           void* stream);
+int ds_bn_backward_stats(int64_t B, int64_t M, int64_t F, int64_t r0, int64_t r1, const float* z, const float* y,
+                         const float* dy, const float* mean_rstd, int32_t act, double* sums, double* workspace,
+                         void* stream);
+int ds_bn_backward_apply(int64_t B, int64_t M, int64_t F, int64_t r0, int64_t r1, const float* z, const float* y,
+                         const float* dy, const float* mean_rstd, const double* sums, double count,
+                         const double* count_dev /* nullable */, int32_t act, int32_t training, float* dz,
+                         float* dbias /* nullable */, void* stream);
+
+/* ---- sphere partition: halo rows around the all-to-all (the reference is single-device, these are the
+ * device halves of the exchange a multi-GPU binder adds around Chebyshev.call, gnn_layers.py:130-161) -----------------
+ * ds_halo_pack:     send[j, b, :] = x[b, rows[j], :], j < n.  The caller concatenates the row lists of all peers, so
+ *                   each peer's block of `send` is contiguous ([rows, B, F]) and one launch packs every peer.
+ * ds_halo_assemble: x_ext [B, n_ext, F]: rows own_start .. own_start+n_own-1 = x_own, row pos[j] = recv[j, b, :].
+ * ds_halo_reduce:   transposed exchange (backward): g_own[b, r, :] = g_ext[b, own_start + r, :] + sum over
+ *                   s in slots[row_slot_ptr[r] .. row_slot_ptr[r+1]) of recv[s, b, :]   (fixed order: reproducible).
+ *                   row_slot_ptr == NULL: no contributions (copy of the own slab). */
+int ds_halo_pack(int64_t B, int64_t n_src, int64_t F, int64_t n, const int32_t* rows, const float* src, float* dst,
+                 void* stream);
+int ds_halo_assemble(int64_t B, int64_t n_own, int64_t n_ext, int64_t own_start, int64_t F, int64_t n_halo,
+                     const int32_t* pos, const float* x_own, const float* recv, float* x_ext, void* stream);
+int ds_halo_reduce(int64_t B, int64_t n_own, int64_t n_ext, int64_t own_start, int64_t F, const int32_t* row_slot_ptr,
+                   const int32_t* slots, const float* g_ext, const float* recv, float* g_own, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

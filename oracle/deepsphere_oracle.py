@@ -423,3 +423,76 @@ def torch_cpu_bernstein(x, Lt, kernel, K):
         stack.append(x3)
     X = torch.stack(stack, dim=0).reshape(K + 1, M, Fin, N).permute(3, 1, 2, 0).reshape(N * M, Fin * (K + 1))
     return (X @ kernel).reshape(N, M, -1)
+
+
+def torch_cpu_layer(x, Lt, kernel, K, recursion="chebyshev", bias=None, activation=None, use_bn=False, training=False,
+                    moving_mean=None, moving_var=None, eps=1e-5):
+    """A whole Chebyshev / Monomial layer (gnn_layers.py:130-161: contraction -> BatchNormalization(center=False,
+    scale=False) -> + bias -> activation) with differentiable torch CPU ops in x's dtype."""
+    import torch
+
+    z = torch_cpu_graph_conv(x, Lt, kernel, K, recursion)
+    if use_bn:
+        if training:
+            mean, var = z.mean(dim=(0, 1)), z.var(dim=(0, 1), unbiased=False)
+        else:
+            F = z.shape[-1]
+            mean = torch.zeros(F, dtype=z.dtype) if moving_mean is None else moving_mean
+            var = torch.ones(F, dtype=z.dtype) if moving_var is None else moving_var
+        z = (z - mean) / torch.sqrt(var + eps)
+    if bias is not None:
+        z = z + bias
+    return _torch_act(activation)(z)
+
+
+def _torch_act(name):
+    import torch
+
+    if name is None or name == "linear":
+        return lambda v: v
+    if callable(name):
+        return name
+    return {"relu": torch.relu, "elu": torch.nn.functional.elu, "sigmoid": torch.sigmoid, "tanh": torch.tanh,
+            "softplus": torch.nn.functional.softplus}[name]
+
+
+def torch_cpu_residual(x, Lt, kernels, K, recursion="chebyshev", layer_activation=None, layer_biases=(None, None),
+                       layer_use_bn=False, activation=None, act_before=False, use_bn=False, norm_type="batch_norm",
+                       alpha=1.0, training=False, eps_bn=1e-3, eps_ln=1e-3, ln_axis=-1):
+    """GCNN_ResidualLayer.call (gnn_layers.py:384-413): in -> layer1 -> [norm] -> layer2 -> [norm] -> skip.
+
+    Both sub-layers are built from the same ``layer_kwargs`` (gnn_layers.py:365-370) and are called WITHOUT an explicit
+    ``training`` argument (:391, :398); inside a Keras model call the training flag of the enclosing call context
+    propagates to them, so a sub-layer's own BatchNormalization (``use_bn`` in layer_kwargs) follows ``training`` too.
+    The norms between the layers are Keras defaults (``BatchNormalization(axis=-1)``: momentum 0.99, epsilon 1e-3, learned
+    gamma = 1 / beta = 0 at initialisation; ``LayerNormalization(axis=...)``: epsilon 1e-3) — evaluated here at their
+    initial affine parameters.  Without an activation the skip is ``x + in`` (alpha ignored, :407-408)."""
+    import torch
+
+    def norm(z):
+        if norm_type == "batch_norm":
+            if training:
+                mean, var = z.mean(dim=(0, 1)), z.var(dim=(0, 1), unbiased=False)
+            else:
+                mean, var = torch.zeros(z.shape[-1], dtype=z.dtype), torch.ones(z.shape[-1], dtype=z.dtype)
+            return (z - mean) / torch.sqrt(var + eps_bn)
+        axes = ln_axis if isinstance(ln_axis, (tuple, list)) else (ln_axis,)
+        axes = tuple(a % z.dim() for a in axes)
+        mean = z.mean(dim=axes, keepdim=True)
+        var = z.var(dim=axes, unbiased=False, keepdim=True)
+        return (z - mean) / torch.sqrt(var + eps_ln)
+
+    h = torch_cpu_layer(x, Lt, kernels[0], K, recursion, bias=layer_biases[0], activation=layer_activation,
+                        use_bn=layer_use_bn, training=training)
+    if use_bn:
+        h = norm(h)
+    h = torch_cpu_layer(h, Lt, kernels[1], K, recursion, bias=layer_biases[1], activation=layer_activation,
+                        use_bn=layer_use_bn, training=training)
+    if use_bn:
+        h = norm(h)
+    if activation is None:
+        return h + x
+    act = _torch_act(activation)
+    if act_before:
+        return act(h) + alpha * x
+    return act(h + alpha * x)

@@ -66,6 +66,9 @@ int main(int argc, char** argv) {
   a.n_tiles = (int)n_tiles; a.pix = pix; a.w = w;
   a.B = B; a.M = M; a.F = (int)F; a.N = (int)N; a.b_split = (int)b_split; a.nsteps = (int)nsteps;
   a.wscale = cheb ? 2.f : 1.f;
+  a.wdiag = 0.f;  // C2_CDIAG builds: the diagonal of L~ is one scalar (ds_plan_attach_lattice checks it on the host)
+  for (size_t i = 0; i < (size_t)n_tiles * C2_P; ++i)
+    if (pix[i] >= 0) { a.wdiag = a.wscale * w[i * 9 + 8]; break; }
   a.dbg = nullptr; a.sleep_mma = 0; a.sleep_ld = 0;
   a.in0 = x;
   for (int s = 0; s < C2_H; ++s) a.out[s] = u[s];

@@ -14,31 +14,45 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = open(os.path.join(ROOT, "deepsphere-cosmo-tf2_b200", "csrc", "ds_lattice_conv2.cu")).read()
 
 
-def pos(j, c):
-    """float4 index inside a plane of lattice (row j, column c): one pad row above, columns de-interleaved mod 3."""
-    return (j + 1) * LW + (c % 3) * 8 + c // 3
+def pos(j, c, BC=3):
+    """float4 index inside a plane of lattice (row j, column c): one pad row above, the columns of the LW / BC blocks
+    de-interleaved (kernel: slot_of_col)."""
+    NB = LW // BC
+    return (j + 1) * LW + (c % BC) * NB + c // BC
 
 
 def test_layout_is_a_bijection_and_quarter_warps_are_contiguous():
-    p = np.array([[pos(j, c) for c in range(LW)] for j in range(LW)])
-    assert len(np.unique(p)) == LW * LW and p.min() == LW and p.max() == (LW + 1) * LW - 1
-    # the 8 column blocks cb = 0..7 of one block row and one in-block column cc are 8 consecutive positions
-    for j in range(LW):
-        for cc in range(3):
-            q = [pos(j, 3 * cb + cc) for cb in range(8)]
-            assert q == list(range(q[0], q[0] + 8))
+    for BC in (3, 6):
+        NB = LW // BC
+        p = np.array([[pos(j, c, BC) for c in range(LW)] for j in range(LW)])
+        assert len(np.unique(p)) == LW * LW and p.min() == LW and p.max() == (LW + 1) * LW - 1
+        # the column blocks cb = 0..NB-1 of one block row and one in-block column cc are NB consecutive positions
+        for j in range(LW):
+            for cc in range(BC):
+                q = [pos(j, BC * cb + cc, BC) for cb in range(NB)]
+                assert q == list(range(q[0], q[0] + NB))
+        # the inverse map the epilogue and the gather warps use (kernel: col_of_slot)
+        for slot in range(LW):
+            c = (slot % NB) * BC + slot // NB
+            assert pos(0, c, BC) == LW + slot
+    assert "return (c % C2_BC) * C2_NB + c / C2_BC;" in SRC and "return (p % C2_NB) * C2_BC + p / C2_NB;" in SRC
 
 
 def test_perimeter_offsets_of_a_block():
-    """Columns -1, 0, 1, 2, 3 relative to the block's column 0 sit at +15, +0, +8, +16, +1 (kernel constant CO)."""
-    co = [int(v) for v in re.search(r"constexpr int CO\[5\] = \{([^}]*)\}", SRC).group(1).split(",")]
-    assert co == [15, 0, 8, 16, 1]
-    for cb in range(1, 7):  # interior column blocks: all five columns exist
-        base = pos(5, 3 * cb)
-        for k, dc in enumerate(range(-1, 4)):
-            assert pos(5, 3 * cb + dc) == base + co[k]
-    # the wrap-around of the outermost blocks stays inside the row (only ever feeds don't-care ring positions)
-    assert pos(5, 0) + 15 == pos(5, 22) and pos(5, 21) + 1 == pos(5, 1)
+    """Columns -1, 0, .., BC relative to the block's column 0 sit at (BC-1) NB - 1, 0, NB, .., (BC-1) NB, +1 (kernel
+    lambda `co`); 3-column blocks: +15, +0, +8, +16, +1."""
+    assert "return k == 0 ? (C2_BC - 1) * C2_NB - 1 : (k == C2_BC + 1 ? 1 : (k - 1) * C2_NB);" in SRC
+    for BC in (3, 6):
+        NB = LW // BC
+        co = [(BC - 1) * NB - 1 if k == 0 else (1 if k == BC + 1 else (k - 1) * NB) for k in range(BC + 2)]
+        if BC == 3:
+            assert co == [15, 0, 8, 16, 1]
+        for cb in range(1, NB - 1):  # interior column blocks: all columns exist
+            base = pos(5, BC * cb, BC)
+            for k, dc in enumerate(range(-1, BC + 1)):
+                assert pos(5, BC * cb + dc, BC) == base + co[k]
+        # the wrap-around of the outermost blocks stays inside the row (only ever feeds don't-care ring positions)
+        assert LW <= pos(0, 0, BC) + co[0] < 2 * LW and LW <= pos(0, LW - BC, BC) + 1 < 2 * LW + 1
 
 
 def test_operand_rows_map_back_to_lattice_positions():

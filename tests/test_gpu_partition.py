@@ -146,3 +146,58 @@ def test_partitioned_healpy_gcnn_two_gpus(tmp_path):
     for r in (0, 1):
         errs = np.load(tmp_path / f"net{r}.npy")
         assert errs.max() <= 5e-3, errs
+
+
+@pytest.mark.parametrize("F", [1, 5, 16])
+def test_halo_kernels_single_gpu_simulated_ranks(F):
+    """ds_halo_pack / ds_halo_assemble / ds_halo_reduce (include/deepsphere_b200.h) on ONE GPU: the 3 ranks of a
+    partition are simulated in-process (the all-to-all is a slice copy), so the C-ABI kernels are checked on every box:
+    forward == the global tensor restricted to ext (bit-exact: pure data movement), backward == the transposed exchange."""
+    from deepsphere import _native as nat
+    from deepsphere.graph import SphereHealpix
+    from deepsphere.partition import HaloPlan
+
+    g = SphereHealpix(16, k=8)
+    M, world, B = g.L.shape[0], 3, 2
+    plans = [HaloPlan(g.L, 4, r, world, align=M // 48) for r in range(world)]
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(B, M, F, device=dev, generator=gen)
+    st = nat.current_stream()
+    lib = nat.lib()
+    sends = []
+    for p in plans:
+        b0, e0 = p.own[p.rank]
+        x_own = x[:, b0:e0].contiguous()
+        send_cat = p.native(dev)[0]
+        buf = torch.empty(len(p.send_cat), B, F, device=dev)
+        nat.check(lib.ds_halo_pack(B, e0 - b0, F, len(p.send_cat), nat.ptr(send_cat), nat.ptr(x_own), nat.ptr(buf), st))
+        sends.append(buf)
+    offs = [np.concatenate(([0], np.cumsum([len(v) for v in p.send_rows]))) for p in plans]
+    roffs = [np.concatenate(([0], np.cumsum([len(v) for v in p.recv_pos]))) for p in plans]
+    g_exts, backs = [], []
+    for r, p in enumerate(plans):
+        recv = torch.cat([sends[q][offs[q][r]: offs[q][r + 1]] for q in range(world)]).contiguous()
+        b0, e0 = p.own[r]
+        x_own = x[:, b0:e0].contiguous()
+        x_ext = torch.full((B, p.n_ext, F), float("nan"), device=dev)
+        nat.check(lib.ds_halo_assemble(B, p.n_own, p.n_ext, p.own_start, F, len(p.recv_cat), nat.ptr(p.native(dev)[1]),
+                                       nat.ptr(x_own), nat.ptr(recv), nat.ptr(x_ext), st))
+        assert torch.equal(x_ext, x[:, torch.as_tensor(p.ext, device=dev)])
+        ge = torch.randn(B, p.n_ext, F, device=dev, generator=gen)
+        g_exts.append(ge)
+        back = torch.empty(len(p.recv_cat), B, F, device=dev)
+        nat.check(lib.ds_halo_pack(B, p.n_ext, F, len(p.recv_cat), nat.ptr(p.native(dev)[1]), nat.ptr(ge), nat.ptr(back), st))
+        backs.append(back)
+    g_global = torch.zeros(B, M, F, device=dev, dtype=torch.float64)
+    for p, ge in zip(plans, g_exts):
+        g_global.index_add_(1, torch.as_tensor(p.ext, device=dev), ge.double())
+    for r, p in enumerate(plans):
+        got = torch.cat([backs[q][roffs[q][r]: roffs[q][r + 1]] for q in range(world)]).contiguous()
+        b0, e0 = p.own[r]
+        g_own = torch.empty(B, p.n_own, F, device=dev)
+        _, _, red_ptr, red_slots = p.native(dev)
+        nat.check(lib.ds_halo_reduce(B, p.n_own, p.n_ext, p.own_start, F, nat.ptr(red_ptr), nat.ptr(red_slots),
+                                     nat.ptr(g_exts[r]), nat.ptr(got), nat.ptr(g_own), st))
+        torch.cuda.synchronize()
+        assert float((g_own.double() - g_global[:, b0:e0]).abs().max()) <= 1e-5 * float(g_global.abs().max())

@@ -200,3 +200,49 @@ def test_partitioned_healpy_gcnn_equals_single_process(tmp_path, world, masked):
         errs = np.load(tmp_path / f"net{r}.npy")
         assert errs[:-1].max() <= 1e-5, errs
         assert errs[-1] > 0  # every rank really has a halo
+
+
+def test_native_halo_lists_reproduce_the_exchange_and_its_transpose():
+    """The concatenated row lists and the row -> slot CSR that the C-ABI halo kernels take (ds_halo_pack / _assemble /
+    _reduce, include/deepsphere_b200.h), evaluated here with numpy on every rank of a 3-way partition with the
+    all-to-all simulated in-process: forward == the global tensor restricted to ext, backward == the transposed
+    exchange (every rank's g_ext scattered to the global rows and summed, restricted to the own rows)."""
+    from deepsphere.graph import SphereHealpix
+    from deepsphere.partition import HaloPlan
+
+    g = SphereHealpix(8, k=8)
+    M, world, B, F = g.L.shape[0], 3, 2, 3
+    plans = [HaloPlan(g.L, 3, r, world, align=M // 48) for r in range(world)]
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((B, M, F))
+    sends = []
+    for p in plans:
+        b0, e0 = p.own[p.rank]
+        x_own = x[:, b0:e0]
+        sends.append(np.transpose(x_own[:, p.send_cat], (1, 0, 2)))  # ds_halo_pack: [n, B, F], peer blocks contiguous
+    offs = [np.concatenate(([0], np.cumsum([len(v) for v in p.send_rows]))) for p in plans]
+    g_ext_all, backs = [], []
+    for r, p in enumerate(plans):
+        recv = np.concatenate([sends[q][offs[q][r]: offs[q][r + 1]] for q in range(world)])  # all_to_all
+        assert len(recv) == len(p.recv_cat)
+        b0, e0 = p.own[r]
+        x_ext = np.full((B, p.n_ext, F), np.nan)
+        x_ext[:, p.own_start: p.own_start + p.n_own] = x[:, b0:e0]          # ds_halo_assemble
+        x_ext[:, p.recv_cat] = np.transpose(recv, (1, 0, 2))
+        assert np.array_equal(x_ext, x[:, p.ext])
+        ge = rng.standard_normal((B, p.n_ext, F))
+        g_ext_all.append(ge)
+        backs.append(np.transpose(ge[:, p.recv_cat], (1, 0, 2)))            # ds_halo_pack on g_ext with recv_cat
+    g_global = np.zeros((B, M, F))
+    for p, ge in zip(plans, g_ext_all):
+        np.add.at(g_global, (slice(None), p.ext), ge)
+    roffs = [np.concatenate(([0], np.cumsum([len(v) for v in p.recv_pos]))) for p in plans]
+    for r, p in enumerate(plans):
+        got = np.concatenate([backs[q][roffs[q][r]: roffs[q][r + 1]] for q in range(world)])  # transposed all_to_all
+        assert len(got) == len(p.send_cat)
+        b0, e0 = p.own[r]
+        g_own = g_ext_all[r][:, p.own_start: p.own_start + p.n_own].copy()   # ds_halo_reduce
+        for row in range(p.n_own):
+            for s in p.reduce_slots[p.reduce_ptr[row]: p.reduce_ptr[row + 1]]:
+                g_own[:, row] += got[s]
+        assert np.allclose(g_own, g_global[:, b0:e0], rtol=0, atol=1e-12)

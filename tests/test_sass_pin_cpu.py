@@ -1,5 +1,7 @@
-"""The device code of the fused lattice convolution kernel is pinned: the SASS of the DEFAULT build (all experiment switches
-off) must stay what was measured and parity-tested on the B200 in round 1 (commit e8f944c, profiles/r1k_*).  The kernel
+"""The device code of the fused lattice convolution kernel is pinned: the SASS of the DEFAULT build must stay what was
+measured and parity-tested on the B200 (round 2, GPU call r2c: the build with the timeline probe compiled out, 27 fused-kernel
+parity tests green, 14.3 ms forward / 41.0 ms forward + backward at the bench configuration; the object file of that run
+and the default build of this commit have the same digest).  The kernel
 file carries compile-time variants and host-emulation seams; this test is what lets them be edited without a GPU — an edit
 that changes the default code generation fails here and has to be re-verified on the GPU before the pin moves.
 (Function names carry a hash of the source path; they are normalised away.)"""
@@ -15,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "deepsphere-cosmo-tf2_b200", "csrc", "ds_lattice_conv2.cu")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CUOBJDUMP = os.path.join(os.path.dirname(NVCC), "cuobjdump")
-PINNED = "5fcb63f4a8e384bf0202701e5a4e1069"
+PINNED = "3d698f0ae6a96f892f8810ae7f65c7f4"
 
 
 def sass_digest(obj):
