@@ -48,6 +48,11 @@ def parse():
     ap.add_argument("--no-experimental", action="store_true")
     ap.add_argument("--model-graph", action="store_true",
                     help="with --model-only: capture the training step in a CUDA graph and time graph replays")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the named configurations C1 (quick_start), C3 (masked survey nside 512), C4 (autoencoder)")
+    ap.add_argument("--experimental", action="store_true",
+                    help="also time the HealpyGCNN step with the opt-in switches (child processes)")
+    ap.add_argument("--no-graph", action="store_true", help="do not try CUDA-graph replays of the model training steps")
     ap.add_argument("--no-partitioned", action="store_true",
                     help="skip the nside-1024 sphere-partitioned HealpyGCNN (strong scaling over the ranks)")
     ap.add_argument("--part-nside", type=int, default=1024)
@@ -209,7 +214,7 @@ def model_train_bench(args, mode, device, world):
     dsd.broadcast_parameters(model)
     params = model.trainable_variables
     use_graph = bool(getattr(args, "model_graph", False))
-    opt = torch.optim.Adam(params, lr=1e-3, capturable=use_graph)
+    opt = torch.optim.Adam(params, lr=1e-3, capturable=True)
     gen = torch.Generator(device=device).manual_seed(11 + int(os.environ.get("RANK", "0")))
     x = torch.randn(Bm, npix, 1, device=device, generator=gen)
     t = torch.randn(Bm, 2, device=device, generator=gen)
@@ -224,17 +229,24 @@ def model_train_bench(args, mode, device, world):
 
     # fingerprint of the very first step (same seeds on every run): loss and per-parameter gradient norms before any
     # update - what an alternative kernel build must reproduce (bench.py --model-only, experimental_model_run)
-    opt.zero_grad(set_to_none=True)
-    loss0 = ((model(x, training=True) - t) ** 2).mean()
-    loss0.backward()
-    first_step = {"loss": float(loss0.detach()), "grad_norms": [float(p.grad.norm()) if p.grad is not None else 0.0 for p in params]}
+    def first():
+        opt.zero_grad(set_to_none=True)
+        loss0 = ((model(x, training=True) - t) ** 2).mean()
+        loss0.backward()
+        return {"loss": float(loss0.detach()),
+                "grad_norms": [float(p.grad.norm()) if p.grad is not None else 0.0 for p in params]}
+
     graph = None
     if use_graph:
         # whole-step capture (forward, backward, Adam): the C-ABI calls only enqueue work on the current stream and take
-        # their scratch memory from cudaMallocAsync, so the step is capturable; replays remove the host launch path
+        # their scratch memory from cudaMallocAsync, so the step is capturable; replays remove the host launch path.
+        # EVERY backward before the capture runs on a side stream: autograd ties a parameter's AccumulateGrad node to the
+        # stream of its first backward, and a node tied to the legacy default stream invalidates the capture (round 1's
+        # "cudaErrorStreamCaptureImplicit" - the fingerprint step ran on the default stream)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
+            first_step = first()
             for _ in range(3):
                 train_step()
         torch.cuda.current_stream().wait_stream(side)
@@ -245,6 +257,7 @@ def model_train_bench(args, mode, device, world):
             static_loss = train_step()
         run_step = lambda: (graph.replay(), static_loss)[1]  # noqa: E731
     else:
+        first_step = first()
         run_step = train_step
         for _ in range(3):
             train_step()
@@ -261,13 +274,89 @@ def model_train_bench(args, mode, device, world):
     torch.cuda.synchronize()
     ms = dsd.allreduce_max(a.elapsed_time(b) / n, device)
     n_params = int(sum(p.numel() for p in params))
+    final_loss = float(loss.detach())
+    del loss
+    # the same step as a CUDA-graph replay (counts only when validated against eager, see graph_replay_timing)
+    graph_t = None
+    eager_ms = ms
+    if not use_graph and not getattr(args, "no_graph", False):
+        graph_t = graph_replay_timing(train_step, params, opt, n, device, world)
+        if graph_t.get("validated"):
+            ms = graph_t["ms_per_step"]
     del graph, model, opt, x, t
     torch.cuda.empty_cache()
     return {"metric": "HealpyGCNN train maps/s", "value": world * Bm / (ms * 1e-3), "unit": "maps/s",
-            "ms_per_step": ms, "batch_per_gpu": Bm, "n_gpus": world, "parameters": n_params, "final_loss": float(loss.detach()),
+            "ms_per_step": ms, "batch_per_gpu": Bm, "n_gpus": world, "parameters": n_params, "final_loss": final_loss,
+            "execution": "CUDA graph replay of the whole step (validated against eager)" if ms != eager_ms else "eager",
+            "eager_ms_per_step": eager_ms, "cuda_graph": graph_t,
             "first_step": first_step,
             "config": f"nside {nside} full sphere ({npix} px): PseudoConv p1 F16 -> [Chebyshev K5 F32 + MAX pool] x3 -> "
                       f"Chebyshev K5 F64 -> AVG pool -> mean -> Dense(2); MSE, Adam, fwd+bwd+all-reduce+step, mode {mode}"}
+
+
+def graph_replay_timing(train_step, params, opt, n, device, world):
+    """Capture one whole training step (forward, backward, gradient collectives, Adam) in a CUDA graph and time replays.
+
+    The C-ABI calls only enqueue work on the current stream (scratch memory from cudaMallocAsync) and NCCL collectives are
+    capturable, so the step has no host-side dependency; a replay removes the Python / launch path that bounds the small
+    levels of a HealpyGCNN.  The number only counts when VALIDATED: from the same weights and optimizer state, 3 eager
+    steps and 3 replays must produce the same losses.  Returns a dict (never raises)."""
+    from deepsphere import distributed as dsd
+
+    try:
+        def snapshot():
+            st = []
+            for p in params:
+                s_ = opt.state.get(p, {})
+                st.append((p.detach().clone(), {k: v.detach().clone() for k, v in s_.items() if isinstance(v, torch.Tensor)}))
+            return st
+
+        def restore(st):
+            with torch.no_grad():
+                for p, (w, s_) in zip(params, st):
+                    p.copy_(w)
+                    for k, v in s_.items():
+                        opt.state[p][k].copy_(v)
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):   # warm-up on a side stream: no autograd node may be tied to the legacy stream
+            for _ in range(3):
+                train_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        state = snapshot()
+        eager_losses = [float(train_step().detach()) for _ in range(3)]
+        restore(state)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            static_loss = train_step()
+        restore(state)   # the capture itself does not run the step, but keep the comparison exact
+        replay_losses = []
+        for _ in range(3):
+            graph.replay()
+            replay_losses.append(float(static_loss.detach()))
+        rel = max(abs(a - b) / max(abs(a), 1e-12) for a, b in zip(eager_losses, replay_losses))
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            graph.replay()
+        b.record()
+        torch.cuda.synchronize()
+        ms = dsd.allreduce_max(a.elapsed_time(b) / n, device)
+        ok = dsd.allreduce_max(0.0 if rel <= 1e-4 else 1.0, device) == 0.0
+        out = {"ms_per_step": ms, "validated": bool(ok), "loss_rel_diff_vs_eager": rel, "eager_losses": eager_losses,
+               "replay_losses": replay_losses, "final_loss": float(static_loss.detach())}
+        del graph
+        return out
+    except Exception as exc:  # a failed capture must not take the eager measurement with it
+        return {"error": str(exc)[:300], "validated": False}
 
 
 def _c5_layers(mode, mean_layer):
@@ -281,6 +370,141 @@ def _c5_layers(mode, mean_layer):
         layers += [hl.HealpyChebyshev(K=5, Fout=32, **kw), hl.HealpyPool(p=1, pool_type="MAX")]
     layers += [hl.HealpyChebyshev(K=5, Fout=64, **kw), hl.HealpyPool(p=1, pool_type="AVG"), mean_layer, kc.Dense(2)]
     return layers
+
+
+def _step_bytes(model, x):
+    """Algorithmic bytes of one training step of a layer stack: every layer reads its input and writes its output in the
+    forward (in + out) and reads input + output gradient and writes the input gradient in the backward (2 in + out)."""
+    sizes = []
+    hooks = [l.register_forward_hook(lambda m, i, o: sizes.append((i[0].numel(), o.numel()))) for l in model.layers]
+    with torch.no_grad():
+        model(x, training=False)
+    for h in hooks:
+        h.remove()
+    return 4 * sum(3 * a + 2 * b for a, b in sizes)
+
+
+def named_config_bench(name, args, device, rank, world, hbm_peak):
+    """Training throughput of one of BASELINE.json's named configurations, batch sharded over the
+    ranks, next to the oracle's torch-CPU restatement of the same network on the host cores (bounded sample, forward +
+    backward) and the forward parity of the two on that sample.  Modes: the library default (fp32 contraction) - these
+    networks have 1 - 16 channels, their layers run on the generic ELL + tail / fp32 paths."""
+    import deepsphere
+    from deepsphere import distributed as dsd, example_networks as nets, healpix as hpx, utils
+    from oracle import bridge, deepsphere_oracle as orc
+
+    torch.manual_seed(11)
+    if name == "C1_quick_start":
+        nside, B, k = 64, 16, 20
+        idx = np.arange(12 * nside**2)
+        model = deepsphere.HealpyGCNN(nside=nside, indices=idx, layers=nets.quick_start_layers(), n_neighbors=k)
+        desc = "examples/quick_start.ipynb:118-127,197 as shipped: nside 64, K 10, F 5, BatchNorm, n_neighbors 20, batch 16/GPU"
+        loss_fn = lambda y, t: -(torch.log(y.clamp_min(1e-12)) * t).sum(dim=1).mean()  # sparse categorical cross-entropy
+        n_out = 2
+    elif name == "C3_masked_survey":
+        nside, B, k = 512, 8, 20
+        idx = utils.extend_indices(hpx.query_disc(nside, [1, 0, 0], 1.5), nside, 64)
+        model = deepsphere.HealpyGCNN(nside=nside, indices=idx, layers=nets.advanced_tutorial_layers(), n_neighbors=k)
+        desc = ("examples/advanced_tutorial.ipynb:137,211,309-325 scaled to nside 512 (BASELINE.json configs[2]): 1.48 M masked "
+                "pixels (query_disc 1.5 rad + extend_indices), Chebyshev / Monomial / residual K 10 F 5 with BatchNorm, "
+                "n_neighbors 20 (ELL + CSR tail path), batch 8/GPU")
+        loss_fn = lambda y, t: -(torch.log(y.clamp_min(1e-12)) * t).sum(dim=1).mean()
+        n_out = 2
+    elif name == "C4_autoencoder":
+        nside, B, k = 128, 5, 20
+        idx = np.arange(12 * nside**2)
+        enc_l, dec_l = nets.autoencoder_layers()
+        enc = deepsphere.HealpyGCNN(nside=nside, indices=idx, layers=enc_l, n_neighbors=k)
+        dec = deepsphere.HealpyGCNN(nside=nside // 8, indices=np.arange(12 * (nside // 8) ** 2), layers=dec_l, n_neighbors=k)
+        model = None
+        desc = ("examples/generative_models.ipynb:185-213,456 scaled to nside 128 (BASELINE.json configs[3]): pseudo-conv "
+                "encoder, Chebyshev K 5 F 16 + LayerNormalization(axis=1) + elu, transposed pseudo-conv decoder, "
+                "n_neighbors 20, MAE loss, batch 5/GPU")
+        loss_fn = None
+        n_out = None
+    else:
+        raise ValueError(name)
+    M = len(idx)
+    gen = torch.Generator(device=device).manual_seed(11 + rank)
+    x = torch.randn(B, M, 1, device=device, generator=gen)
+    if name == "C4_autoencoder":
+        enc.build(input_shape=(None, M, 1))
+        dec.build(input_shape=(None, M // 64, 16))
+        modules = [enc, dec]
+        fwd = lambda v, training: dec(enc(v, training=training), training=training)
+        step_loss = lambda: (fwd(x, True) - x).abs().mean()
+        layers_all = list(enc.layers) + list(dec.layers)
+    else:
+        model.build(input_shape=(None, M, 1))
+        modules = [model]
+        labels = torch.nn.functional.one_hot(torch.randint(0, n_out, (B,), device=device, generator=gen), n_out).float()
+        fwd = lambda v, training: model(v, training=training)
+        step_loss = lambda: loss_fn(fwd(x, True), labels)
+        layers_all = list(model.layers)
+    for m in modules:
+        m.to(device)
+        dsd.broadcast_parameters(m)
+    params = [p for m in modules for p in m.trainable_variables]
+    opt = torch.optim.Adam(params, lr=1e-3)
+
+    def train_step():
+        opt.zero_grad(set_to_none=True)
+        loss = step_loss()
+        loss.backward()
+        dsd.allreduce_gradients(params)
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        train_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+    n = max(3, min(args.steps, 10))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        loss = train_step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = dsd.allreduce_max(a.elapsed_time(b) / n, device)
+    nbytes = sum(_step_bytes(m, xi) for m, xi in zip(modules, [x] if len(modules) == 1 else
+                                                      [x, torch.zeros(B, M // 64, 16, device=device)]))
+    out = {"metric": "HealpyGCNN train maps/s", "value": world * B / (ms * 1e-3), "unit": "maps/s", "ms_per_step": ms,
+           "batch_per_gpu": B, "n_gpus": world, "parameters": int(sum(p.numel() for p in params)),
+           "final_loss": float(loss.detach()), "config": desc,
+           "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak,
+                        "note": "algorithmic bytes of one step (every layer: forward in + out, backward 2 in + out) / step "
+                                "time; these 1 - 16 channel networks are launch- and latency-bound, not HBM-bound"}}
+    # CPU restatement on the host cores (rank 0, N = 1 only): one sample, forward + backward; parity of the forward
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        specs, _ = bridge.specs_from_layers(layers_all)
+        for kind, p in specs:   # float32 weights: the reference's floatx arithmetic
+            for key, v in list(p.items()):
+                if isinstance(v, torch.Tensor):
+                    p[key] = v.detach().float().requires_grad_(v.requires_grad)
+                elif isinstance(v, (list, tuple)) and v and isinstance(v[0], torch.Tensor):
+                    p[key] = [u.detach().float().requires_grad_(True) for u in v]
+        xs = x[:1].detach().cpu()
+        with torch.no_grad():
+            y_gpu = fwd(x[:1], False).detach().cpu()
+        t0 = time.perf_counter()
+        y_cpu = orc.torch_cpu_network(xs.clone().requires_grad_(True), specs, training=False)
+        y_cpu.sum().backward()
+        t_cpu = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 1.0 / t_cpu, "unit": "maps/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": "1 map, forward + backward, torch-CPU restatement of the same layer list "
+                                         "(oracle.torch_cpu_network), inference-mode BatchNorm", "ms_per_step": t_cpu * 1e3}
+        err = float((y_gpu - y_cpu.detach()).abs().max() / y_cpu.detach().abs().max().clamp_min(1e-30))
+        out["parity"] = {"rel_err": {"y": err}, "tolerance": 1e-4, "ok": bool(err <= 1e-4),
+                         "what": "GPU forward of one map vs the CPU restatement (fp32), max|err| / max|ref|"}
+    for m in modules:
+        del m
+    del opt, x
+    torch.cuda.empty_cache()
+    return out
 
 
 def partition_parity_check(mode, device, rank, world, nside=64, batch=2):
@@ -305,7 +529,7 @@ def partition_parity_check(mode, device, rank, world, nside=64, batch=2):
         p.grad = None
     y = part(x[:, b0:e0].contiguous(), training=True)
     ((y - t) ** 2).mean().backward()
-    dsd.allreduce_gradients(params, average=False)
+    part.allreduce_gradients()   # sums the row-local partial sums; the head behind the mean is replicated
     torch.cuda.synchronize()
     out = None
     if rank == 0:
@@ -354,7 +578,7 @@ def model_train_partitioned_bench(args, mode, device, rank, world):
     model(x, training=True)  # builds the weights and the device plans
     dsd.broadcast_parameters(model)
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.Adam(params, lr=1e-3)
+    opt = torch.optim.Adam(params, lr=1e-3, capturable=True)
     prep_s = time.time() - t0
     ar_events = []
 
@@ -364,7 +588,7 @@ def model_train_partitioned_bench(args, mode, device, rank, world):
         loss.backward()
         if timed:
             a = torch.cuda.Event(enable_timing=True); a.record()
-        dsd.allreduce_gradients(params, average=False)
+        model.allreduce_gradients()
         if timed:
             b = torch.cuda.Event(enable_timing=True); b.record()
             ar_events.append((a, b))
@@ -394,15 +618,23 @@ def model_train_partitioned_bench(args, mode, device, rank, world):
     ar_ms = sum(u.elapsed_time(v) for u, v in ar_events) / 2
     ex_ms = dsd.allreduce_max(ex_ms / 2, device)
     ar_ms = dsd.allreduce_max(ar_ms, device)
+    del loss
+    graph_t = None if args.no_graph else graph_replay_timing(train_step, params, opt, n, device, world)
+    eager_ms = ms
+    if graph_t is not None and graph_t.get("validated"):
+        ms = graph_t["ms_per_step"]
     convs = [l for l in model.layers_use if isinstance(l, partition.PartitionedGraphConv)]
     halo = [{"level_rows_own": int(c.plan.n_own), "halo_rows": int(c.plan.halo_rows), "hops": int(c.plan.n_hops),
              "lattice": int(c.layer._plan.info(device.index or 0)["lattice"])} for c in convs]
     n_params = int(sum(p.numel() for p in params))
     out = {"metric": "HealpyGCNN train maps/s, nside %d, one sphere partitioned over the ranks" % nside,
            "value": Bm / (ms * 1e-3), "unit": "maps/s", "ms_per_step": ms, "global_batch": Bm, "n_gpus": world,
-           "scaling": "strong", "parameters": n_params, "final_loss": float(loss.detach()),
+           "scaling": "strong", "parameters": n_params,
+           "execution": "CUDA graph replay of the whole step (validated against eager)" if ms != eager_ms else "eager",
+           "eager_ms_per_step": eager_ms, "cuda_graph": graph_t,
            "time_split_ms": {"halo_exchanges": ex_ms, "halo_exchanges_per_step": ex_n // 2, "grad_allreduce": ar_ms,
-                             "rest (kernels, optimizer, host launch gaps)": ms - ex_ms - ar_ms},
+                             "rest (kernels, optimizer, host launch gaps)": eager_ms - ex_ms - ar_ms,
+                             "note": "device time between event pairs in two instrumented EAGER steps"},
            "limiting_collective": None if world == 1 else ("halo all_to_all" if ex_ms >= ar_ms else "gradient all-reduce"),
            "halo": halo, "host_prep_s": prep_s,
            "config": f"nside {nside} ({npix} px): PseudoConv p1 F16 -> [Chebyshev K5 F32 + MAX pool] x4 -> Chebyshev K5 F64 "
@@ -661,12 +893,26 @@ def main():
 
             model_train_partitioned = {"error": str(exc)[:300], "trace": traceback.format_exc()[-600:]}
 
+    # ---- BASELINE.json's other named configurations, each with its CPU restatement beside it
+    named_configs = None
+    if not args.no_configs and not args.no_model:
+        named_configs = {}
+        for cname in ("C1_quick_start", "C4_autoencoder", "C3_masked_survey"):
+            try:
+                named_configs[cname] = named_config_bench(cname, args, device, rank, world, hbm_peak)
+            except Exception as exc:
+                import traceback
+
+                named_configs[cname] = {"error": str(exc)[:300], "trace": traceback.format_exc()[-500:]}
+            torch.cuda.empty_cache()
+
     # ---- the same training step with the opt-in streaming pseudo-convolution kernels (ds_skinny.cu, written after
     # this round's GPU budget was spent: host-emulated only, hence not the default).  Separate process so that a fault
     # there cannot touch this measurement; "validated" = its first-step loss and per-parameter gradient norms (same
     # seeds, before any update) equal the default path's to 1e-4.
     model_train_experimental = None
-    if model_train is not None and "error" not in model_train and not args.no_experimental and world == 1:
+    if model_train is not None and "error" not in model_train and args.experimental and not args.no_experimental \
+            and world == 1:
         model_train_experimental = {}
         for key, env_sw, flags in (("streaming_kernels", {"DEEPSPHERE_SKINNY": "1"}, ()),
                                    ("cuda_graph", None, ("--model-graph",)),
@@ -787,6 +1033,7 @@ def main():
             "roofline": roofline, "layer_roofline": layer_roofline, "kernels": kernels, "other_modes": other_modes, "model_train": model_train,
             "model_train_experimental": model_train_experimental,
             "model_train_partitioned": model_train_partitioned, "partition_parity": partition_parity,
+            "named_configs": named_configs,
             "cpu_baseline": cpu_baseline, "parity": parity, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
         }
         print(json.dumps(line))

@@ -29,6 +29,7 @@ int fused_conv(const ds_plan* plan, int32_t recursion, int32_t K, int64_t B, int
                float* y, int mode, cudaStream_t st);
 
 bool lattice_usable(const ds_plan* plan, int32_t K, int64_t B, int64_t F);
+int lattice_halo(const ds_plan* plan);
 int lattice_recursion(const ds_plan* plan, int64_t B, int F, int nsteps, const float* in0, const float* const* add,
                       float* const* out, const float* alpha, const float* beta, const float* gamma, cudaStream_t st);
 
@@ -53,18 +54,33 @@ int compute_basis(const ds_plan* plan, int32_t recursion, int32_t K, int64_t B, 
   const SparseDev& S = transpose ? plan->bwd : plan->fwd;  // the lattice path requires L~ symmetric
   const int64_t A = B * S.M * Fin;
   if (lattice_usable(plan, K, B, Fin)) {
-    // all K-1 hops fused on chip (ds_lattice.cu); every hop's own-tile result goes to its basis slot
-    const float* add[16] = {};
-    float* out[16] = {};
-    float al[16], be[16], ga[16];
-    for (int s = 1; s < K; ++s) {
-      const bool cheb2 = recursion == DS_RECURSION_CHEBYSHEV && s >= 2;
-      al[s - 1] = cheb2 ? 2.f : 1.f;
-      be[s - 1] = cheb2 ? -1.f : 0.f;
-      ga[s - 1] = 0.f;
-      out[s - 1] = basis + (int64_t)(s - 1) * A;
+    // the hops run fused on chip (ds_lattice.cu), every hop's own-tile result goes to its basis slot.  The lattice
+    // tables carry an H-ring halo: K - 1 <= H hops are one pass; longer recursions (the reference ships K = 10,
+    // examples/quick_start.ipynb:118-127) are CHAINED in passes of <= H hops - pass j starts from cur = T_{jH} and, for
+    // Chebyshev, takes old = T_{jH-1} as the first hop's additive input (2 L~ T_{jH} - T_{jH-1}); HBM sees each basis
+    // tensor written once and the two seam tensors read once more, instead of 3 tensors per hop
+    const int H = lattice_halo(plan);
+    auto T = [&](int k) -> const float* { return k == 0 ? x : basis + (int64_t)(k - 1) * A; };
+    for (int k0 = 0; k0 < K - 1; k0 += H) {
+      const int n = std::min(H, K - 1 - k0);
+      const float* add[16] = {};
+      float* out[16] = {};
+      float al[16], be[16], ga[16];
+      for (int s = 1; s <= n; ++s) {
+        const int k = k0 + s;  // this hop produces T_k
+        const bool cheb2 = recursion == DS_RECURSION_CHEBYSHEV && k >= 2;
+        al[s - 1] = cheb2 ? 2.f : 1.f;
+        be[s - 1] = cheb2 && s >= 2 ? -1.f : 0.f;   // old = the pass's previous tensor (on chip from the 2nd hop on)
+        ga[s - 1] = 0.f;
+        if (cheb2 && s == 1) {                       // seam: T_{k-2} comes from HBM
+          add[0] = T(k - 2);
+          ga[0] = -1.f;
+        }
+        out[s - 1] = basis + (int64_t)(k - 1) * A;
+      }
+      DS_TRY(lattice_recursion(plan, B, (int)Fin, n, T(k0), add, out, al, be, ga, st));
     }
-    return lattice_recursion(plan, B, (int)Fin, K - 1, x, add, out, al, be, ga, st);
+    return 0;
   }
   auto T = [&](int k) -> const float* { return k == 0 ? x : basis + (int64_t)(k - 1) * A; };
   for (int k = 1; k < K; ++k) {

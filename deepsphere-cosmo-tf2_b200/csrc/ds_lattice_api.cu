@@ -63,11 +63,13 @@ void lattice_free(LatticeAttachment* L) {
 bool lattice_usable(const ds_plan* plan, int32_t K, int64_t B, int64_t F) {
   if (!plan->lattice || !plan->symmetric) return false;
   const LatticeAttachment* L = plan->lattice;
-  if (K - 1 > L->H || K < 2 || F % 4 != 0) return false;
+  if (L->H < 1 || K < 2 || F % 4 != 0) return false;  // K - 1 > H: chained passes (compute_basis, ds_api.cu)
   LatticeArgs a;
   int threads = 0, smem = 0;
   return lattice_configure(L->dev, B, plan->M, (int)F, a, &threads, &smem) == 0;
 }
+
+int lattice_halo(const ds_plan* plan) { return plan->lattice ? plan->lattice->H : 0; }
 
 // generic (unfused) recursion on the closure sub-problem, used for the irregular tiles
 // steps: out_s = alpha_s * S cur + beta_s * old + gamma_s * add_s on gathered tensors; results scattered

@@ -241,7 +241,17 @@ class Model(torch.nn.Module):
 
     @property
     def losses(self):
-        return [reg(p) for reg, p in self._regularizers]
+        """Regularisation terms of this layer AND of every layer below it (Keras aggregates the `losses` of nested
+        layers: a Sequential / HealpyGCNN / residual layer built from layers with `regularizer=` kwargs reports them
+        all), one entry per (regularizer, weight) pair."""
+        out, seen = [], set()
+        for m in self.modules():
+            for reg, p in getattr(m, "_regularizers", ()):
+                key = (id(reg), id(p))
+                if key not in seen:
+                    seen.add(key)
+                    out.append(reg(p))
+        return out
 
     def build(self, input_shape):
         pass

@@ -365,6 +365,14 @@ class PartitionedHealpyGCNN(torch.nn.Module):
         align = 4 ** max_depth
         if M % align:
             raise ValueError(f"{M} pixels cannot be pooled {max_depth} times: use utils.extend_indices first")
+        # the index set must be closed under the 4^depth sibling groups (the check of HealpyGCNN, healpy_networks.py:
+        # 66-86): a compatible COUNT with incomplete groups would let local pooling mix unrelated pixels
+        if max_depth > 0 and not np.array_equal(hpx.refine_indices(hpx.coarsen_indices(idx, max_depth), max_depth), idx):
+            raise ValueError(
+                "With the given indices it would not be possible to properly reduce the input maps "
+                "with the reduction factor determined by the layers. Use the function "
+                "<extend_indices> from utils with the determined minimal nside to make your set of "
+                "indices compatible...")
         if M % 48 == 0 and (M // 48) % align == 0 and world <= 48:
             align = M // 48  # quarter-face blocks of a full sphere
         if M // align < world:
@@ -403,6 +411,33 @@ class PartitionedHealpyGCNN(torch.nn.Module):
                 raise NotImplementedError("residual layers on a partitioned sphere")
             else:
                 self.layers_use.append(layer if isinstance(layer, torch.nn.Module) else _Callable(layer))
+
+    def row_local_parameters(self):
+        """Weights of the layers that run on a rank's OWN rows (everything before the PartitionedMean head): their
+        gradients are partial sums over the rows and have to be SUMMED over the group."""
+        out = []
+        for layer in self.layers_use:
+            if isinstance(layer, PartitionedMean):
+                break
+            out += [p for p in layer.parameters() if p.requires_grad]
+        return out
+
+    def replicated_parameters(self):
+        """Weights of the layers behind the PartitionedMean head: they see replicated tensors, every rank computes the
+        same gradient (average them, or leave them alone)."""
+        out, behind = [], False
+        for layer in self.layers_use:
+            if behind:
+                out += [p for p in layer.parameters() if p.requires_grad]
+            behind = behind or isinstance(layer, PartitionedMean)
+        return out
+
+    def allreduce_gradients(self):
+        """The gradient exchange of one training step: sum of the row-local partial sums over the group (one flat
+        all-reduce); the replicated head is identical on every rank by construction and needs no exchange."""
+        from .distributed import allreduce_gradients
+
+        return allreduce_gradients(self.row_local_parameters(), group=self.group, average=False)
 
     def forward(self, x_own, training=False):
         from .keras_compat import _accepts_training

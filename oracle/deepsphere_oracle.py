@@ -496,3 +496,89 @@ def torch_cpu_residual(x, Lt, kernels, K, recursion="chebyshev", layer_activatio
     if act_before:
         return act(h) + alpha * x
     return act(h + alpha * x)
+
+
+# --------------------------------------------------------------------------------------
+# Whole networks (healpy_networks.HealpyGCNN as a Sequential of the layers above) with differentiable torch CPU ops:
+# the yardstick for network-level parity (forward AND every weight gradient) and the timed CPU baseline of the named
+# configurations.  A network is a list of specs (kind, params) whose weights are torch tensors:
+#   ("conv", dict(Lt, K, recursion, kernel, bias|None, activation, use_bn))      gnn_layers.py:130-161 / 281-309
+#   ("pool", dict(p, pool_type))                                                  healpy_layers.py:48-63
+#   ("pconv", dict(kernel [4^p, Fin, Fout], bias, activation))                    healpy_layers.py:118-126
+#   ("pconvT", dict(kernel [1, 4^p, Fout, Fin], bias, activation))                healpy_layers.py:180-188
+#   ("residual", dict(Lt, K, recursion, kernels, biases, layer_activation, layer_use_bn, activation, act_before, use_bn,
+#                     norm_type, alpha))                                          gnn_layers.py:384-413
+#   ("layernorm", dict(axis, gamma, beta, eps))                                   tf.keras.layers.LayerNormalization
+#   ("mean", {}) / ("mean_softmax", {})     reduce_mean over pixels (+ softmax), the Lambda heads of the notebooks
+#   ("dense", dict(kernel [Fin, Fout], bias))
+# --------------------------------------------------------------------------------------
+
+
+def torch_cpu_pool(x, p, pool_type="MAX"):
+    r = int(4**p)
+    N, M, F = x.shape
+    xr = x.reshape(N, M // r, r, F)
+    return xr.max(dim=2).values if pool_type == "MAX" else xr.mean(dim=2)
+
+
+def torch_cpu_pconv(x, kernel, bias=None, activation=None):
+    r, Fin, Fout = kernel.shape
+    N, M, _ = x.shape
+    z = (x.reshape(N * (M // r), r * Fin) @ kernel.reshape(r * Fin, Fout)).reshape(N, M // r, Fout)
+    if bias is not None:
+        z = z + bias
+    return _torch_act(activation)(z)
+
+
+def torch_cpu_pconv_transpose(x, kernel, bias=None, activation=None):
+    _, r, Fout, Fin = kernel.shape
+    N, M, _ = x.shape
+    z = (x.reshape(N * M, Fin) @ kernel[0].reshape(r * Fout, Fin).T).reshape(N, M * r, Fout)
+    if bias is not None:
+        z = z + bias
+    return _torch_act(activation)(z)
+
+
+def torch_cpu_network(x, specs, training=False):
+    import torch
+
+    h = x
+    for kind, p in specs:
+        if kind == "conv":
+            h = torch_cpu_layer(h, p["Lt"], p["kernel"], p["K"], p["recursion"], bias=p.get("bias"),
+                                activation=p.get("activation"), use_bn=p.get("use_bn", False), training=training,
+                                moving_mean=p.get("moving_mean"), moving_var=p.get("moving_var"))
+        elif kind == "pool":
+            h = torch_cpu_pool(h, p["p"], p["pool_type"])
+        elif kind == "pconv":
+            h = torch_cpu_pconv(h, p["kernel"], p.get("bias"), p.get("activation"))
+        elif kind == "pconvT":
+            h = torch_cpu_pconv_transpose(h, p["kernel"], p.get("bias"), p.get("activation"))
+        elif kind == "residual":
+            h = torch_cpu_residual(h, p["Lt"], p["kernels"], p["K"], p["recursion"], layer_activation=p.get("layer_activation"),
+                                   layer_biases=p.get("biases", (None, None)), layer_use_bn=p.get("layer_use_bn", False),
+                                   activation=p.get("activation"), act_before=p.get("act_before", False),
+                                   use_bn=p.get("use_bn", False), norm_type=p.get("norm_type", "batch_norm"),
+                                   alpha=p.get("alpha", 1.0), training=training)
+        elif kind == "layernorm":
+            axes = p["axis"] if isinstance(p["axis"], (tuple, list)) else (p["axis"],)
+            axes = tuple(a % h.dim() for a in axes)
+            mean = h.mean(dim=axes, keepdim=True)
+            var = h.var(dim=axes, unbiased=False, keepdim=True)
+            h = (h - mean) / torch.sqrt(var + p.get("eps", 1e-3))
+            shape = [h.shape[a] if a in axes else 1 for a in range(h.dim())]
+            if p.get("gamma") is not None:
+                h = h * p["gamma"].reshape(shape)
+            if p.get("beta") is not None:
+                h = h + p["beta"].reshape(shape)
+        elif kind == "mean":
+            h = h.mean(dim=1)
+        elif kind == "mean_softmax":
+            h = torch.softmax(h.mean(dim=1), dim=-1)
+        elif kind == "dense":
+            h = h @ p["kernel"]
+            if p.get("bias") is not None:
+                h = h + p["bias"]
+        else:
+            raise ValueError(f"oracle network: unknown layer kind {kind}")
+    return h

@@ -218,3 +218,30 @@ def test_save_load_weights_roundtrip(tmp_path):
     b.load_weights(path)
     for wa, wb in zip(a.get_weights(), b.get_weights()):
         assert np.allclose(wa, wb, atol=1e-6)
+
+
+def test_losses_aggregate_over_nested_layers():
+    """Keras reports the regularisation losses of nested layers on the outer model: HealpyGCNN and the
+    residual layer must not drop the `regularizer=` kwargs of their graph layers."""
+    import deepsphere
+    from deepsphere import gnn_layers, healpy_layers as hl
+
+    reg = lambda w: (w ** 2).sum()  # noqa: E731
+    layers = [hl.HealpyChebyshev(K=3, Fout=4, regularizer=reg), hl.HealpyPool(p=1), hl.HealpyMonomial(K=2, Fout=2, regularizer=reg)]
+    model = deepsphere.HealpyGCNN(nside=4, indices=np.arange(192), layers=layers)
+    model.build(input_shape=(None, 192, 1))
+    assert len(model.losses) == 2
+    res = gnn_layers.GCNN_ResidualLayer("CHEBY", {"L": np.eye(12), "K": 2, "regularizer": reg})
+    res.build_from_shape((1, 12, 3))
+    assert len(res.losses) == 2 and all(float(v) > 0 for v in res.losses)
+
+
+def test_partitioned_model_rejects_incomplete_sibling_groups():
+    """A masked index set whose COUNT is compatible with the pooling depth but whose 4^p groups are incomplete must raise
+    the same ValueError as HealpyGCNN."""
+    from deepsphere import healpy_layers as hl, partition
+
+    idx = np.arange(0, 192 * 4, 1)[::3][:64 * 3]  # 192 pixels of nside 8, not closed under 4-groups
+    assert len(idx) % 4 == 0
+    with pytest.raises(ValueError):
+        partition.PartitionedHealpyGCNN(8, idx, [hl.HealpyPool(p=1)], rank=0, world=1)

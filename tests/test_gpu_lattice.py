@@ -20,7 +20,7 @@ def _run(layer, x, dy):
 
 @pytest.mark.parametrize("cls", ["Chebyshev", "Monomial"])
 @pytest.mark.parametrize("nside,B,Fin,Fout,K", [(32, 3, 4, 4, 5), (32, 2, 16, 8, 3), (64, 2, 64, 64, 5), (32, 5, 8, 4, 2),
-                                                (32, 2, 12, 4, 8)])
+                                                (32, 2, 12, 4, 8), (32, 2, 8, 8, 10), (32, 1, 4, 4, 13)])
 def test_lattice_forward_backward_matches_oracle(cls, nside, B, Fin, Fout, K):
     g = SphereHealpix(nside, k=8)
     M = g.L.shape[0]

@@ -323,3 +323,31 @@ def test_bench_experimental_child_validation(monkeypatch):
 
     monkeypatch.setattr(subprocess, "run", boom)
     assert "error" in bench.experimental_model_run(args, base, sw)
+
+
+def test_lmax_table_entries_are_what_the_solver_returns(monkeypatch):
+    """deepsphere/_lmax_table.json (tools/make_lmax_table.py) is keyed by a fingerprint of the matrix CONTENT: the entries of
+    the small graphs are recomputed here with the cache bypassed; an unknown or perturbed matrix must miss."""
+    import json
+
+    from scipy import sparse
+
+    from deepsphere import utils
+    from deepsphere.graph import SphereHealpix
+
+    path = os.path.join(os.path.dirname(utils.__file__), "_lmax_table.json")
+    table = json.load(open(path))
+    assert len(table) >= 8
+    for nside, k in ((32, 8), (64, 8), (32, 20)):
+        L = sparse.csr_matrix(SphereHealpix(nside, k=k).L, dtype=np.float64)
+        key = utils.matrix_fingerprint(L)
+        assert key in table
+        utils._LMAX_MEMO.clear()
+        cached = utils.largest_eigenvalue(L)
+        monkeypatch.setenv("DEEPSPHERE_LMAX", "nocache")
+        fresh = utils.largest_eigenvalue(L)
+        monkeypatch.delenv("DEEPSPHERE_LMAX")
+        assert cached == table[key] and abs(fresh - cached) <= 1e-12 * abs(fresh)
+        L2 = L.copy()
+        L2.data[7] *= 1.001
+        assert utils.matrix_fingerprint(L2) != key
