@@ -28,7 +28,10 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = "HealpyChebyshev fwd+bwd algorithmic GB/s (nside 256, K 5, Fin=Fout=64, batch 32/GPU)"
-TRAFFIC_DEFAULT = 14552909000  # dram read 8.168 GB + write 6.385 GB per launch, profiles/r1k_prof_lattice_conv2_raw.csv
+# dram__bytes_read.sum + dram__bytes_write.sum of lattice_conv2_kernel from the round-2 `ncu --set full` capture of the
+# default build (profiles/r2h_prof_lattice_conv2_raw.csv: batch 8, 1.9007 GB read + 1.5576 GB written per launch), scaled
+# to the bench's batch 32 (the kernel's work and traffic are linear in the batch): 13.83 GB vs 12.88 GB algorithmic
+TRAFFIC_DEFAULT = int(4 * (1.900713e9 + 1.557593e9))
 
 
 def parse():
@@ -48,6 +51,7 @@ def parse():
     ap.add_argument("--no-experimental", action="store_true")
     ap.add_argument("--model-graph", action="store_true",
                     help="with --model-only: capture the training step in a CUDA graph and time graph replays")
+    ap.add_argument("--no-f-sweep", action="store_true", help="skip the fused forward at Fin = Fout = 16 / 32")
     ap.add_argument("--no-configs", action="store_true",
                     help="skip the named configurations C1 (quick_start), C3 (masked survey nside 512), C4 (autoencoder)")
     ap.add_argument("--experimental", action="store_true",
@@ -134,6 +138,28 @@ class ClockSampler:
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs that are local to GPU `index` (NVML's ideal CPU affinity) BEFORE any pinned host
+    buffer is allocated: first-touch then places the buffers on the GPU's own NUMA node.  Round 1's 8-rank e2e leg
+    (host -> device -> host of 19 GB per rank and step) ran 4x slower per rank than at N = 1 with every rank's buffers
+    wherever the kernel put them.  Returns the CPU list (or None when NVML / the affinity call is unavailable)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
 
 
 def build_layer(args, mode):
@@ -445,7 +471,7 @@ def named_config_bench(name, args, device, rank, world, hbm_peak):
         m.to(device)
         dsd.broadcast_parameters(m)
     params = [p for m in modules for p in m.trainable_variables]
-    opt = torch.optim.Adam(params, lr=1e-3)
+    opt = torch.optim.Adam(params, lr=1e-3, capturable=True)
 
     def train_step():
         opt.zero_grad(set_to_none=True)
@@ -471,9 +497,17 @@ def named_config_bench(name, args, device, rank, world, hbm_peak):
     ms = dsd.allreduce_max(a.elapsed_time(b) / n, device)
     nbytes = sum(_step_bytes(m, xi) for m, xi in zip(modules, [x] if len(modules) == 1 else
                                                       [x, torch.zeros(B, M // 64, 16, device=device)]))
+    final_loss = float(loss.detach())
+    del loss
+    eager_ms = ms
+    graph_t = None if args.no_graph else graph_replay_timing(train_step, params, opt, n, device, world)
+    if graph_t is not None and graph_t.get("validated"):
+        ms = graph_t["ms_per_step"]
     out = {"metric": "HealpyGCNN train maps/s", "value": world * B / (ms * 1e-3), "unit": "maps/s", "ms_per_step": ms,
            "batch_per_gpu": B, "n_gpus": world, "parameters": int(sum(p.numel() for p in params)),
-           "final_loss": float(loss.detach()), "config": desc,
+           "final_loss": final_loss, "config": desc,
+           "execution": "CUDA graph replay of the whole step (validated against eager)" if ms != eager_ms else "eager",
+           "eager_ms_per_step": eager_ms, "cuda_graph": graph_t,
            "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak,
                         "note": "algorithmic bytes of one step (every layer: forward in + out, backward 2 in + out) / step "
@@ -481,12 +515,16 @@ def named_config_bench(name, args, device, rank, world, hbm_peak):
     # CPU restatement on the host cores (rank 0, N = 1 only): one sample, forward + backward; parity of the forward
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         specs, _ = bridge.specs_from_layers(layers_all)
-        for kind, p in specs:   # float32 weights: the reference's floatx arithmetic
-            for key, v in list(p.items()):
-                if isinstance(v, torch.Tensor):
-                    p[key] = v.detach().float().requires_grad_(v.requires_grad)
-                elif isinstance(v, (list, tuple)) and v and isinstance(v[0], torch.Tensor):
-                    p[key] = [u.detach().float().requires_grad_(True) for u in v]
+        def f32(v):   # float32 weights: the reference's floatx arithmetic
+            if isinstance(v, torch.Tensor):
+                return v.detach().float().requires_grad_(v.requires_grad)
+            if isinstance(v, (list, tuple)):
+                return type(v)(f32(u) for u in v)
+            return v
+
+        for kind, p in specs:
+            for key in list(p.keys()):
+                p[key] = f32(p[key])
         xs = x[:1].detach().cpu()
         with torch.no_grad():
             y_gpu = fwd(x[:1], False).detach().cpu()
@@ -722,6 +760,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dsd.init_from_env()
     mode = args.mode
     if args.model_only:
@@ -825,8 +864,8 @@ def main():
                "algorithmic_bytes": 2 * A_bytes, "GBps": 2 * A_bytes / fwd_ms / 1e6,
                "stencil_TFLOPs_fp32": fma_flops / fwd_ms / 1e9, "contraction_TFLOPs_tf32": gemm_flops / fwd_ms / 1e9}
         kernels["fused_forward"] = dom
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture of the default
-        # config (profiles/r1k_prof_lattice_conv2_raw.csv); only quoted for that config
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` capture (see TRAFFIC_DEFAULT);
+        # only quoted for the default config
         traffic = TRAFFIC_DEFAULT if (args.nside, B, F, K) == (256, 32, 64, 5) else None
     else:
         contraction_ms = max(fwd_ms - basis_ms, 1e-6)
@@ -871,6 +910,25 @@ def main():
             finally:
                 layer.mode = mode
                 torch.cuda.empty_cache()
+
+    # ---- the fused forward at narrower layers (the arithmetic intensity falls with F) -------------------
+    f_sweep = None
+    if not args.no_f_sweep and rank == 0 and world == 1 and fused_conv:
+        from deepsphere import gnn_layers
+
+        f_sweep = {}
+        for Fs in (16, 32):
+            try:
+                ls = gnn_layers.Chebyshev(L=g.L, K=K, Fout=Fs, mode=mode, lmax=layer.lmax)
+                xs = torch.randn(B, M, Fs, device=device)
+                with torch.no_grad():
+                    t_ms = time_fn(lambda: ls(xs))
+                f_sweep[f"F{Fs}"] = {"ms": t_ms, "GBps": 2 * 4 * B * M * Fs / t_ms / 1e6,
+                                     "frac_of_hbm_peak": 2 * 4 * B * M * Fs / t_ms / 1e6 / hbm_peak}
+                del ls, xs
+            except Exception as exc:
+                f_sweep[f"F{Fs}"] = {"error": str(exc)[:120]}
+            torch.cuda.empty_cache()
 
     # ---- HealpyGCNN training throughput (the second half of the metric) ------------------------------
     model_train = None
@@ -1000,7 +1058,8 @@ def main():
         e2e = {"value": world * algorithmic_bytes(Be, M, F, F) / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s",
                "h2d_bytes_per_step": 2 * 4 * Be * M * F, "d2h_bytes_per_step": 4 * Be * M * F + 4 * K * F * F,
                "ms_per_step": e2e_ms, "batch": Be, "steps": n_e2e,
-               "pipeline": f"{n_chunks} batch chunks over 3 streams (H2D | fwd+bwd | D2H), pinned host buffers"}
+               "pipeline": f"{n_chunks} batch chunks over 3 streams (H2D | fwd+bwd | D2H), pinned host buffers",
+               "host_numa_binding": None if numa_cpus is None else f"{len(numa_cpus)} CPUs local to GPU {local_rank} (NVML)"}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle port on a bounded sample -------------------
     cpu_baseline = None
@@ -1030,7 +1089,8 @@ def main():
             "config": {"workload": f"HealpyChebyshev layer nside {args.nside} (M={M}) K {K} Fin=Fout={F} "
                                    f"batch {B}/GPU fwd+bwd, 8-neighbour HEALPix graph",
                        "mode": mode, "parallelism": f"batch-sharded x{world}", "l2": "inputs (6.4 GB/tensor) >> L2"},
-            "roofline": roofline, "layer_roofline": layer_roofline, "kernels": kernels, "other_modes": other_modes, "model_train": model_train,
+            "roofline": roofline, "layer_roofline": layer_roofline, "kernels": kernels, "fused_forward_narrow_layers": f_sweep,
+            "other_modes": other_modes, "model_train": model_train,
             "model_train_experimental": model_train_experimental,
             "model_train_partitioned": model_train_partitioned, "partition_parity": partition_parity,
             "named_configs": named_configs,

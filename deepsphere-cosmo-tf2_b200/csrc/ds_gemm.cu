@@ -250,25 +250,25 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(int64_t R, int64_t 
   }
 }
 
-// out[f] = sum over blocks and folded columns (c = f, f + F, ...) of partial[b][c]; 32 outputs per CTA, 8 thread
-// groups split the blocks (fixed order: deterministic), combined through shared memory
+// out[f] = sum over blocks and folded columns (c = f, f + F, ...) of partial[b][c].  One WARP per output: the lanes split
+// the nblk * (Ncols / F) terms (independent loads, fixed assignment and a fixed shuffle tree: deterministic).  (Round 1
+// used ceil(F / 32) CTAs whose threads each walked 64 block partials serially: one or two SMs busy for ~0.3 ms per call,
+// 15 % of a HealpyGCNN training step in the ncu launch list.)
 __global__ void __launch_bounds__(256) colsum_final_kernel(int64_t Ncols, int64_t F, int nblk,
                                                             const float* __restrict__ partial, float* __restrict__ out) {
-  __shared__ float red[8][33];
-  const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int64_t f = (int64_t)blockIdx.x * 32 + cl;
+  const int lane = threadIdx.x & 31;
+  const int64_t f = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (f >= F) return;
+  const int64_t fold = (Ncols - f + F - 1) / F;  // columns f, f + F, ... < Ncols
+  const int64_t terms = (int64_t)nblk * fold;
   float s = 0.f;
-  if (f < F)
-    for (int b = g; b < nblk; b += 8)
-      for (int64_t c = f; c < Ncols; c += F) s += __ldg(partial + (int64_t)b * Ncols + c);
-  red[g][cl] = s;
-  __syncthreads();
-  if (g == 0 && f < F) {
-    float t = 0.f;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) t += red[q][cl];
-    out[f] = t;
+  for (int64_t i = lane; i < terms; i += 32) {
+    const int64_t b = i / fold, j = i - b * fold;
+    s += __ldg(partial + b * Ncols + f + j * F);
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[f] = s;
 }
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -353,7 +353,7 @@ int launch_act_backward(int64_t R, int64_t Ncols, int64_t F, const float* y, con
 
 // out[f] = sum over `nblk` block partials [nblk, Ncols] (and folded columns c = f, f + F, ...)
 int launch_colsum_final(int64_t Ncols, int64_t F, int nblk, const float* partial, float* out, cudaStream_t st) {
-  colsum_final_kernel<<<(unsigned)cdiv(F, 32), 256, 0, st>>>(Ncols, F, nblk, partial, out);
+  colsum_final_kernel<<<(unsigned)cdiv(F, 8), 256, 0, st>>>(Ncols, F, nblk, partial, out);
   DS_LAUNCHED();
   return 0;
 }
@@ -362,7 +362,7 @@ int launch_colsum(int64_t R, int64_t Ncols, int64_t F, const float* Z, float* ou
   const int nblk = (int)std::max<int64_t>(1, std::min<int64_t>(COLSUM_BLOCKS, cdiv(R, 64)));
   colsum_partial_kernel<<<nblk, 256, 0, st>>>(R, Ncols, Z, workspace);
   DS_LAUNCHED();
-  colsum_final_kernel<<<(unsigned)cdiv(F, 32), 256, 0, st>>>(Ncols, F, nblk, workspace, out);
+  colsum_final_kernel<<<(unsigned)cdiv(F, 8), 256, 0, st>>>(Ncols, F, nblk, workspace, out);
   DS_LAUNCHED();
   return 0;
 }

@@ -65,7 +65,9 @@ def specs_from_layers(layers):
             specs.append(("residual", dict(Lt=s1["Lt"], K=l1.K, recursion=s1["recursion"], kernels=[s1["kernel"], s2["kernel"]],
                                            biases=(s1["bias"], s2["bias"]), layer_activation=s1["activation"],
                                            layer_use_bn=l1.use_bn, activation=_act_name(layer), act_before=layer.act_before,
-                                           use_bn=layer.use_bn, norm_type=layer.norm_type, alpha=layer.alpha)))
+                                           use_bn=layer.use_bn, norm_type=layer.norm_type, alpha=layer.alpha,
+                                           layer_moving=((s1.get("moving_mean"), s1.get("moving_var")),
+                                                         (s2.get("moving_mean"), s2.get("moving_var"))))))
         elif isinstance(layer, hl.HealpyPool):
             specs.append(("pool", dict(p=layer.p, pool_type=layer.pool_type)))
         elif isinstance(layer, hl.HealpyPseudoConv_Transpose):

@@ -458,7 +458,8 @@ def _torch_act(name):
 
 def torch_cpu_residual(x, Lt, kernels, K, recursion="chebyshev", layer_activation=None, layer_biases=(None, None),
                        layer_use_bn=False, activation=None, act_before=False, use_bn=False, norm_type="batch_norm",
-                       alpha=1.0, training=False, eps_bn=1e-3, eps_ln=1e-3, ln_axis=-1):
+                       alpha=1.0, training=False, eps_bn=1e-3, eps_ln=1e-3, ln_axis=-1,
+                       layer_moving=((None, None), (None, None))):
     """GCNN_ResidualLayer.call (gnn_layers.py:384-413): in -> layer1 -> [norm] -> layer2 -> [norm] -> skip.
 
     Both sub-layers are built from the same ``layer_kwargs`` (gnn_layers.py:365-370) and are called WITHOUT an explicit
@@ -483,11 +484,11 @@ def torch_cpu_residual(x, Lt, kernels, K, recursion="chebyshev", layer_activatio
         return (z - mean) / torch.sqrt(var + eps_ln)
 
     h = torch_cpu_layer(x, Lt, kernels[0], K, recursion, bias=layer_biases[0], activation=layer_activation,
-                        use_bn=layer_use_bn, training=training)
+                        use_bn=layer_use_bn, training=training, moving_mean=layer_moving[0][0], moving_var=layer_moving[0][1])
     if use_bn:
         h = norm(h)
     h = torch_cpu_layer(h, Lt, kernels[1], K, recursion, bias=layer_biases[1], activation=layer_activation,
-                        use_bn=layer_use_bn, training=training)
+                        use_bn=layer_use_bn, training=training, moving_mean=layer_moving[1][0], moving_var=layer_moving[1][1])
     if use_bn:
         h = norm(h)
     if activation is None:
@@ -559,7 +560,8 @@ def torch_cpu_network(x, specs, training=False):
                                    layer_biases=p.get("biases", (None, None)), layer_use_bn=p.get("layer_use_bn", False),
                                    activation=p.get("activation"), act_before=p.get("act_before", False),
                                    use_bn=p.get("use_bn", False), norm_type=p.get("norm_type", "batch_norm"),
-                                   alpha=p.get("alpha", 1.0), training=training)
+                                   alpha=p.get("alpha", 1.0), training=training,
+                                   layer_moving=p.get("layer_moving", ((None, None), (None, None))))
         elif kind == "layernorm":
             axes = p["axis"] if isinstance(p["axis"], (tuple, list)) else (p["axis"],)
             axes = tuple(a % h.dim() for a in axes)
