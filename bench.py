@@ -972,9 +972,8 @@ def main():
     if model_train is not None and "error" not in model_train and args.experimental and not args.no_experimental \
             and world == 1:
         model_train_experimental = {}
-        for key, env_sw, flags in (("streaming_kernels", {"DEEPSPHERE_SKINNY": "1"}, ()),
-                                   ("cuda_graph", None, ("--model-graph",)),
-                                   ("both", {"DEEPSPHERE_SKINNY": "1"}, ("--model-graph",))):
+        # (round 2: the streaming pseudo-convolution kernels became the default; the child runs the OTHER setting)
+        for key, env_sw, flags in (("tiled_pseudo_conv_kernels", {"DEEPSPHERE_SKINNY": "0"}, ("--no-graph",)),):
             model_train_experimental[key] = experimental_model_run(args, model_train, env_sw, flags)
             if "timed out" in str(model_train_experimental[key].get("error", "")):
                 break  # do not spend more of the bench's minutes on a child that hangs

@@ -82,6 +82,16 @@ __host__ __device__ constexpr int col_of_slot(int p) { return (p % C2_NB) * C2_B
 #define C2_NLOAD 96
 #endif
 static_assert(C2_NLOAD % 32 == 0 && (2 * C2_LW * C2_LW) % C2_NLOAD == 0, "gather threads");
+// 1 = the accumulator drain (TMEM -> bias / activation -> y) runs on the IO warps instead of the compute warps: the three
+// gather warps (CTA warps 5, 6, 7 = TMEM lane quarters 1, 2, 3) between their gathers, and the UMMA-issuing warp (CTA warp
+// 4 = quarter 0) right after it has committed a group's last UMMAs.  ncu source page of the round-2 default build: 17.7 %
+// of the compute warps' samples sit in the drain, while the IO warps sleep 82 % of the time.  (A fifth IO warp for quarter
+// 0 does not work: setmaxnreg is a WARPGROUP instruction - all four warps of an aligned group of four must execute the
+// same one, which is also why the 6-compute-warp variants of round 1 fault.)
+#ifndef C2_IO_DRAIN
+#define C2_IO_DRAIN 0
+#endif
+static_assert(!C2_IO_DRAIN || (C2_NCW == 4 && C2_NLOAD == 96), "IO-side drain: warps 4..7 must cover the four TMEM lane quarters");
 constexpr int C2_NCOMP = 32 * C2_NCW, C2_THREADS = C2_NCOMP + 32 + C2_NLOAD;
 constexpr int C2_NEPI = C2_NCW >= 8 ? 8 : 4;  // warps that drain the accumulators (TMEM lane quarter = warp % 4)
 // registers per CTA (two CTAs per SM): the pool is what the launch allocates, threads x (registers per thread of the
@@ -361,6 +371,36 @@ __device__ __forceinline__ void hop_perimeter(cvec (&acc)[C2_BR][C2_BC], const f
   }
 }
 
+// TMEM -> bias / activation -> y for the 32 accumulator rows (TMEM lane quarter `warp & 3`) of the 3 M-tiles; rows[mt] = row
+// of y of this thread's accumulator row (or -1).  Warp-collective.
+__device__ __forceinline__ void drain_quarter(const Conv2Args& a, uint32_t tmem_base, int warp, const int (&rows)[3], int64_t b) {
+  const int N = a.N, NV16 = N / 16;
+#pragma unroll 1
+  for (int mt = 0; mt < 3; ++mt) {
+    const int row = rows[mt];
+    float* yrow = a.y + (b * a.M + (row >= 0 ? row : 0)) * (int64_t)N;
+#pragma unroll 1
+    for (int cc = 0; cc < NV16; ++cc) {
+      uint32_t r[16];
+      ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mt * N + cc * 16), r);
+      ptx::tmem_ld_wait();
+      if (row >= 0) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          float4 o = make_float4(__uint_as_float(r[v * 4]), __uint_as_float(r[v * 4 + 1]), __uint_as_float(r[v * 4 + 2]),
+                                 __uint_as_float(r[v * 4 + 3]));
+          if (a.bias != nullptr) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + cc * 16 + v * 4));
+            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+          }
+          if (a.act != DS_ACT_LINEAR) o = act4(o, a.act);
+          __stcs(reinterpret_cast<float4*>(yrow + cc * 16 + v * 4), o);
+        }
+      }
+    }
+  }
+}
+
 template <bool CHEB>
 __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv2Args a) {
   C2_DYNAMIC_SMEM(c2_smem);
@@ -390,7 +430,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
       ptx::mbar_init(&ctl->mma_done[i], 1);
     }
     ptx::mbar_init(&ctl->acc_full, 1);
-    ptx::mbar_init(&ctl->acc_empty, C2_NEPI);
+    ptx::mbar_init(&ctl->acc_empty, C2_IO_DRAIN ? 4 : C2_NEPI);
     ptx::fence_mbar_init();
   }
   if (warp == C2_NCW) ptx::tmem_alloc(&ctl->tmem_base, C2_TMEM_COLS);
@@ -776,7 +816,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
           last_par = par[last];
 
           if (c == n_chunks - 1) {
-            pend = warp < C2_NEPI;  // TMEM lanes 32 (w % 4) .. + 31 belong to warp w: 4 (or 2 x 4, half the slices each) warps drain
+            pend = !C2_IO_DRAIN && warp < C2_NEPI;  // TMEM lanes 32 (w % 4) .. + 31 belong to warp w: 4 (or 2 x 4, half the slices each) warps drain
             pend_g = g;
             pend_b = b;
             pend_rows[0] = erow[0]; pend_rows[1] = erow[1]; pend_rows[2] = erow[2];
@@ -788,6 +828,97 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
     }
     if (pend) epilogue();
   } else if (warp == C2_NCW) {
+#if C2_IO_DRAIN
+    // ================================ UMMA issuer / weight streamer (+ drain of TMEM lane quarter 0) =================
+    C2_SETMAXNREG_DEC(C2_REG_IO);
+    {
+      // Lane 0 alone waits, issues and commits (a lane that polled the pipeline barriers without gating them could miss
+      // a phase); the other lanes follow the item sequence without touching a barrier and meet lane 0 at the end of every
+      // group, where the whole warp drains quarter 0: acc_full cannot advance again before this warp has arrived on
+      // acc_empty, so that wait is safe for all lanes.
+      uint32_t total_items = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int64_t b_begin = (int64_t)(unit % a.b_split) * b_per;
+        const int64_t b_end = min(a.B, b_begin + b_per);
+        if (b_end > b_begin) total_items += (uint32_t)((b_end - b_begin) * n_chunks);
+      }
+      const uint32_t idesc = ptx::make_idesc_tf32(128, N, 0, 0);
+      const uint32_t buf_u32 = ptx::smem_u32(bufs);
+      const uint32_t wbuf_u32 = ptx::smem_u32(wbuf);
+      auto load_w = [&](uint32_t item, int chunk) {
+        const uint32_t wb = item & 1;
+        ptx::mbar_arrive_expect_tx(&ctl->w_full[wb], wslice_bytes);
+        ptx::bulk_load_1d(wbuf + (size_t)wb * wslice_bytes,
+                          reinterpret_cast<const uint8_t*>(a.b_img) + (size_t)chunk * wslice_bytes, wslice_bytes,
+                          &ctl->w_full[wb]);
+      };
+      auto issue = [&](uint32_t a_buf_u32, uint32_t w_u32, int k, bool first) {
+        const uint32_t a_base = a_buf_u32 + (uint32_t)((C2_H + 1) * C2_LW) * 16;  // plane 0, lattice row 4, position 0
+        const uint64_t bd = ptx::make_smem_desc(w_u32 + (uint32_t)k * img_bytes, (uint32_t)N * 16, 128,
+                                                ptx::LAYOUT_SWIZZLE_NONE);
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt) {
+          const uint64_t ad = ptx::make_smem_desc(a_base + (uint32_t)(mt * 128) * 16, C2_PL * 16, 128,
+                                                  ptx::LAYOUT_SWIZZLE_NONE);
+          ptx::umma_tf32(tmem_base + (uint32_t)(mt * N), ad, bd, idesc, first ? 0u : 1u);
+        }
+      };
+      uint32_t it = 0, g = 0, ch[2] = {0, 0};
+      if (lane == 0 && total_items > 0) load_w(0, 0);
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int64_t b_begin = (int64_t)(unit % a.b_split) * b_per;
+        const int64_t b_end = min(a.B, b_begin + b_per);
+        if (b_begin >= b_end) continue;
+        int erow[3];
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt) {  // accumulator row (mt, TMEM lane of quarter 0) -> lattice position -> row of y
+          const int m = mt * 128 + lane;
+          const int j = C2_H + m / C2_LW, p = m % C2_LW, cl = col_of_slot(p);
+          erow[mt] = (cl >= C2_H && cl < C2_H + C2_T) ? __ldg(a.pix + (size_t)(unit / a.b_split) * C2_P + j * C2_LW + cl) : -1;
+        }
+        for (int64_t b = b_begin; b < b_end; ++b) {
+          for (int c = 0; c < n_chunks; ++c) {
+            if (lane == 0) {
+              const uint32_t st = it & 1;
+              if (c == 0 && g >= 1) ptx::mbar_wait_backoff(&ctl->acc_empty, (g - 1) & 1, (uint32_t)a.sleep_mma);  // previous group drained
+              ptx::mbar_wait_backoff(&ctl->w_full[st], (it >> 1) & 1, (uint32_t)a.sleep_mma);
+              ptx::mbar_wait_backoff(&ctl->in_full[st], (it >> 1) & 1, (uint32_t)a.sleep_mma);
+              ptx::tc_fence_after_sync();
+              const uint32_t w_u32 = wbuf_u32 + st * wslice_bytes;
+              issue(buf_u32 + st * (uint32_t)(C2_BUF * 16), w_u32, 0, c == 0);
+              if (it + 1 < total_items) {  // stream the next chunk's weight slice into the other buffer
+                if (it >= 1) ptx::mbar_wait_backoff(&ctl->item_done[(it + 1) & 1], ((it - 1) >> 1) & 1, (uint32_t)a.sleep_mma);
+                load_w(it + 1, (c + 1) % n_chunks);
+              }
+              for (int s = 1; s <= nsteps; ++s) {
+                const int p = (s - 1) & 1;
+                ptx::mbar_wait_backoff(&ctl->hop_full[p], ch[p] & 1, (uint32_t)a.sleep_mma);
+                ch[p]++;
+                ptx::tc_fence_after_sync();
+                issue(buf_u32 + (uint32_t)(2 + p) * (uint32_t)(C2_BUF * 16), w_u32, s, false);
+                ptx::umma_commit(&ctl->mma_done[p]);
+                if (s == 1) ptx::umma_commit(&ctl->in_empty[st]);
+              }
+              ptx::umma_commit(&ctl->item_done[st]);
+              if (c == n_chunks - 1) ptx::umma_commit(&ctl->acc_full);
+              ++it;
+            }
+            if (c == n_chunks - 1) {
+              __syncwarp();
+              ptx::mbar_wait_backoff(&ctl->acc_full, g & 1, (uint32_t)a.sleep_mma);
+              ptx::tc_fence_after_sync();
+              drain_quarter(a, tmem_base, warp, erow, b);
+              ptx::tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(&ctl->acc_empty);
+              ++g;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+#else
     // ================================ UMMA issuer / weight streamer ================================
     C2_SETMAXNREG_DEC(C2_REG_IO);
     if (lane == 0) {
@@ -869,15 +1000,36 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
       }
     }
     __syncwarp();
+#endif
   } else {
-    // ================================ input gather warps ================================
+    // ================================ input gather warps (+ accumulator drain, C2_IO_DRAIN) ================================
     C2_SETMAXNREG_DEC(C2_REG_IO);
     const int t = tid - (C2_NCW + 1) * 32;  // 0..95
+    constexpr bool gathers = true;
     const int q = t & 1, pl0 = t >> 1;    // channel quad; position within a pair of lattice rows (0..47)
     const int inpos = pl0 % C2_LW, r0 = pl0 / C2_LW;
     const int col = col_of_slot(inpos);
     const int FV = a.F / 4;
     uint32_t it = 0;
+#if C2_IO_DRAIN
+    // groups (tile, b) whose last chunk has been passed, waiting for their drain: slot = group index & 3.  A group is
+    // drained two items after its closing item: by then the next two items are gathered (the compute warps never wait
+    // for this warp), and the wait for acc_full ends when the compute warps finish the closing item.
+    uint32_t g_closed = 0, g_drained = 0;
+    uint32_t close_it[4];
+    int64_t close_b[4];
+    int close_rows[4][3];
+    auto drain = [&](uint32_t g) {
+      const int sl = g & 3;
+      const int rws[3] = {close_rows[sl][0], close_rows[sl][1], close_rows[sl][2]};
+      ptx::mbar_wait_backoff(&ctl->acc_full, g & 1, (uint32_t)a.sleep_ld);
+      ptx::tc_fence_after_sync();
+      drain_quarter(a, tmem_base, warp, rws, close_b[sl]);
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&ctl->acc_empty);
+    };
+#endif
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
       const int tile = unit / a.b_split;
       const int64_t b_begin = (int64_t)(unit % a.b_split) * b_per;
@@ -886,25 +1038,48 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
       int rows[C2_LW / 2];
 #pragma unroll
       for (int k = 0; k < C2_LW / 2; ++k) rows[k] = __ldg(a.pix + (size_t)tile * C2_P + (2 * k + r0) * C2_LW + col);
+#if C2_IO_DRAIN
+      int erow[3];
+#pragma unroll
+      for (int mt = 0; mt < 3; ++mt) {  // accumulator row (mt, TMEM lane) -> lattice position -> row of y
+        const int m = mt * 128 + (warp & 3) * 32 + lane;
+        const int j = C2_H + m / C2_LW, p = m % C2_LW, c = col_of_slot(p);
+        erow[mt] = (c >= C2_H && c < C2_H + C2_T) ? __ldg(a.pix + (size_t)tile * C2_P + j * C2_LW + c) : -1;
+      }
+#endif
       for (int64_t b = b_begin; b < b_end; ++b) {
         for (int c = 0; c < n_chunks; ++c) {
           const uint32_t st = it & 1;
-          if (it >= 2) ptx::mbar_wait_backoff(&ctl->in_empty[st], ((it >> 1) - 1) & 1, (uint32_t)a.sleep_ld);
-          float4* dst = bufs + (size_t)st * C2_BUF + q * C2_PL + (r0 + 1) * C2_LW + inpos;
-          const float4* src = reinterpret_cast<const float4*>(a.in0 + (b * a.M * a.F + c * C2_FC)) + q;
+          if (gathers) {
+            if (it >= 2) ptx::mbar_wait_backoff(&ctl->in_empty[st], ((it >> 1) - 1) & 1, (uint32_t)a.sleep_ld);
+            float4* dst = bufs + (size_t)st * C2_BUF + q * C2_PL + (r0 + 1) * C2_LW + inpos;
+            const float4* src = reinterpret_cast<const float4*>(a.in0 + (b * a.M * a.F + c * C2_FC)) + q;
 #pragma unroll
-          for (int k = 0; k < C2_LW / 2; ++k) {
-            const int row = rows[k];
-            cp_async16(dst + 2 * k * C2_LW, row >= 0 ? (const void*)(src + (int64_t)row * FV) : (const void*)a.in0,
-                       row >= 0 ? 16u : 0u);
+            for (int k = 0; k < C2_LW / 2; ++k) {
+              const int row = rows[k];
+              cp_async16(dst + 2 * k * C2_LW, row >= 0 ? (const void*)(src + (int64_t)row * FV) : (const void*)a.in0,
+                         row >= 0 ? 16u : 0u);
+            }
+            cp_async_wait_all();
+            ptx::fence_proxy_async_smem();
+            ptx::mbar_arrive(&ctl->in_full[st]);
           }
-          cp_async_wait_all();
-          ptx::fence_proxy_async_smem();
-          ptx::mbar_arrive(&ctl->in_full[st]);
+#if C2_IO_DRAIN
+          if (c == n_chunks - 1) {
+            const int sl = g_closed & 3;
+            close_it[sl] = it; close_b[sl] = b;
+            close_rows[sl][0] = erow[0]; close_rows[sl][1] = erow[1]; close_rows[sl][2] = erow[2];
+            ++g_closed;
+          }
+          while (g_drained < g_closed && close_it[g_drained & 3] + 2 <= it) drain(g_drained++);
+#endif
           ++it;
         }
       }
     }
+#if C2_IO_DRAIN
+    while (g_drained < g_closed) drain(g_drained++);
+#endif
   }
   ptx::tc_fence_before_sync();
   __syncthreads();

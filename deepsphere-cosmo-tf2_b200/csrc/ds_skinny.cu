@@ -8,8 +8,10 @@
 //
 // HBM-bound by construction: forward reads R*Kc and writes R*N floats; backward reads R*(Kc + 2N) floats.
 //
-// EXPERIMENTAL in round 1: written after the round's GPU budget was spent, therefore OFF unless DEEPSPHERE_SKINNY=1;
-// bench.py times the HealpyGCNN step with it in a separate process and checks the result against the default path.
+// Round 1 wrote these after its GPU budget was spent (host-emulated only, opt-in).  Round 2 measured them on the B200 -
+// HealpyGCNN training step nside 256 / batch 16: 7.94 -> 5.85 ms; the sphere-partitioned nside-1024 step: 55.9 -> 39.5 ms
+// (the first pseudo-convolution alone was 30 % of it), same losses and gradients - and made them the default;
+// DEEPSPHERE_SKINNY=0 switches back to the tiled kernels.
 #include <algorithm>
 #include <cstdlib>
 
@@ -170,8 +172,8 @@ __global__ void __launch_bounds__(SK_THREADS) act_backward_colsum_kernel(int64_t
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-inline bool enabled() {
-  static const bool on = [] { const char* e = getenv("DEEPSPHERE_SKINNY"); return e && atoi(e) == 1; }();
+inline bool enabled() {  // on by default since round 2 (DEEPSPHERE_SKINNY=0 falls back to the tiled kernels)
+  static const bool on = [] { const char* e = getenv("DEEPSPHERE_SKINNY"); return e == nullptr || atoi(e) != 0; }();
   return on;
 }
 

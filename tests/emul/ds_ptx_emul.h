@@ -83,7 +83,8 @@ inline void mbar_wait(uint64_t* bar, uint32_t parity) {
   const auto t0 = std::chrono::steady_clock::now();
   while (!mbar_try_wait(bar, parity)) {
     if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) {
-      std::fprintf(stderr, "emul: mbarrier wait timed out (block %u thread %u) - protocol deadlock\n", blockIdx.x, threadIdx.x);
+      std::fprintf(stderr, "emul: mbarrier wait timed out (block %u thread %u, barrier at shared offset %td, parity %u) - protocol deadlock\n",
+                   blockIdx.x, threadIdx.x, reinterpret_cast<uint8_t*>(bar) - emul::dynamic_smem(), parity);
       std::abort();
     }
   }
