@@ -60,7 +60,8 @@ def parse():
     ap.add_argument("--no-partitioned", action="store_true",
                     help="skip the nside-1024 sphere-partitioned HealpyGCNN (strong scaling over the ranks)")
     ap.add_argument("--part-nside", type=int, default=1024)
-    ap.add_argument("--part-batch", type=int, default=8)
+    ap.add_argument("--part-batch", type=int, default=16,
+                    help="global batch of the sphere-partitioned nside-1024 network (halved until it fits one GPU's memory)")
     ap.add_argument("--model-nside", type=int, default=256)
     ap.add_argument("--model-batch", type=int, default=16)
     ap.add_argument("--nside", type=int, default=256)
@@ -344,6 +345,8 @@ def graph_replay_timing(train_step, params, opt, n, device, world):
                     for k, v in s_.items():
                         opt.state[p][k].copy_(v)
 
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()   # the capture allocates from its own pool: give the eager pool's cached blocks back first
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):   # warm-up on a side stream: no autograd node may be tied to the legacy stream
@@ -604,6 +607,14 @@ def model_train_partitioned_bench(args, mode, device, rank, world):
 
     nside, Bm = args.part_nside, args.part_batch
     npix = 12 * nside * nside
+    # the whole batch must fit ONE GPU (N = 1 is the whole sphere on one GPU): measured peak 4.9 GB per nside-1024 sample
+    # (156 GB at batch 32: activations kept for the backward + the top layer's basis workspace); the same decision on
+    # every rank and at every N, so that the scaling curve is one global batch throughout
+    per_sample = 5.0e9 * (nside / 1024.0) ** 2
+    cap = 0.8 * torch.cuda.get_device_properties(device).total_memory
+    while Bm > 1 and Bm * per_sample > cap:
+        Bm //= 2
+    torch.cuda.reset_peak_memory_stats(device)
     t0 = time.time()
     torch.manual_seed(11)
     model = partition.PartitionedHealpyGCNN(nside, np.arange(npix), _c5_layers(mode, partition.PartitionedMean()),
@@ -657,7 +668,10 @@ def model_train_partitioned_bench(args, mode, device, rank, world):
     ex_ms = dsd.allreduce_max(ex_ms / 2, device)
     ar_ms = dsd.allreduce_max(ar_ms, device)
     del loss
-    graph_t = None if args.no_graph else graph_replay_timing(train_step, params, opt, n, device, world)
+    # a captured step allocates from its own memory pool, next to the eager pool's working set: only when both fit
+    fits_twice = 2.2 * torch.cuda.max_memory_allocated(device) < cap
+    graph_t = graph_replay_timing(train_step, params, opt, n, device, world) if (fits_twice and not args.no_graph) else \
+        {"skipped": "the step's working set does not fit twice (eager pool + graph pool)", "validated": False}
     eager_ms = ms
     if graph_t is not None and graph_t.get("validated"):
         ms = graph_t["ms_per_step"]
@@ -667,7 +681,7 @@ def model_train_partitioned_bench(args, mode, device, rank, world):
     n_params = int(sum(p.numel() for p in params))
     out = {"metric": "HealpyGCNN train maps/s, nside %d, one sphere partitioned over the ranks" % nside,
            "value": Bm / (ms * 1e-3), "unit": "maps/s", "ms_per_step": ms, "global_batch": Bm, "n_gpus": world,
-           "scaling": "strong", "parameters": n_params,
+           "scaling": "strong", "parameters": n_params, "peak_memory_GB": torch.cuda.max_memory_allocated(device) / 1e9,
            "execution": "CUDA graph replay of the whole step (validated against eager)" if ms != eager_ms else "eager",
            "eager_ms_per_step": eager_ms, "cuda_graph": graph_t,
            "time_split_ms": {"halo_exchanges": ex_ms, "halo_exchanges_per_step": ex_n // 2, "grad_allreduce": ar_ms,

@@ -165,8 +165,8 @@ class _BnBiasAct(torch.autograd.Function):
                 sums = torch.empty(2 * F + 1, device=dev, dtype=torch.float64)
                 nat.check(lib.ds_bn_stats(B, M, F, r0, r1, nat.ptr(z), nat.ptr(sums), nat.ptr(ws), st), "ds_bn_stats")
                 if do_sync:  # the global row count travels with the sums and stays on the device (no host sync)
-                    sums[2 * F] = count
-                    dist.all_reduce(sums, group=group)
+                    sums[2 * F:].fill_(count)  # (a fill kernel: an indexed assignment of a Python float is a host copy,
+                    dist.all_reduce(sums, group=group)  # which a CUDA-graph capture refuses)
                     count_dev = sums[2 * F:]
             nat.check(
                 lib.ds_bn_bias_act_forward(B, M, F, nat.ptr(z), nat.ptr(sums), count, nat.ptr(count_dev), float(eps),

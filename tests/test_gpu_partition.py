@@ -83,7 +83,7 @@ def test_partitioned_chebyshev_two_gpus(tmp_path, mode, tol):
         assert ey <= tol and edx <= tol and edw <= tol, (mode, r, ey, edx, edw)
 
 
-def _net_worker(rank, world, port, out_dir):
+def _net_worker(rank, world, port, out_dir, use_bn=False):
     import torch.distributed as dist
 
     import deepsphere
@@ -100,8 +100,10 @@ def _net_worker(rank, world, port, out_dir):
 
     def layers(head):
         return [hl.HealpyPseudoConv(p=1, Fout=8, activation="elu"),
-                hl.HealpyChebyshev(K=5, Fout=16, use_bias=True, activation="elu", mode="tf32"),
-                hl.HealpyPool(p=1, pool_type="AVG"), hl.HealpyChebyshev(K=3, Fout=8), head, kc.Dense(2)]
+                hl.HealpyChebyshev(K=5, Fout=16, use_bias=True, use_bn=use_bn, activation="elu", mode="tf32"),
+                hl.HealpyPool(p=1, pool_type="AVG"),
+                hl.HealpyChebyshev(K=3, Fout=8, use_bias=use_bn, use_bn=use_bn, activation="tanh" if use_bn else None), head,
+                kc.Dense(2)]
 
     torch.manual_seed(0)
     whole = deepsphere.HealpyGCNN(nside=nside, indices=np.arange(npix), layers=layers(kc.Lambda(lambda v: v.mean(dim=1))))
@@ -143,6 +145,19 @@ def test_partitioned_healpy_gcnn_two_gpus(tmp_path):
     import torch.multiprocessing as mp
 
     mp.spawn(_net_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r in (0, 1):
+        errs = np.load(tmp_path / f"net{r}.npy")
+        assert errs.max() <= 5e-3, errs
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_partitioned_healpy_gcnn_two_gpus_batchnorm(tmp_path):
+    """The same with use_bn=True in the graph layers (round 2): the BatchNormalization statistics of a partitioned layer are
+    those of the whole sphere (own rows of every rank, ds_bn_* row range + one all-reduce of the 2F + 1 sums per direction),
+    so output, input gradient and every weight gradient still equal the whole-sphere network."""
+    import torch.multiprocessing as mp
+
+    mp.spawn(_net_worker, args=(2, _free_port(), str(tmp_path), True), nprocs=2, join=True)
     for r in (0, 1):
         errs = np.load(tmp_path / f"net{r}.npy")
         assert errs.max() <= 5e-3, errs
