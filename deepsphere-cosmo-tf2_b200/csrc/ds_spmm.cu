@@ -345,7 +345,12 @@ int launch_spmm(const SparseDev& S, int64_t B, int64_t F, const float* in, float
   const int64_t max_blocks = (int64_t)num_sms() * 3 * 8;
   const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>(B * units_per_b, max_blocks));
   const int threads = 256;
-  if (vec4 && F <= 128 && S.M * (F / 4) < (int64_t)1 << 31 && S.Wp <= 64) {
+  // small problems (the closure sub-problem of the irregular lattice tiles, the coarse levels of a network: the whole
+  // hop lives in L2) take the plain gather kernel: the bulk-copy ring of spmm_tile_kernel costs ~19 us per launch in
+  // pipeline fill alone (32 such launches were 10 % of a HealpyGCNN training step, profiles/r2p_launches_model_train.csv)
+  static const int64_t small_bytes = [] { const char* e = getenv("DEEPSPHERE_SPMM_SMALL_BYTES"); return e ? atoll(e) : (int64_t)(24 << 20); }();
+  const bool small = B * S.M * F * 4 <= small_bytes;
+  if (vec4 && F <= 128 && S.M * (F / 4) < (int64_t)1 << 31 && S.Wp <= 64 && !small) {
     // unit: rows so that one slab is <= 32 KB; stages from the shared-memory budget
     int U = 1024;
     while (U > 16 && (int64_t)U * F * 4 > 32768) U >>= 1;

@@ -30,5 +30,13 @@ def rel_err(a, ref):
     return float(np.abs(a - ref).max() / max(np.abs(ref).max(), 1e-300))
 
 
+def rel_l2(a, ref):
+    """||a - ref||_2 / ||ref||_2 — a second, scale-aware parity metric next to the max-norm one (the max-norm
+    ratio is lenient where most of a tensor is small next to its largest element)."""
+    a = np.asarray(a, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    return float(np.linalg.norm((a - ref).ravel()) / max(np.linalg.norm(ref.ravel()), 1e-300))
+
+
 CONV_CASES = ["cheb_ref3x3", "mono_ref3x3", "cheb_eye192", "cheb_nside4_k8", "mono_nside4_k8", "cheb_nside8_k20",
               "cheb_masked16_k20", "cheb_masked16_k8"]

@@ -6,7 +6,7 @@ import torch
 from deepsphere import _native as nat
 from deepsphere import gnn_layers, healpix as hpx, utils
 from deepsphere.graph import SphereHealpix
-from helpers import orc, rel_err
+from helpers import orc, rel_err, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -111,6 +111,10 @@ def test_fused_lattice_conv_matches_oracle(mode, tol, cls, nside, B, Fin, Fout, 
     assert rel_err(xt.grad.cpu().numpy(), xr.grad.numpy()) <= tol
     assert rel_err(layer.kernel.grad.cpu().numpy(), wr.grad.numpy()) <= tol
     assert rel_err(layer.bias.grad.cpu().numpy(), br.grad.numpy()) <= tol
+    # the scale-aware metric as well (errors relative to the tensor's norm, not to its largest element)
+    assert rel_l2(y.detach().cpu().numpy(), yr.detach().numpy()) <= tol
+    assert rel_l2(xt.grad.cpu().numpy(), xr.grad.numpy()) <= tol
+    assert rel_l2(layer.kernel.grad.cpu().numpy(), wr.grad.numpy()) <= tol
 
 
 def test_fused_conv2_masked_sky_tf32():

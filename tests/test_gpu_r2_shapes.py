@@ -7,7 +7,7 @@ from scipy import sparse
 
 from deepsphere import gnn_layers, healpix as hpx, utils
 from deepsphere.graph import SphereHealpix
-from helpers import orc, rel_err
+from helpers import orc, rel_err, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -51,6 +51,8 @@ def test_c3_masked_survey_layers_match_oracle(k):
         yr = orc.torch_cpu_layer(xr, Lt, wr, K, rec, bias=br, activation="elu")
         yr.backward(torch.tensor(dy))
         assert rel_err(y.detach().cpu().numpy(), yr.detach().numpy()) <= 1e-5, (k, rec)
+        assert rel_l2(y.detach().cpu().numpy(), yr.detach().numpy()) <= 1e-5, (k, rec)
+        assert rel_l2(xt.grad.cpu().numpy(), xr.grad.numpy()) <= 1e-5, (k, rec)
         assert rel_err(xt.grad.cpu().numpy(), xr.grad.numpy()) <= 1e-5, (k, rec)
         assert rel_err(layer.kernel.grad.cpu().numpy(), wr.grad.numpy()) <= 1e-5, (k, rec)
         assert rel_err(layer.bias.grad.cpu().numpy(), br.grad.numpy()) <= 1e-5, (k, rec)
@@ -119,6 +121,8 @@ def test_tf32_relu_gradients_with_masked_kinks(K):
     y = layer(xt)
     y.backward(torch.tensor(dy, dtype=torch.float32, device="cuda"))
     assert rel_err(y.detach().cpu().numpy(), torch.relu(z).detach().numpy()) <= 1e-3
+    assert rel_l2(y.detach().cpu().numpy(), torch.relu(z).detach().numpy()) <= 1e-3
+    assert rel_l2(xt.grad.cpu().numpy(), xr.grad.numpy()) <= 1e-3
     assert rel_err(xt.grad.cpu().numpy(), xr.grad.numpy()) <= 1e-3
     assert rel_err(layer.kernel.grad.cpu().numpy(), wr.grad.numpy()) <= 1e-3
     assert rel_err(layer.bias.grad.cpu().numpy(), br.grad.numpy()) <= 1e-3

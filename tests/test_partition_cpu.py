@@ -180,9 +180,12 @@ def _net_worker(rank, world, port, out_dir, masked):
     yp = part(xo, training=True)
     ((yw - t) ** 2).sum().backward()
     ((yp - t) ** 2).sum().backward()
-    # graph-layer weights hold partial sums over own rows; the Dense head sees replicated activations on every rank
+    # graph-layer weights hold partial sums over own rows; the Dense head sees replicated activations on every rank:
+    # PartitionedHealpyGCNN.allreduce_gradients() sums exactly the row-local ones
     graph_params = [p_ for m in part.layers_use if isinstance(m, partition.PartitionedGraphConv) for p_ in m.parameters()]
-    dsd.allreduce_gradients(graph_params, average=False)
+    assert [id(q) for q in part.row_local_parameters()] == [id(q) for q in graph_params]
+    assert len(part.replicated_parameters()) == 2 and len(part.row_local_parameters()) + 2 == len(pp)
+    part.allreduce_gradients()
     errs = [float((yp - yw).abs().max()), float((xo.grad - xw.grad[:, b:e]).abs().max())]
     errs += [float((c.grad.double() - a.grad.double()).abs().max()) for a, c in zip(pw, pp)]
     halo = [m.plan.halo_rows for m in part.layers_use if isinstance(m, partition.PartitionedGraphConv)]
