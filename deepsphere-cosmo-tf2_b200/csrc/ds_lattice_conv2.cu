@@ -92,6 +92,14 @@ static_assert(C2_NLOAD % 32 == 0 && (2 * C2_LW * C2_LW) % C2_NLOAD == 0, "gather
 #define C2_IO_DRAIN 0
 #endif
 static_assert(!C2_IO_DRAIN || (C2_NCW == 4 && C2_NLOAD == 96), "IO-side drain: warps 4..7 must cover the four TMEM lane quarters");
+// 1 = the per-hop basis stores of a launch with `out` (the backward-data launch hands U_k = T_k(L~) dz to the weight-gradient
+// kernel: 4A bytes; forward 14.3 ms, the same launch with the stores 20.5 ms) are done by the GATHER warps from the exchange
+// buffer - every hop's T_k of all positions is in shared memory anyway - instead of by the compute threads from registers
+// (9 row look-ups, 9 address computations and 9 scattered 16-byte stores per thread and hop in the hop's dependency chain).
+#ifndef C2_IO_OUT
+#define C2_IO_OUT 0
+#endif
+
 constexpr int C2_NCOMP = 32 * C2_NCW, C2_THREADS = C2_NCOMP + 32 + C2_NLOAD;
 constexpr int C2_NEPI = C2_NCW >= 8 ? 8 : 4;  // warps that drain the accumulators (TMEM lane quarter = warp % 4)
 // registers per CTA (two CTAs per SM): the pool is what the launch allocates, threads x (registers per thread of the
@@ -131,6 +139,9 @@ struct Conv2Args {
 
 struct Conv2Ctl {
   uint64_t in_full[2], in_empty[2], w_full[2], item_done[2], hop_full[2], mma_done[2], acc_full, acc_empty;
+#if C2_IO_OUT
+  uint64_t out_done[2];  // the gather warps have copied the hop in X[p] to global memory (launches with `out`)
+#endif
 #if C2_SPLIT_BAR
   uint64_t hop_ready[2];
 #endif
@@ -291,6 +302,8 @@ __device__ __forceinline__ constexpr int dir_of(int dr, int dc) {
 #define C2_LOOP 0
 #endif
 static_assert(!C2_LOOP || (C2_FFMA2 && !C2_SPLIT_BAR && !C2_SKIP_OUTER), "looped hops: packed arithmetic, one barrier per hop");
+static_assert(!C2_IO_OUT || (C2_FFMA2 && C2_CPT == 4 && C2_BC == 3 && !C2_IO_DRAIN && !C2_SPLIT_BAR && !C2_LOOP),
+              "IO-side basis stores: implemented for the default block shape and hop sequence");
 #if C2_SYMW
 // the weight of the tap (r, cc) <- (sr, sc), both inside the block, is read from the OTHER pixel's table entry
 __host__ __device__ constexpr bool sym_other(int r, int cc, int sr, int sc) { return (sr * C2_BC + sc) < (r * C2_BC + cc); }
@@ -428,6 +441,9 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
       ptx::mbar_init(&ctl->hop_ready[i], C2_NCOMP);
 #endif
       ptx::mbar_init(&ctl->mma_done[i], 1);
+#if C2_IO_OUT
+      ptx::mbar_init(&ctl->out_done[i], C2_NLOAD);
+#endif
     }
     ptx::mbar_init(&ctl->acc_full, 1);
     ptx::mbar_init(&ctl->acc_empty, C2_IO_DRAIN ? 4 : C2_NEPI);
@@ -557,7 +573,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
       const int64_t b_end = min(a.B, b_begin + b_per);
       if (b_begin >= b_end) continue;
       const int32_t* tpix = a.pix + (size_t)tile * C2_P;
-      if (has_out) {  // own-pixel rows of this tile for the basis stores
+      if (has_out && !C2_IO_OUT) {  // own-pixel rows of this tile for the basis stores
         ptx::named_bar_sync(1, C2_NCOMP);
         for (int p = tid; p < C2_P; p += C2_NCOMP) {
           const int j = p / C2_LW, c = p % C2_LW;
@@ -694,6 +710,10 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
             if (!skp) hop_perimeter<(CHEB && s == 1), rot_of_hop(s)>(acc, w, src + own0);
             if (probe) pd[1] = clock64();
             if (!mma_ok) ptx::mbar_wait(&ctl->mma_done[p], (cnt_done[p] - 1) & 1);
+#if C2_IO_OUT
+            // ... and the gather warps that copied X[p]'s previous contents to the basis tensor
+            if (has_out && cnt_done[p] > 0) ptx::mbar_wait(&ctl->out_done[p], (cnt_done[p] - 1) & 1);
+#endif
             if (s == 1 && last_bar >= 0) {  // previous item's last phase: everybody has finished reading X[0] (a warp that
                                             // sits this hop out waits too: its arrival must not land in that phase)
 #if C2_SPLIT_BAR
@@ -720,7 +740,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
             ptx::mbar_arrive(&ctl->hop_full[p]);
 #endif
             if (probe) pd[3] = clock64();
-            float* outp = a.out[s - 1];
+            float* outp = C2_IO_OUT ? nullptr : a.out[s - 1];
             if (outp != nullptr && !skp) {
               cvec* ob = reinterpret_cast<cvec*>(outp + (b * a.M * a.F + c * C2_FC)) + q * C2_VP + h;
 #pragma unroll
@@ -1011,6 +1031,41 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
     const int col = col_of_slot(inpos);
     const int FV = a.F / 4;
     uint32_t it = 0;
+#if C2_IO_OUT
+    // Basis stores from the exchange buffer.  Unit u = t + 96 k (k < 6, u < 512): channel quad u & 1 (two consecutive
+    // lanes write the 32 contiguous bytes of a pixel's chunk), centre position u >> 1 = 16 jj + cc.  The copies of item
+    // i - 1 are served after the gather of item i (prefetch distance one item); `prev_*` is that item.
+    const bool io_out = a.out[0] != nullptr || a.out[1] != nullptr || a.out[2] != nullptr || a.out[3] != nullptr;
+    uint32_t chh[2] = {0, 0};
+    int prev_rows[6] = {-1, -1, -1, -1, -1, -1};
+    int64_t prev_b = 0;
+    int prev_c = 0;
+    bool prev_valid = false;
+    int xoff[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int u = t + C2_NLOAD * k, pi = (u >> 1) & 255;
+      xoff[k] = (u & 1) * C2_PL + (C2_H + pi / C2_T + 1) * C2_LW + slot_of_col(C2_H + pi % C2_T);
+    }
+    auto serve = [&]() {  // all hops of the previous item: wait for the hop, copy its centre to out[s - 1], release X[p]
+      for (int s = 1; s <= nsteps; ++s) {
+        const int p = (s - 1) & 1;
+        ptx::mbar_wait_backoff(&ctl->hop_full[p], chh[p] & 1, (uint32_t)a.sleep_ld);
+        chh[p]++;
+        float* outp = s == 1 ? a.out[0] : (s == 2 ? a.out[1] : (s == 3 ? a.out[2] : a.out[3]));
+        if (outp != nullptr) {
+          const float4* X = bufs + (size_t)(2 + p) * C2_BUF;
+          float4* ob = reinterpret_cast<float4*>(outp + (prev_b * a.M * a.F + prev_c * C2_FC)) + q;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            const int row = prev_rows[k];
+            if (row >= 0) __stcs(ob + (int64_t)row * FV, X[xoff[k]]);
+          }
+        }
+        ptx::mbar_arrive(&ctl->out_done[p]);
+      }
+    };
+#endif
 #if C2_IO_DRAIN
     // groups (tile, b) whose last chunk has been passed, waiting for their drain: slot = group index & 3.  A group is
     // drained two items after its closing item: by then the next two items are gathered (the compute warps never wait
@@ -1038,6 +1093,15 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
       int rows[C2_LW / 2];
 #pragma unroll
       for (int k = 0; k < C2_LW / 2; ++k) rows[k] = __ldg(a.pix + (size_t)tile * C2_P + (2 * k + r0) * C2_LW + col);
+#if C2_IO_OUT
+      int orow[6];  // rows of the basis tensor of this thread's 6 copy units (own pixels of this tile)
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const int u = t + C2_NLOAD * k, pi = u >> 1;
+        orow[k] = (io_out && u < 2 * C2_T * C2_T)
+                      ? __ldg(a.pix + (size_t)tile * C2_P + (C2_H + pi / C2_T) * C2_LW + C2_H + pi % C2_T) : -1;
+      }
+#endif
 #if C2_IO_DRAIN
       int erow[3];
 #pragma unroll
@@ -1064,6 +1128,14 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
             ptx::fence_proxy_async_smem();
             ptx::mbar_arrive(&ctl->in_full[st]);
           }
+#if C2_IO_OUT
+          if (io_out) {
+            if (prev_valid) serve();
+#pragma unroll
+            for (int k = 0; k < 6; ++k) prev_rows[k] = orow[k];
+            prev_b = b; prev_c = c; prev_valid = true;
+          }
+#endif
 #if C2_IO_DRAIN
           if (c == n_chunks - 1) {
             const int sl = g_closed & 3;
@@ -1079,6 +1151,9 @@ __global__ void __launch_bounds__(C2_THREADS, 2) lattice_conv2_kernel(const Conv
     }
 #if C2_IO_DRAIN
     while (g_drained < g_closed) drain(g_drained++);
+#endif
+#if C2_IO_OUT
+    if (io_out && prev_valid) serve();
 #endif
   }
   ptx::tc_fence_before_sync();

@@ -75,6 +75,16 @@ SIGNATURES = {
     "ds_halo_pack": (ctypes.c_int, [_i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr]),
     "ds_halo_assemble": (ctypes.c_int, [_i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "ds_halo_reduce": (ctypes.c_int, [_i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "ds_comm_load_nccl": (ctypes.c_int, [ctypes.c_char_p]),
+    "ds_comm_unique_id": (ctypes.c_int, [_ptr]),
+    "ds_comm_create": (ctypes.c_int, [_i32, _i32, _ptr, ctypes.POINTER(_ptr)]),
+    "ds_comm_destroy": (ctypes.c_int, [_ptr]),
+    "ds_comm_allreduce_sum": (ctypes.c_int, [_ptr, _ptr, _i64, _i32, _ptr]),
+    "ds_comm_alltoallv": (ctypes.c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "ds_halo_exchange": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "ds_halo_exchange_backward": (
+        ctypes.c_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]
+    ),
     "ds_pconvT_forward": (ctypes.c_int, [_i64, _i64, _i64, _i64, _i32, _ptr, _ptr, _ptr, _i32, _ptr, _i32, _ptr]),
     "ds_pconvT_backward_workspace_elems": (_i64, [_i64, _i64, _i64, _i64, _i32, _i32]),
     "ds_pconvT_backward": (

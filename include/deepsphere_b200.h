@@ -54,6 +54,7 @@ extern "C" {
 #define DS_POOL_AVG 1
 
 typedef struct ds_plan ds_plan_t;
+typedef struct ds_comm ds_comm_t; /* an NCCL communicator of the ranks that share one sphere / one batch */
 
 int ds_abi_version(void);
 /* message of the calling thread's last error ("" if none) */
@@ -214,6 +215,30 @@ int ds_halo_assemble(int64_t B, int64_t n_own, int64_t n_ext, int64_t own_start,
                      const int32_t* pos, const float* x_own, const float* recv, float* x_ext, void* stream);
 int ds_halo_reduce(int64_t B, int64_t n_own, int64_t n_ext, int64_t own_start, int64_t F, const int32_t* row_slot_ptr,
                    const int32_t* slots, const float* g_ext, const float* recv, float* g_own, void* stream);
+
+/* ---- ds_comm_*: thin wrappers over NCCL, so that a binder without a collective library of its own can
+ * run the multi-GPU path through this C-ABI alone.  NCCL is loaded at run time (ds_comm_load_nccl(path), or
+ * DEEPSPHERE_NCCL_LIB, or the loader's default "libnccl.so.2"): nothing here is needed on a single GPU.
+ *   ds_comm_unique_id: rank 0 creates the 128-byte id and hands it to the others out of band; ds_comm_create: every rank.
+ *   ds_comm_allreduce_sum: in place, n floats (is_double = 0) or doubles (1): weight gradients, the 2F + 1 BatchNorm sums.
+ *   ds_comm_alltoallv: peer blocks in rank order, counts in floats (grouped ncclSend / ncclRecv).
+ *   ds_halo_exchange / ds_halo_exchange_backward: ds_halo_pack -> all-to-all -> ds_halo_assemble (resp. -> ds_halo_reduce)
+ *   in ONE call; `*_rows_per_peer` [world] split the concatenated row lists; workspace = (rows sent + rows received) * B * F
+ *   floats. */
+int ds_comm_load_nccl(const char* path /* nullable */);
+int ds_comm_unique_id(char* id128);
+int ds_comm_create(int32_t world, int32_t rank, const char* id128, ds_comm_t** out);
+int ds_comm_destroy(ds_comm_t* comm);
+int ds_comm_allreduce_sum(ds_comm_t* comm, void* buf, int64_t n, int32_t is_double, void* stream);
+int ds_comm_alltoallv(ds_comm_t* comm, const float* send, const int64_t* send_counts, float* recv,
+                      const int64_t* recv_counts, void* stream);
+int ds_halo_exchange(ds_comm_t* comm, int64_t B, int64_t n_own, int64_t n_ext, int64_t own_start, int64_t F,
+                     const int32_t* send_rows, const int64_t* send_rows_per_peer, const int32_t* recv_pos,
+                     const int64_t* recv_rows_per_peer, const float* x_own, float* x_ext, float* workspace, void* stream);
+int ds_halo_exchange_backward(ds_comm_t* comm, int64_t B, int64_t n_own, int64_t n_ext, int64_t own_start, int64_t F,
+                              const int64_t* send_rows_per_peer, const int32_t* recv_pos,
+                              const int64_t* recv_rows_per_peer, const int32_t* row_slot_ptr, const int32_t* slots,
+                              const float* g_ext, float* g_own, float* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -94,6 +94,8 @@ def conv2_problem():
     ("bc6loop", ["-DC2_LOOP=1", "-DC2_CPT=2", "-DC2_BC=6", "-DC2_SYMW=1", "-DC2_PROBE=0"]),
     # the accumulator drain on the gather warps + one extra warp (288 threads)
     ("iodrain", ["-DC2_IO_DRAIN=1", "-DC2_SYMW=1"]),
+    # the per-hop basis stores of a launch with `out` done by the gather warps from the exchange buffer
+    ("ioout", ["-DC2_IO_OUT=1"]),
 ])
 def test_fused_lattice_kernel_on_the_host_emulator(tmp_path, conv2_problem, variant, defines):
     import numpy as np
@@ -117,7 +119,7 @@ def test_fused_lattice_kernel_on_the_host_emulator(tmp_path, conv2_problem, vari
     for ci, (name, K, B, F, N, act, has_bias, b_split, grid, want_basis) in enumerate(cases):
         if F == 64 and variant not in ("default", "br2all", "bc6", "loop", "iodrain"):
             continue  # the large case only for the measured kernel and the most changed variant (CPU suite budget)
-        if K <= 3 and variant not in ("default", "split", "br2all", "bc6", "loop", "bc6loop", "iodrain"):
+        if K <= 3 and variant not in ("default", "split", "br2all", "bc6", "loop", "bc6loop", "iodrain", "ioout"):
             continue  # 1- and 2-hop launches: only where the hop sequence itself differs
         bwd = name.endswith("-bwd")
         name = name.split("-")[0]
@@ -171,6 +173,7 @@ def test_fused_lattice_kernel_on_the_host_emulator(tmp_path, conv2_problem, vari
     ("bc6", ["-DC2_CPT=2", "-DC2_BC=6", "-DC2_SYMW=1", "-DC2_PROBE=0"]),
     ("loop", ["-DC2_LOOP=1", "-DC2_PROBE=0"]),
     ("iodrain", ["-DC2_IO_DRAIN=1", "-DC2_SYMW=1"]),
+    ("ioout", ["-DC2_IO_OUT=1"]),
 ])
 def test_fused_lattice_kernel_protocol_under_thread_sanitizer(tmp_path, conv2_problem, variant, defines):
     """The barrier protocol of the fused kernel under ThreadSanitizer: every emulated mbarrier is its own lock, so the

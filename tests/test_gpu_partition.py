@@ -216,3 +216,82 @@ def test_halo_kernels_single_gpu_simulated_ranks(F):
                                      nat.ptr(g_exts[r]), nat.ptr(got), nat.ptr(g_own), st))
         torch.cuda.synchronize()
         assert float((g_own.double() - g_global[:, b0:e0]).abs().max()) <= 1e-5 * float(g_global.abs().max())
+
+
+def _comm_worker(rank, world, id_path, out_dir):
+    """ds_comm_* + ds_halo_exchange(_backward) through ctypes alone (no torch.distributed): what a TF binder would call."""
+    import ctypes
+    import glob
+    import time
+
+    from deepsphere import _native as nat
+    from deepsphere.graph import SphereHealpix
+    from deepsphere.partition import HaloPlan
+
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    lib = nat.lib()
+    cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so*"))
+    nat.check(lib.ds_comm_load_nccl(cands[0].encode() if cands else None), "ds_comm_load_nccl")
+    idbuf = ctypes.create_string_buffer(128)
+    if rank == 0:
+        nat.check(lib.ds_comm_unique_id(idbuf), "ds_comm_unique_id")
+        with open(id_path + ".tmp", "wb") as f:
+            f.write(idbuf.raw)
+        os.replace(id_path + ".tmp", id_path)
+    else:
+        t0 = time.time()
+        while not os.path.exists(id_path):
+            assert time.time() - t0 < 120
+            time.sleep(0.05)
+        idbuf = ctypes.create_string_buffer(open(id_path, "rb").read(), 128)
+    comm = ctypes.c_void_p()
+    nat.check(lib.ds_comm_create(world, rank, idbuf, ctypes.byref(comm)), "ds_comm_create")
+    g = SphereHealpix(16, k=8)
+    M, B, F = g.L.shape[0], 2, 8
+    plans = [HaloPlan(g.L, 4, r, world, align=M // 48) for r in range(world)]
+    p = plans[rank]
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(B, M, F, generator=gen)
+    g_exts = [torch.randn(B, q.n_ext, F, generator=torch.Generator().manual_seed(10 + r)) for r, q in enumerate(plans)]
+    b0, e0 = p.own[rank]
+    st = nat.current_stream()
+    send_cat, recv_cat, red_ptr, red_slots = p.native(dev)
+    spp = (ctypes.c_int64 * world)(*[len(v) for v in p.send_rows])
+    rpp = (ctypes.c_int64 * world)(*[len(v) for v in p.recv_pos])
+    ws = torch.empty((len(p.send_cat) + len(p.recv_cat)) * B * F + 4, device=dev)
+    x_own = x[:, b0:e0].contiguous().to(dev)
+    x_ext = torch.full((B, p.n_ext, F), float("nan"), device=dev)
+    nat.check(lib.ds_halo_exchange(comm, B, p.n_own, p.n_ext, p.own_start, F, nat.ptr(send_cat), spp, nat.ptr(recv_cat), rpp,
+                                   nat.ptr(x_own), nat.ptr(x_ext), nat.ptr(ws), st), "ds_halo_exchange")
+    torch.cuda.synchronize()
+    err_f = float((x_ext.cpu() - x[:, torch.as_tensor(p.ext)]).abs().max())
+    g_ext = g_exts[rank].to(dev)
+    g_own = torch.empty(B, p.n_own, F, device=dev)
+    nat.check(lib.ds_halo_exchange_backward(comm, B, p.n_own, p.n_ext, p.own_start, F, spp, nat.ptr(recv_cat), rpp,
+                                            nat.ptr(red_ptr), nat.ptr(red_slots), nat.ptr(g_ext), nat.ptr(g_own), nat.ptr(ws), st),
+              "ds_halo_exchange_backward")
+    g_global = torch.zeros(B, M, F, dtype=torch.float64)
+    for q, ge in zip(plans, g_exts):
+        g_global.index_add_(1, torch.as_tensor(q.ext), ge.double())
+    torch.cuda.synchronize()
+    err_b = float((g_own.cpu().double() - g_global[:, b0:e0]).abs().max())
+    v = torch.full((5,), float(rank + 1), device=dev, dtype=torch.float64)
+    nat.check(lib.ds_comm_allreduce_sum(comm, nat.ptr(v), 5, 1, st), "ds_comm_allreduce_sum")
+    torch.cuda.synchronize()
+    err_a = float((v.cpu() - sum(range(1, world + 1))).abs().max())
+    lib.ds_comm_destroy(comm)
+    np.save(os.path.join(out_dir, f"comm{rank}.npy"), np.array([err_f, err_b, err_a]))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_ds_comm_and_halo_exchange_through_the_c_abi_alone(tmp_path):
+    """ds_comm_* (NCCL loaded at run time) + ds_halo_exchange / _backward: the halo exchange of a partitioned layer and the
+    all-reduce as ONE C-ABI call each, driven through ctypes without torch.distributed — forward bit-exact, transposed
+    exchange to fp32 round-off."""
+    import torch.multiprocessing as mp
+
+    mp.spawn(_comm_worker, args=(2, str(tmp_path / "nccl_id"), str(tmp_path)), nprocs=2, join=True)
+    for r in (0, 1):
+        errs = np.load(tmp_path / f"comm{r}.npy")
+        assert errs[0] == 0.0 and errs[1] <= 1e-5 and errs[2] == 0.0, errs
