@@ -24,6 +24,10 @@ for _p in (os.path.join(ROOT, "deepsphere-cosmo-tf2_b200"), ROOT):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+# the package logger mirrors the reference's (INFO lines to stdout while a HealpyGCNN is built): bench.py's stdout is ONE
+# JSON line, so the level goes to WARNING here unless the caller set one
+os.environ.setdefault("DEEPSPHERE_LOG_LEVEL", "3")
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -677,7 +681,11 @@ def model_train_partitioned_bench(args, mode, device, rank, world):
         ms = graph_t["ms_per_step"]
     convs = [l for l in model.layers_use if isinstance(l, partition.PartitionedGraphConv)]
     halo = [{"level_rows_own": int(c.plan.n_own), "halo_rows": int(c.plan.halo_rows), "hops": int(c.plan.n_hops),
+             "channels_in": int(c.layer.kernel.shape[0] // c.layer._n_terms),
              "lattice": int(c.layer._plan.info(device.index or 0)["lattice"])} for c in convs]
+    # bytes this rank RECEIVES per step: every layer's halo rows once in the forward (inputs) and once in the backward
+    # (input gradients travel the other way, same volume)
+    halo_bytes = int(sum(2 * h["halo_rows"] * Bm * h["channels_in"] * 4 for h in halo))
     n_params = int(sum(p.numel() for p in params))
     out = {"metric": "HealpyGCNN train maps/s, nside %d, one sphere partitioned over the ranks" % nside,
            "value": Bm / (ms * 1e-3), "unit": "maps/s", "ms_per_step": ms, "global_batch": Bm, "n_gpus": world,
@@ -688,7 +696,7 @@ def model_train_partitioned_bench(args, mode, device, rank, world):
                              "rest (kernels, optimizer, host launch gaps)": eager_ms - ex_ms - ar_ms,
                              "note": "device time between event pairs in two instrumented EAGER steps"},
            "limiting_collective": None if world == 1 else ("halo all_to_all" if ex_ms >= ar_ms else "gradient all-reduce"),
-           "halo": halo, "host_prep_s": prep_s,
+           "halo": halo, "halo_bytes_per_step_per_rank": halo_bytes, "host_prep_s": prep_s,
            "config": f"nside {nside} ({npix} px): PseudoConv p1 F16 -> [Chebyshev K5 F32 + MAX pool] x4 -> Chebyshev K5 F64 "
                      f"-> AVG pool -> mean -> Dense(2); MSE, Adam; mode {mode}; rank r owns 48/{world} quarter-face blocks"}
     del model, opt, x
