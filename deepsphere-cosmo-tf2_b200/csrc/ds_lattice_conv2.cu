@@ -101,6 +101,12 @@ static_assert(!C2_IO_DRAIN || (C2_NCW == 4 && C2_NLOAD == 96), "IO-side drain: w
 #endif
 
 constexpr int C2_NCOMP = 32 * C2_NCW, C2_THREADS = C2_NCOMP + 32 + C2_NLOAD;
+// setmaxnreg is a WARPGROUP instruction: the four warps of an aligned group of four must all execute the same one.  The
+// compute warps (inc) therefore have to fill whole warpgroups - the 6-warp shape of C2_BR = 2 (round 1, host-emulated only)
+// faults on the B200 (round 2, call 1) - and the IO warps (dec) are exactly one warpgroup.
+#ifndef DS_EMULATE
+static_assert(C2_NCW % 4 == 0 && C2_NLOAD == 96, "compute and IO warps must each fill whole warpgroups (setmaxnreg)");
+#endif
 constexpr int C2_NEPI = C2_NCW >= 8 ? 8 : 4;  // warps that drain the accumulators (TMEM lane quarter = warp % 4)
 // registers per CTA (two CTAs per SM): the pool is what the launch allocates, threads x (registers per thread of the
 // launch bound, a multiple of 8); setmaxnreg moves it between the roles.  Overridable for the variant builds.

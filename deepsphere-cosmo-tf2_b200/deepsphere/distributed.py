@@ -126,11 +126,13 @@ def allreduce_sum_autograd(x, group=None):
     return _AllReduceSum.apply(x, group)
 
 
-def batch_statistics(x, dims, group=None):
+def batch_statistics(x, dims, group=None, sync=True):
     """Per-channel mean and (biased) variance of `x` over `dims` AND over all ranks: with the batch
     sharded over GPUs, BatchNormalization (gnn_layers.py:53, 152-153) must see the statistics of the global batch
     to reproduce the single-device reference.  One all-reduce of [count, sum, sum of squares] (2F + 1 floats)."""
-    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+    # `sync=False`: local statistics even under an initialised process group (a replicated model that the ranks do not
+    # run in lock-step would otherwise dead-lock in the all-reduce, ADVICE r1)
+    if not sync or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return x.mean(dim=dims), x.var(dim=dims, unbiased=False)
     n = 1
     for d in dims:

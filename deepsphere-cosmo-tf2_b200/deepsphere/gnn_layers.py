@@ -192,6 +192,7 @@ class _GraphConvBase(Model):
             if self._bn_rows is not None:
                 raise nat.NativeError("BatchNormalization over a row range (sphere-partitioned layer) runs in the CUDA "
                                       "kernels only (ds_bn_*): CUDA tensors and a named activation are required")
+            self.bn.sync_group = self._bn_sync
             x = self.bn(x, training=training)
         if self._act_id is not None:
             return _ops.bias_act(x, bias, self._act_id)

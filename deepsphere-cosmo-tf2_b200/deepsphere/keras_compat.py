@@ -375,6 +375,9 @@ class BatchNormalization(Model):
         if axis != -1:
             raise NotImplementedError("BatchNormalization shim supports axis=-1 only")
         self.momentum, self.epsilon, self.center, self.scale = momentum, epsilon, center, scale
+        # statistics of the GLOBAL batch when a process group is initialised (True), of this process only (False), or
+        # over a given group
+        self.sync_group = True
 
     def build(self, input_shape):
         F = int(input_shape[-1])
@@ -391,7 +394,8 @@ class BatchNormalization(Model):
             # batch sharded over ranks: statistics of the GLOBAL batch (one small all-reduce), see distributed.py
             from .distributed import batch_statistics
 
-            mean, var = batch_statistics(x, dims)
+            mean, var = batch_statistics(x, dims, group=None if self.sync_group in (True, False) else self.sync_group,
+                                         sync=self.sync_group is not False)
             with torch.no_grad():
                 self.moving_mean.mul_(self.momentum).add_(mean.detach() * (1 - self.momentum))
                 self.moving_variance.mul_(self.momentum).add_(var.detach() * (1 - self.momentum))

@@ -79,13 +79,9 @@ def conv2_problem():
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
 @pytest.mark.parametrize("variant,defines", [
     ("default", []),
-    ("br2", ["-DC2_BR=2"]),
     ("split", ["-DC2_SPLIT_BAR=1"]),
-    ("epipipe", ["-DC2_EPI_PIPE=1"]),
     ("symw", ["-DC2_SYMW=1"]),
     ("br3all", ["-DC2_SYMW=1", "-DC2_EPI_PIPE=1", "-DC2_PROBE=0", "-DC2_SPLIT_BAR=1"]),
-    ("br2all", ["-DC2_BR=2", "-DC2_SYMW=1", "-DC2_EPI_PIPE=1", "-DC2_PROBE=0", "-DC2_SPLIT_BAR=1",
-                "-DC2_REGS_COMPUTE=128", "-DC2_REGS_IO=32"]),
     # round 2: two channels per thread (8 compute warps), and the 3 x 6 pixel block with the scalar diagonal
     ("cpt2", ["-DC2_CPT=2", "-DC2_SYMW=1", "-DC2_PROBE=0"]),
     ("bc6", ["-DC2_CPT=2", "-DC2_BC=6", "-DC2_SYMW=1", "-DC2_PROBE=0"]),
@@ -117,9 +113,9 @@ def test_fused_lattice_kernel_on_the_host_emulator(tmp_path, conv2_problem, vari
         ("Chebyshev", 5, 1, 64, 64, 1, True, 1, 3, False),      # the bench layer's shape: 8 chunks, 192 TMEM columns
     ]
     for ci, (name, K, B, F, N, act, has_bias, b_split, grid, want_basis) in enumerate(cases):
-        if F == 64 and variant not in ("default", "br2all", "bc6", "loop", "iodrain"):
+        if F == 64 and variant not in ("default", "bc6"):
             continue  # the large case only for the measured kernel and the most changed variant (CPU suite budget)
-        if K <= 3 and variant not in ("default", "split", "br2all", "bc6", "loop", "bc6loop", "iodrain", "ioout"):
+        if K <= 3 and variant not in ("default", "split", "bc6", "loop", "bc6loop", "iodrain", "ioout"):
             continue  # 1- and 2-hop launches: only where the hop sequence itself differs
         bwd = name.endswith("-bwd")
         name = name.split("-")[0]
@@ -168,8 +164,6 @@ def test_fused_lattice_kernel_on_the_host_emulator(tmp_path, conv2_problem, vari
 @pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
 @pytest.mark.parametrize("variant,defines", [
     ("default", []),
-    ("br2all", ["-DC2_BR=2", "-DC2_SYMW=1", "-DC2_EPI_PIPE=1", "-DC2_PROBE=0", "-DC2_SPLIT_BAR=1",
-                "-DC2_REGS_COMPUTE=128", "-DC2_REGS_IO=32"]),
     ("bc6", ["-DC2_CPT=2", "-DC2_BC=6", "-DC2_SYMW=1", "-DC2_PROBE=0"]),
     ("loop", ["-DC2_LOOP=1", "-DC2_PROBE=0"]),
     ("iodrain", ["-DC2_IO_DRAIN=1", "-DC2_SYMW=1"]),
