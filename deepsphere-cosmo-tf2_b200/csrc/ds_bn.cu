@@ -89,13 +89,18 @@ __global__ void __launch_bounds__(BN_THREADS) bn_partial_kernel(int64_t B, int64
   }
 }
 
-__global__ void bn_reduce_kernel(int blocks, int64_t F, const double* __restrict__ partial, double* __restrict__ sums) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // 0 .. 2F
+// sums[i] = sum over the blocks' partials, one WARP per output i (fixed lane assignment + shuffle tree: deterministic)
+__global__ void __launch_bounds__(256) bn_reduce_kernel(int blocks, int64_t F, const double* __restrict__ partial,
+                                                        double* __restrict__ sums) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);  // 0 .. 2F
   if (i >= 2 * F) return;
   const int64_t which = i / F, ch = i - which * F;
   double acc = 0.0;
-  for (int k = 0; k < blocks; ++k) acc += partial[((int64_t)k * 2 + which) * F + ch];
-  sums[i] = acc;
+  for (int k = lane; k < blocks; k += 32) acc += partial[((int64_t)k * 2 + which) * F + ch];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) sums[i] = acc;
 }
 
 // mean / rstd from the (all-reduced) sums, moving statistics, and the affine form of the normalisation
@@ -191,7 +196,7 @@ int bn_sums(int64_t B, int64_t M, int64_t F, int64_t r0, int64_t r1, const float
   const int blocks = bn_blocks(B * (r1 - r0) * F, F);
   bn_partial_kernel<MODE><<<blocks, BN_THREADS, 0, st>>>(B, M, F, r0, r1, z, y, dy, mean_rstd, act, workspace);
   DS_LAUNCHED();
-  bn_reduce_kernel<<<(unsigned)((2 * F + 127) / 128), 128, 0, st>>>(blocks, F, workspace, sums);
+  bn_reduce_kernel<<<(unsigned)((2 * F + 7) / 8), 256, 0, st>>>(blocks, F, workspace, sums);
   DS_LAUNCHED();
   return 0;
 }

@@ -163,6 +163,17 @@ int64_t colsum_workspace_elems(int64_t Ncols);
 int launch_colsum(int64_t R, int64_t Ncols, int64_t F, const float* Z, float* out, float* workspace, cudaStream_t st);
 int launch_colsum_final(int64_t Ncols, int64_t F, int nblk, const float* partial, float* out, cudaStream_t st);
 
+// streaming kernels for narrow contractions (ds_narrow.cu: few output columns, short reduction per segment - the 1 - 5
+// channel layers of the reference's notebooks); B(seg, k, n) = Bm[k * sk + seg * ss + n * sn]
+bool narrow_rows_usable(int64_t N, int64_t K, int nseg);
+bool narrow_tn_usable(int64_t N, int64_t K, int nseg);
+int64_t narrow_tn_workspace_elems(int64_t R, int64_t K, int nseg, int64_t N);
+int launch_narrow_rows(int64_t R, int64_t N, int64_t K, int nseg, const float* A0, const float* Arest, int64_t a_seg_stride,
+                       int64_t lda, const float* Bm, int64_t sk, int64_t ss, int64_t sn, const float* bias, int64_t bias_mod,
+                       int act, float* C, int64_t ldc, cudaStream_t st);
+int launch_narrow_tn(int64_t R, int64_t N, int64_t K, int nseg, const float* A0, const float* Arest, int64_t a_seg_stride,
+                     int64_t lda, const float* D, int64_t ldd, float* partial, int64_t* nblk, cudaStream_t st);
+
 // streaming kernels for contractions with a very short reduction (ds_skinny.cu; opt-in with DEEPSPHERE_SKINNY=1).
 // The launchers return -1 (nothing launched) when an operand is not 16-byte aligned: the caller then takes the
 // tiled kernels; 0 = done, > 0 = error (ds_last_error).

@@ -287,6 +287,9 @@ int launch_gemm_nn(int64_t R, int64_t N, int64_t Kc, int nseg, const float* A0, 
                    int64_t a_seg_stride, int64_t lda, const float* Bm, int64_t ldb, int64_t b_kc_stride,
                    int64_t b_seg_stride, const float* bias, int64_t bias_mod, int act, float* C, int64_t ldc,
                    cudaStream_t st) {
+  if (narrow_rows_usable(N, Kc, nseg))  // few output columns, short reduction: stream it (ds_narrow.cu)
+    return launch_narrow_rows(R, N, Kc, nseg, A0, Arest, a_seg_stride, lda, Bm, b_kc_stride * ldb, b_seg_stride * ldb, 1, bias,
+                              bias_mod, act, C, ldc, st);
   dim3 grid((unsigned)cdiv(R, BM), (unsigned)cdiv(N, BN));
   DS_CHECK(cdiv(N, BN) < 65536, "gemm_nn: N too large");
   gemm_nn_kernel<<<grid, 256, 0, st>>>(R, N, Kc, nseg, A0, Arest, a_seg_stride, lda, Bm, ldb, b_kc_stride,
@@ -309,6 +312,9 @@ int launch_gemm_nt(int64_t R, int64_t Nc, int64_t Kd, int nseg, const float* A, 
 int launch_gemm_nt_seg(int64_t R, int64_t Nc, int64_t Kd, int nseg, const float* A0, const float* Arest,
                        int64_t a_seg_stride, int64_t lda, const float* Bm, int64_t ldb, int64_t b_nc_stride,
                        int64_t b_seg_stride, float* C, int64_t ldc, cudaStream_t st) {
+  if (narrow_rows_usable(Nc, Kd, nseg))  // B(seg, kd, c) = Bm[(c * b_nc_stride + seg * b_seg_stride) * ldb + kd]
+    return launch_narrow_rows(R, Nc, Kd, nseg, A0, Arest, a_seg_stride, lda, Bm, 1, b_seg_stride * ldb, b_nc_stride * ldb,
+                              nullptr, 1, DS_ACT_LINEAR, C, ldc, st);
   dim3 grid((unsigned)cdiv(R, BM), (unsigned)cdiv(Nc, BN));
   DS_CHECK(cdiv(Nc, BN) < 65536, "gemm_nt_seg: N too large");
   gemm_nt_seg_kernel<<<grid, 256, 0, st>>>(R, Nc, Kd, nseg, A0, Arest, a_seg_stride, lda, Bm, ldb, b_nc_stride,
@@ -318,7 +324,7 @@ int launch_gemm_nt_seg(int64_t R, int64_t Nc, int64_t Kd, int nseg, const float*
 }
 
 int64_t gemm_tn_workspace_elems(int64_t R, int64_t Kc, int nseg, int64_t N) {
-  return tn_splits(R, Kc, nseg, N) * nseg * Kc * N;
+  return std::max(tn_splits(R, Kc, nseg, N) * nseg * Kc * N, narrow_tn_workspace_elems(R, Kc, nseg, N));
 }
 
 int64_t colsum_workspace_elems(int64_t Ncols) { return (int64_t)COLSUM_BLOCKS * Ncols; }
@@ -326,6 +332,15 @@ int64_t colsum_workspace_elems(int64_t Ncols) { return (int64_t)COLSUM_BLOCKS * 
 int launch_gemm_tn(int64_t R, int64_t N, int64_t Kc, int nseg, const float* A0, const float* Arest,
                    int64_t a_seg_stride, int64_t lda, const float* D, int64_t ldd, float* C, int64_t ldc,
                    int64_t c_kc_stride, int64_t c_seg_stride, float* partial, cudaStream_t st) {
+  if (narrow_tn_usable(N, Kc, nseg)) {  // a [nseg * Kc, N] output of a few hundred elements: streaming kernel (ds_narrow.cu)
+    int64_t nblk = 0;
+    DS_TRY(launch_narrow_tn(R, N, Kc, nseg, A0, Arest, a_seg_stride, lda, D, ldd, partial, &nblk, st));
+    const int64_t tot = (int64_t)nseg * Kc * N;
+    gemm_tn_reduce_kernel<<<(unsigned)std::min<int64_t>(cdiv(tot, 256), 4096), 256, 0, st>>>(
+        N, Kc, nseg, nblk, partial, C, ldc, c_kc_stride, c_seg_stride);
+    DS_LAUNCHED();
+    return 0;
+  }
   const int64_t splits = tn_splits(R, Kc, nseg, N);
   const int64_t rows_per_split = cdiv(cdiv(R, splits), BK) * BK;
   const int kc_tiles = (int)cdiv(Kc, BM);
