@@ -9,7 +9,7 @@ constexpr int LAT_MAX_STEPS = 16;
 constexpr int LAT_S = 8;  // strip height (pixels per thread per feature)
 
 struct LatticeDev {
-  int n_tiles = 0;   // regular tiles
+  int n_tiles = 0;   // tiles in the tables (all that have an exact own pixel)
   int LW = 0, H = 0, T = 0;
   int32_t* pix = nullptr;  // [n_tiles][LW*LW]
   float* w = nullptr;      // [n_tiles][LW*LW][9]

@@ -1,6 +1,9 @@
 // C-ABI glue of the fused lattice recursion: attaching the tile plan to a ds_plan, and the forward basis /
-// backward Clenshaw drivers that combine the lattice kernel (regular tiles) with the generic kernels on a
-// compact sub-problem (the few irregular tiles around the valence-3 vertices of the HEALPix tessellation).
+// backward Clenshaw drivers that combine the lattice kernel (every tile) with the generic kernels on a compact
+// sub-problem: the own pixels within H hops' reach of the 8 valence-3 vertices of the HEALPix tessellation, where the
+// neighbourhood is not a lattice (15 pixels in each of the 24 tiles around them for H = 4; deepsphere/lattice.py works
+// them out per pixel).  The lattice kernel writes those rows too - wrongly -, the scatter of the sub-problem, which
+// follows it on the stream, overwrites them.
 #include <vector>
 
 #include "ds_lattice.cuh"
@@ -10,11 +13,11 @@ namespace ds {
 struct LatticeAttachment {
   LatticeDev dev;
   int H = 0;
-  // irregular tiles: generic kernels on the closure (all rows within H hops of the irregular tiles' pixels)
+  // irregular rows: generic kernels on the closure (all rows within H hops of them)
   ds_plan* sub_plan = nullptr;   // L~ restricted to the closure (owned)
   int64_t n_closure = 0, n_own = 0;
   int32_t* closure_rows = nullptr;  // [n_closure] global row of each closure row
-  int32_t* own_sub = nullptr;       // [n_own] closure rows whose results are exact (the irregular tiles' own pixels)
+  int32_t* own_sub = nullptr;       // [n_own] closure rows whose results are exact and wanted (the irregular rows)
   int64_t device_bytes = 0;
 };
 
@@ -30,7 +33,8 @@ __global__ void gather_rows_kernel(int64_t B, int64_t M, int64_t n, int FV, cons
     dst[e] = __ldg(src + (b * M + rows[j]) * FV + c);
   }
 }
-// dst[b, closure_rows[own[j]], :] = src[b, own[j], :]
+// dst[t][b, closure_rows[own[j]], :] = src[t][b, own[j], :] for nt tensors laid out back to back (B counts them all:
+// the tensors are [B/nt, rows, F] each and contiguous, so tensor t, sample b is plain sample t * (B/nt) + b)
 __global__ void scatter_rows_kernel(int64_t B, int64_t M, int64_t n_closure, int64_t n_own, int FV,
                                     const int32_t* __restrict__ closure_rows, const int32_t* __restrict__ own,
                                     const float4* __restrict__ src, float4* __restrict__ dst) {
@@ -71,7 +75,7 @@ bool lattice_usable(const ds_plan* plan, int32_t K, int64_t B, int64_t F) {
 
 int lattice_halo(const ds_plan* plan) { return plan->lattice ? plan->lattice->H : 0; }
 
-// generic (unfused) recursion on the closure sub-problem, used for the irregular tiles
+// generic (unfused) recursion on the closure sub-problem, used for the irregular rows
 // steps: out_s = alpha_s * S cur + beta_s * old + gamma_s * add_s on gathered tensors; results scattered
 static int sub_problem_recursion(const ds_plan* plan, int64_t B, int F, int nsteps, const float* in0,
                                  const float* const* add, float* const* out, const float* alpha, const float* beta,
@@ -148,13 +152,13 @@ bool fused_conv_usable(const ds_plan* plan, int32_t K, int64_t B, int64_t F, int
   (void)B;
   if (!plan->lattice || !plan->symmetric || K < 2) return false;
   const LatticeAttachment* L = plan->lattice;
-  if (umma_supported(F, K, N) != 0) return false;  // the irregular tiles go through the tensor-core GEMM
+  if (umma_supported(F, K, N) != 0) return false;  // the irregular rows go through the tensor-core GEMM
   return lattice_conv2_usable(L->dev, K - 1, (int)F, (int)N, mode);  // register-resident kernel (ds_lattice_conv2.cu)
 }
 
 // y = act( sum_k T_k(L~)(in0) B_k + bias ),  B_k(f, n) = W[f*s_f + k*s_k + n*s_n];  basis_out (optional):
-// [K-1, B, M, F] receives T_1..T_{K-1}(in0).  Regular tiles: one fused kernel; irregular tiles: generic hops +
-// tensor-core GEMM on the gathered closure, own rows scattered back.
+// [K-1, B, M, F] receives T_1..T_{K-1}(in0).  All tiles: one fused kernel; then the irregular rows: generic hops +
+// tensor-core GEMM on the gathered closure, scattered over what the fused kernel left there.
 int fused_conv(const ds_plan* plan, int32_t recursion, int32_t K, int64_t B, int64_t F, int64_t N, const float* in0,
                float* basis_out, const float* W, int64_t s_f, int64_t s_k, int64_t s_n, const float* bias, int act,
                float* y, int mode, cudaStream_t st) {
@@ -168,7 +172,7 @@ int fused_conv(const ds_plan* plan, int32_t recursion, int32_t K, int64_t B, int
   DS_TRY(launch_lattice_conv2(L->dev, K - 1, B, M, (int)F, (int)N, recursion, in0, basis_out ? out : nullptr, W, s_f,
                               s_k, s_n, bias, act, y, st));
   if (L->n_own == 0) return 0;
-  // ---- irregular tiles ----
+  // ---- irregular rows ----
   const int FV = (int)(F / 4), NV = (int)(N / 4);
   const int64_t n = L->n_closure, As = B * n * F;
   float* ws = nullptr;  // [K][B, n, F] basis on the closure, then [B, n, N] result
@@ -183,12 +187,13 @@ int fused_conv(const ds_plan* plan, int32_t recursion, int32_t K, int64_t B, int
     const bool cheb2 = recursion == DS_RECURSION_CHEBYSHEV && k >= 2;
     rc = launch_spmm(L->sub_plan->fwd, B, F, ws + (int64_t)(k - 1) * As, cheb2 ? 2.f : 1.f,
                      cheb2 ? ws + (int64_t)(k - 2) * As : nullptr, -1.f, nullptr, 0.f, ws + (int64_t)k * As, st);
-    if (rc == 0 && basis_out != nullptr) {
-      scatter_rows_kernel<<<grid_for(B * L->n_own * FV), 256, 0, st>>>(
-          B, M, n, L->n_own, FV, L->closure_rows, L->own_sub, reinterpret_cast<const float4*>(ws + (int64_t)k * As),
-          reinterpret_cast<float4*>(out[k - 1]));
-      g_launches.fetch_add(1);
-    }
+  }
+  if (rc == 0 && basis_out != nullptr) {  // T_1 .. T_{K-1}: [K-1][B, n, F] -> [K-1][B, M, F], one launch
+    const int64_t BK = (int64_t)(K - 1) * B;
+    scatter_rows_kernel<<<grid_for(BK * L->n_own * FV), 256, 0, st>>>(
+        BK, M, n, L->n_own, FV, L->closure_rows, L->own_sub, reinterpret_cast<const float4*>(ws + As),
+        reinterpret_cast<float4*>(basis_out));
+    g_launches.fetch_add(1);
   }
   if (rc == 0)
     rc = launch_umma_gemm(B * n, N, F, K, ws, ws + As, B * n, W, s_f, s_k, s_n, bias, N, act, ys, N, mode, st);

@@ -32,10 +32,18 @@ DJ = hpx.NB_YOFF
 
 
 class LatticePlan:
-    def __init__(self, nside, H, tile_side, LW, tile_face, tile_x0, tile_y0, pix, w, regular, n_rows):
+    def __init__(self, nside, H, tile_side, LW, tile_face, tile_x0, tile_y0, pix, w, exact, n_rows):
         self.nside, self.H, self.tile_side, self.LW = nside, H, tile_side, LW
         self.tile_face, self.tile_x0, self.tile_y0 = tile_face, tile_x0, tile_y0
-        self.pix, self.w, self.regular, self.n_rows = pix, w, regular, n_rows
+        self.pix, self.w, self.n_rows = pix, w, n_rows
+        # exact [n_tiles, LW*LW] bool: the H-hop recursion on the lattice gives the true value at this position
+        # (holes count as exact).  A tile is `regular` when that holds on all of its own pixels, `usable` when it
+        # holds on at least one of them (the others are recomputed by the generic path, see irregular_rows).
+        self.exact = exact
+        own = self.own_mask()
+        has = pix[:, own] >= 0
+        self.regular = (exact[:, own] | ~has).all(axis=1)
+        self.usable = (exact[:, own] & has).any(axis=1)
 
     @property
     def n_tiles(self):
@@ -49,10 +57,18 @@ class LatticePlan:
         return m.ravel()
 
     def irregular_rows(self):
-        """Rows of L~ owned by irregular tiles (to be handled by the generic path)."""
+        """Rows of L~ whose H-hop value the lattice does not reproduce (to be handled by the generic path): the own
+        pixels within reach of a valence-3 vertex - a 4 x 4 corner of each of the 24 tiles around them for H = 4 -
+        and every own pixel of a tile that is not launched at all."""
         own = self.own_mask()
-        rows = self.pix[~self.regular][:, own].ravel()
-        return np.sort(rows[rows >= 0])
+        rows, ex = self.pix[:, own], self.exact[:, own] & self.usable[:, None]
+        return np.sort(rows[(rows >= 0) & ~ex])
+
+    def lattice_rows(self):
+        """Rows of L~ whose result comes from the lattice launch (the complement of irregular_rows)."""
+        own = self.own_mask()
+        rows, ex = self.pix[:, own], self.exact[:, own] & self.usable[:, None]
+        return np.sort(rows[(rows >= 0) & ex])
 
 
 def neighbour_table(nside):
@@ -162,23 +178,42 @@ def build_lattice_plan(Lt, nside, indices, H, tile_order=4):
         w[:, :, d] = np.where(has, ldir[rsafe, (d + rot) % 8], 0.0)
     w[:, :, 8] = np.where(has, ldir[rsafe, 8], 0.0)
 
-    # verification: for every position that gets computed (ring <= H-1) the lattice neighbour in
-    # direction d must be the true graph neighbour in that direction (or both absent)
+    # verification, per lattice position: the lattice neighbour in direction d must be the true graph neighbour in
+    # that direction wherever L~ has one (a direction without a true neighbour carries weight 0: whatever sits there is
+    # harmless).  A position that fails is `bad`: its value is wrong from hop 1 on ...
     pos_j, pos_i = np.divmod(np.arange(LW * LW), LW)
     inner = (pos_j >= 1) & (pos_j <= LW - 2) & (pos_i >= 1) & (pos_i <= LW - 2)
-    regular = np.ones(nt, dtype=bool)
+    bad = np.zeros((nt, LW * LW), dtype=bool)
+    present = np.zeros((nt, LW * LW, 8), dtype=bool)
+    tgts = []
     nbr_true_all = NB[np.where(pixel >= 0, pixel, 0)]  # [nt, P, 8] face-frame order
     for d in range(8):
         tgt = (pos_j + DJ[d]) * LW + (pos_i + DI[d])
         tgt = np.where(inner, tgt, 0)
-        lat_pix = pixel[:, tgt]  # pixel sitting at the lattice neighbour
+        tgts.append(tgt)
         true_pix = np.take_along_axis(nbr_true_all, ((d + rot) % 8)[..., None], axis=2)[..., 0]
-        # only selected pixels matter: compare rows (a neighbour outside the selection == absent)
-        ok = (lut[np.where(lat_pix >= 0, lat_pix, npix)] == lut[np.where(true_pix >= 0, true_pix, npix)])
-        ok = ok | ~has | ~inner[None, :]
-        regular &= ok.all(axis=1)
+        true_row = lut[np.where(true_pix >= 0, true_pix, npix)]  # a neighbour outside the selection == absent
+        present[:, :, d] = has & (true_row >= 0)
+        bad |= present[:, :, d] & inner[None, :] & (row[:, tgt] != true_row)
+    del nbr_true_all
+    # ... and the error travels one position per hop: exact_h(p) = p is computed at hop h (inside the shrinking region),
+    # not bad, and every true neighbour was exact at hop h - 1.  Away from the valence-3 vertices nothing is bad and the
+    # own pixels (depth >= H) are exact by construction, so only the tiles with a bad position are propagated.
+    depth = np.minimum(np.minimum(pos_j, LW - 1 - pos_j), np.minimum(pos_i, LW - 1 - pos_i))
+    exact = np.broadcast_to(depth >= H, (nt, LW * LW)) | ~has
+    hit = np.flatnonzero(bad.any(axis=1))
+    if len(hit):
+        ex = np.ones((len(hit), LW * LW), dtype=bool)  # hop 0: the gathered input
+        for h in range(1, H + 1):
+            nxt = (depth >= h)[None, :] & ~bad[hit]
+            for d in range(8):
+                nxt &= ~present[hit][:, :, d] | ex[:, tgts[d]]
+            ex = nxt | ~has[hit]
+        exact = exact.copy()
+        exact[hit] = ex
+    del present
     # every row must be owned by exactly one tile
-    plan = LatticePlan(nside, H, T, LW, tf, tx, ty, row.astype(np.int32), w, regular, M)
+    plan = LatticePlan(nside, H, T, LW, tf, tx, ty, row.astype(np.int32), w, exact, M)
     own_rows = plan.pix[:, plan.own_mask()]
     owned = np.sort(own_rows[own_rows >= 0])
     if len(owned) != M or np.any(owned != np.arange(M)):
@@ -188,7 +223,8 @@ def build_lattice_plan(Lt, nside, indices, H, tile_order=4):
 
 def check_plan(plan, Lt, rng=None, n_tiles=None):
     """Numerical self-check: one application of the stencil on random data equals Lt @ x on the
-    computed region of every (sampled) regular tile.  Returns the max abs error."""
+    computed region of every (sampled) regular tile.  Returns the max abs error.  (The H-hop statement, including
+    the exact pixels of the tiles at the valence-3 vertices: tests/test_lattice_cpu.py.)"""
     rng = rng or np.random.default_rng(0)
     M = plan.n_rows
     x = rng.standard_normal(M)
@@ -214,9 +250,11 @@ def check_plan(plan, Lt, rng=None, n_tiles=None):
 
 def make_payload(Lt, nside, indices, H, tile_order=4):
     """Everything ds_plan_attach_lattice needs, as contiguous numpy arrays (or None if the fused path does
-    not apply): tables of the regular tiles + the compact generic sub-problem covering the irregular ones."""
+    not apply): tables of every tile the lattice serves + the compact generic sub-problem that recomputes the rows it
+    gets wrong (plan.irregular_rows(): the own pixels within H hops' reach of a valence-3 vertex; the kernels write
+    all own pixels of a launched tile and the sub-problem's scatter, which runs after them, overwrites those rows)."""
     plan = build_lattice_plan(Lt, nside, indices, H, tile_order)
-    if plan is None or not plan.regular.any():
+    if plan is None or not plan.usable.any():
         return None
     csr = sparse.csr_matrix(Lt)
     # the backward pass re-uses the same stencil for L~^T: symmetric up to rounding (same rule as ds_plan_create_coo)
@@ -239,7 +277,7 @@ def make_payload(Lt, nside, indices, H, tile_order=4):
         closure = np.zeros(0, dtype=np.int64)
         sub_idx, sub_val = np.zeros((0, 2), np.int64), np.zeros(0, np.float32)
         own_sub = np.zeros(0, dtype=np.int32)
-    reg = plan.regular
+    reg = plan.usable
     return {
         "n_tiles": int(reg.sum()), "LW": int(plan.LW), "H": int(plan.H), "T": int(plan.tile_side),
         "pix": np.ascontiguousarray(plan.pix[reg], dtype=np.int32),
@@ -247,5 +285,6 @@ def make_payload(Lt, nside, indices, H, tile_order=4):
         "sub": (sub_idx, sub_val, int(len(closure))),
         "closure_rows": np.ascontiguousarray(closure, dtype=np.int32),
         "own_sub": np.ascontiguousarray(own_sub, dtype=np.int32),
-        "n_irregular_tiles": int((~reg).sum()),
+        "n_irregular_tiles": int((~plan.regular).sum()),
+        "lattice_rows": plan.lattice_rows(),
     }

@@ -37,9 +37,10 @@ def test_masked_plan_and_payload():
     assert plan is not None and (plan.pix < 0).any()  # holes outside the survey footprint
     assert lattice.check_plan(plan, Lt) < 1e-12
     p = lattice.make_payload(Lt, 64, ext, 3)
-    assert p["n_tiles"] == int(plan.regular.sum()) and p["pix"].dtype == np.int32 and p["w"].shape[2] == 9
-    # the sub-problem covers every row owned by an irregular tile
+    assert p["n_tiles"] == int(plan.usable.sum()) and p["pix"].dtype == np.int32 and p["w"].shape[2] == 9
+    # the sub-problem covers every row the lattice launch does not get right, the launch all the others
     assert np.array_equal(p["closure_rows"][p["own_sub"]], plan.irregular_rows())
+    assert np.array_equal(np.sort(np.concatenate([p["lattice_rows"], plan.irregular_rows()])), np.arange(len(ext)))
 
 
 def test_not_applicable_cases():
@@ -47,7 +48,9 @@ def test_not_applicable_cases():
     assert lattice.build_lattice_plan(g20.L, 16, np.arange(12 * 256), 2, 3) is None  # not an 8-neighbour graph
     Lt = _prepared(8)
     assert lattice.build_lattice_plan(Lt, 8, np.arange(768), 2, 4) is None  # tile larger than a face
-    assert lattice.make_payload(_prepared(16), 16, np.arange(12 * 256), 4) is None  # every tile touches a vertex
+    # nside 16: every 16 x 16 tile (= base face) touches valence-3 vertices, yet all but 30 pixels of each are exact
+    p = lattice.make_payload(_prepared(16), 16, np.arange(12 * 256), 4)
+    assert p["n_tiles"] == 12 and p["n_irregular_tiles"] == 12 and len(p["own_sub"]) == 360
 
 
 @pytest.mark.parametrize("recursion", ["chebyshev", "monomial"])
@@ -70,22 +73,27 @@ def test_shrinking_region_recursion_matches_sparse(recursion):
             T.append(L64 @ T[-1])
     LW = plan.LW
     own = plan.own_mask().reshape(LW, LW)
-    for t in np.flatnonzero(plan.regular)[:6]:
+    DJ, DI = np.asarray(lattice.DJ), np.asarray(lattice.DI)
+    irregular = np.flatnonzero(~plan.regular)
+    assert len(irregular) == 24
+    n_wrong = 0
+    for t in list(np.flatnonzero(plan.regular)[:6]) + list(irregular):
         pix = plan.pix[t].reshape(LW, LW)
         w = plan.w[t].reshape(LW, LW, 9).astype(np.float64)
+        good = plan.exact[t].reshape(LW, LW) & own & (pix >= 0)
+        assert good.sum() == (256 if plan.regular[t] else 256 - 15)
         cur = np.where(pix >= 0, x[np.maximum(pix, 0)], 0.0)
         oth = np.zeros_like(cur)
         for s in range(1, H + 1):
-            lo, hi = s, LW - 1 - s
+            lo, hi = s, LW - s  # computed region [lo, hi)
+            acc = w[lo:hi, lo:hi, 8] * cur[lo:hi, lo:hi]
+            for d in range(8):
+                acc = acc + w[lo:hi, lo:hi, d] * cur[lo + DJ[d] : hi + DJ[d], lo + DI[d] : hi + DI[d]]
             new = oth.copy()
-            for j in range(lo, hi + 1):
-                for i in range(lo, hi + 1):
-                    acc = w[j, i, 8] * cur[j, i]
-                    for d in range(8):
-                        acc += w[j, i, d] * cur[j + lattice.DJ[d], i + lattice.DI[d]]
-                    if recursion == "chebyshev" and s >= 2:
-                        new[j, i] = 2 * acc - oth[j, i]
-                    else:
-                        new[j, i] = acc
+            new[lo:hi, lo:hi] = 2 * acc - oth[lo:hi, lo:hi] if recursion == "chebyshev" and s >= 2 else acc
             cur, oth = new, cur
-            assert np.abs(cur[own] - T[s][pix[own]]).max() < 1e-12, (t, s)
+            assert np.abs(cur[good] - T[s][pix[good]]).max() < 1e-12, (t, s)
+        # ... and the pixels the plan hands to the generic path really are wrong on the lattice (the rule is tight)
+        rest = own & (pix >= 0) & ~good
+        n_wrong += int((np.abs(cur[rest] - T[H][pix[rest]]) > 1e-9).sum())
+    assert n_wrong == 24 * 15
