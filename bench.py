@@ -66,6 +66,8 @@ def parse():
     ap.add_argument("--part-nside", type=int, default=1024)
     ap.add_argument("--part-batch", type=int, default=16,
                     help="global batch of the sphere-partitioned nside-1024 network (halved until it fits one GPU's memory)")
+    ap.add_argument("--adam", default="fused", choices=["fused", "foreach"],
+                    help="torch.optim.Adam implementation of the training-step benches")
     ap.add_argument("--model-nside", type=int, default=256)
     ap.add_argument("--model-batch", type=int, default=16)
     ap.add_argument("--nside", type=int, default=256)
@@ -221,6 +223,12 @@ def cpu_reference_time(L, args, batch, steps, warmup, Lt=None, sample=None):
     return float(np.mean(times)), algorithmic_bytes(batch, M, F, F), parity
 
 
+def _adam(params, args):
+    """Adam for the training-step benches: the fused multi-tensor implementation (ONE kernel per step for all parameters
+    instead of ~13 foreach launches + one step-counter update per parameter), capturable into the step's CUDA graph."""
+    return torch.optim.Adam(params, lr=1e-3, capturable=True, fused=getattr(args, "adam", "fused") == "fused")
+
+
 def model_train_bench(args, mode, device, world):
     """Second half of BASELINE.json's metric: HealpyGCNN training throughput (maps/s).  The regression network of
     SURVEY 8d config C5 (PseudoConv p=1 F16 -> [Chebyshev K5 F32 + MAX pool] x 3 -> Chebyshev K5 F64 -> pool ->
@@ -245,7 +253,7 @@ def model_train_bench(args, mode, device, world):
     dsd.broadcast_parameters(model)
     params = model.trainable_variables
     use_graph = bool(getattr(args, "model_graph", False))
-    opt = torch.optim.Adam(params, lr=1e-3, capturable=True)
+    opt = _adam(params, args)
     gen = torch.Generator(device=device).manual_seed(11 + int(os.environ.get("RANK", "0")))
     x = torch.randn(Bm, npix, 1, device=device, generator=gen)
     t = torch.randn(Bm, 2, device=device, generator=gen)
@@ -478,7 +486,7 @@ def named_config_bench(name, args, device, rank, world, hbm_peak):
         m.to(device)
         dsd.broadcast_parameters(m)
     params = [p for m in modules for p in m.trainable_variables]
-    opt = torch.optim.Adam(params, lr=1e-3, capturable=True)
+    opt = _adam(params, args)
 
     def train_step():
         opt.zero_grad(set_to_none=True)
@@ -631,7 +639,7 @@ def model_train_partitioned_bench(args, mode, device, rank, world):
     model(x, training=True)  # builds the weights and the device plans
     dsd.broadcast_parameters(model)
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.Adam(params, lr=1e-3, capturable=True)
+    opt = _adam(params, args)
     prep_s = time.time() - t0
     ar_events = []
 

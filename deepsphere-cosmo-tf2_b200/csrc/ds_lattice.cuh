@@ -36,6 +36,21 @@ struct LatticeArgs {
 };
 
 
+// the irregular rows of the plan grouped into connected patches of their H-hop closure (ds_patch.cu)
+struct PatchDev {
+  int n_patches = 0, max_rows = 0, max_own = 0;
+  int32_t* row_ptr = nullptr;    // [n_patches + 1] ranges of `rows`
+  int32_t* rows = nullptr;       // global row of every patch row
+  int32_t* ell_col = nullptr;    // [n_rows][9] patch-local column (-1: none)
+  float* ell_val = nullptr;      // [n_rows][9]
+  int32_t* own_ptr = nullptr;    // [n_patches + 1] ranges of `own_local`
+  int32_t* own_local = nullptr;  // patch-local rows whose result is wanted
+};
+bool patch_usable(const PatchDev& P, int nsteps, int F, int N);
+int launch_patch_conv(const PatchDev& P, int nsteps, int64_t B, int64_t M, int F, int N, int recursion, const float* in0,
+                      float* const* out, const float* W, int64_t s_f, int64_t s_k, int64_t s_n, const float* bias,
+                      int act, float* y, cudaStream_t st);
+
 int lattice_configure(const LatticeDev& L, int64_t B, int64_t M, int F, LatticeArgs& a, int* threads, int* smem);
 int launch_lattice(const LatticeDev& L, LatticeArgs& a, int threads, int smem, cudaStream_t st);
 

@@ -18,6 +18,7 @@ struct LatticeAttachment {
   int64_t n_closure = 0, n_own = 0;
   int32_t* closure_rows = nullptr;  // [n_closure] global row of each closure row
   int32_t* own_sub = nullptr;       // [n_own] closure rows whose results are exact and wanted (the irregular rows)
+  PatchDev patch;  // optional: the same rows as connected patches, for the one-launch kernel of ds_patch.cu
   int64_t device_bytes = 0;
 };
 
@@ -59,6 +60,12 @@ void lattice_free(LatticeAttachment* L) {
   cudaFree(L->dev.w);
   cudaFree(L->closure_rows);
   cudaFree(L->own_sub);
+  cudaFree(L->patch.row_ptr);
+  cudaFree(L->patch.rows);
+  cudaFree(L->patch.ell_col);
+  cudaFree(L->patch.ell_val);
+  cudaFree(L->patch.own_ptr);
+  cudaFree(L->patch.own_local);
   if (L->sub_plan) ds_plan_destroy(L->sub_plan);
   delete L;
 }
@@ -173,6 +180,9 @@ int fused_conv(const ds_plan* plan, int32_t recursion, int32_t K, int64_t B, int
                               s_k, s_n, bias, act, y, st));
   if (L->n_own == 0) return 0;
   // ---- irregular rows ----
+  if (patch_usable(L->patch, K - 1, (int)F, (int)N))  // one launch: gather, hops, fp32 contraction, epilogue, stores
+    return launch_patch_conv(L->patch, K - 1, B, M, (int)F, (int)N, recursion, in0, basis_out ? out : nullptr, W, s_f, s_k,
+                             s_n, bias, act, y, st);
   const int FV = (int)(F / 4), NV = (int)(N / 4);
   const int64_t n = L->n_closure, As = B * n * F;
   float* ws = nullptr;  // [K][B, n, F] basis on the closure, then [B, n, N] result
@@ -259,5 +269,56 @@ extern "C" int ds_plan_attach_lattice(ds_plan_t* plan, int32_t n_tiles, int32_t 
   L->sub_plan = n_own > 0 ? sub_plan : nullptr;  // ownership moves to the parent plan
   plan->lattice = L;
   plan->device_bytes += L->device_bytes;
+  return 0;
+}
+
+extern "C" int ds_plan_attach_patches(ds_plan_t* plan, int32_t n_patches, const int32_t* row_ptr, const int32_t* rows,
+                                      const int32_t* ell_col, const float* ell_val, const int32_t* own_ptr,
+                                      const int32_t* own_local) {
+  using namespace ds;
+  DS_CHECK(plan != nullptr && plan->lattice != nullptr, "ds_plan_attach_patches: the plan has no lattice attachment");
+  DS_CHECK(n_patches >= 1 && row_ptr && rows && ell_col && ell_val && own_ptr && own_local,
+           "ds_plan_attach_patches: bad argument");
+  LatticeAttachment* L = plan->lattice;
+  DS_CHECK(L->patch.n_patches == 0, "ds_plan_attach_patches: already attached");
+  const int64_t n_rows = row_ptr[n_patches], n_own = own_ptr[n_patches];
+  DS_CHECK(row_ptr[0] == 0 && own_ptr[0] == 0 && n_rows == L->n_closure && n_own == L->n_own,
+           "ds_plan_attach_patches: the patches must partition the closure and list every irregular row");
+  PatchDev P;
+  for (int p = 0; p < n_patches; ++p) {
+    const int nr = row_ptr[p + 1] - row_ptr[p], no = own_ptr[p + 1] - own_ptr[p];
+    DS_CHECK(nr >= 1 && no >= 0, "ds_plan_attach_patches: empty patch");
+    for (int i = own_ptr[p]; i < own_ptr[p + 1]; ++i)
+      DS_CHECK(own_local[i] >= 0 && own_local[i] < nr, "ds_plan_attach_patches: wanted row outside its patch");
+    for (int64_t e = (int64_t)row_ptr[p] * 9; e < (int64_t)row_ptr[p + 1] * 9; ++e)
+      DS_CHECK(ell_col[e] >= -1 && ell_col[e] < nr, "ds_plan_attach_patches: column outside its patch");
+    P.max_rows = std::max(P.max_rows, nr);
+    P.max_own = std::max(P.max_own, no);
+  }
+  for (int64_t i = 0; i < n_rows; ++i)
+    DS_CHECK(rows[i] >= 0 && rows[i] < plan->M, "ds_plan_attach_patches: row outside the graph");
+  int64_t bytes = 0;
+  auto up = [&](const void* src, size_t nbytes, void** dst) -> int {
+    *dst = nullptr;
+    DS_CUDA(cudaMalloc(dst, std::max<size_t>(nbytes, 16)));
+    if (nbytes) DS_CUDA(cudaMemcpy(*dst, src, nbytes, cudaMemcpyHostToDevice));
+    bytes += (int64_t)nbytes;
+    return 0;
+  };
+  int rc = up(row_ptr, sizeof(int32_t) * (n_patches + 1), (void**)&P.row_ptr);
+  if (rc == 0) rc = up(rows, sizeof(int32_t) * n_rows, (void**)&P.rows);
+  if (rc == 0) rc = up(ell_col, sizeof(int32_t) * n_rows * 9, (void**)&P.ell_col);
+  if (rc == 0) rc = up(ell_val, sizeof(float) * n_rows * 9, (void**)&P.ell_val);
+  if (rc == 0) rc = up(own_ptr, sizeof(int32_t) * (n_patches + 1), (void**)&P.own_ptr);
+  if (rc == 0) rc = up(own_local, sizeof(int32_t) * n_own, (void**)&P.own_local);
+  if (rc != 0) {
+    cudaFree(P.row_ptr); cudaFree(P.rows); cudaFree(P.ell_col); cudaFree(P.ell_val); cudaFree(P.own_ptr);
+    cudaFree(P.own_local);
+    return rc;
+  }
+  P.n_patches = n_patches;
+  L->patch = P;
+  L->device_bytes += bytes;
+  plan->device_bytes += bytes;
   return 0;
 }

@@ -260,19 +260,43 @@ umma_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
 }
 
 // C[kc*s_kc + seg*s_seg + n*s_n] = sum over CTAs of partial[cta][q*32 + i][n],  kc = (q % q_per_seg)*32 + i
-__global__ void umma_tn_reduce_kernel(int n_cta, int n_q, int q_per_seg, int N, int64_t Kc, const float* __restrict__ partial,
-                                      float* __restrict__ C, int64_t s_kc, int64_t s_seg, int64_t s_n) {
+// 256 threads = 32 consecutive outputs x 8 slices of the CTA range (slice sl takes CTAs sl, sl + 8, ...: four loads in
+// flight per thread), then a fixed-order sum of the 8 slices: one thread walking all n_cta partials of its output was a
+// chain of ~150 dependent L2 loads = 29 us per launch whatever the size (profiles/r2p_launches_model_train.csv).
+constexpr int RED_SLICES = 8, RED_OUT = 32;
+__global__ void __launch_bounds__(RED_SLICES* RED_OUT)
+    umma_tn_reduce_kernel(int n_cta, int n_q, int q_per_seg, int N, int64_t Kc, const float* __restrict__ partial,
+                          float* __restrict__ C, int64_t s_kc, int64_t s_seg, int64_t s_n) {
+  __shared__ float red[RED_SLICES][RED_OUT];
   const int64_t total = (int64_t)n_q * BLK * N;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int n = (int)(e % N);
-    const int row = (int)(e / N);
-    const int q = row / BLK, i = row % BLK;
-    const int seg = q / q_per_seg;
-    const int64_t kc = (int64_t)(q % q_per_seg) * BLK + i;
-    if (kc >= Kc) continue;
-    float s = 0.f;
-    for (int c = 0; c < n_cta; ++c) s += partial[(size_t)c * total + e];
-    C[kc * s_kc + seg * s_seg + n * s_n] = s;
+  const int o = threadIdx.x % RED_OUT, sl = threadIdx.x / RED_OUT;
+  for (int64_t e0 = (int64_t)blockIdx.x * RED_OUT; e0 < total; e0 += (int64_t)gridDim.x * RED_OUT) {
+    const int64_t e = e0 + o;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (e < total) {
+      int c = sl;
+      for (; c + 3 * RED_SLICES < n_cta; c += 4 * RED_SLICES) {
+        s0 += partial[(size_t)c * total + e];
+        s1 += partial[(size_t)(c + RED_SLICES) * total + e];
+        s2 += partial[(size_t)(c + 2 * RED_SLICES) * total + e];
+        s3 += partial[(size_t)(c + 3 * RED_SLICES) * total + e];
+      }
+      for (; c < n_cta; c += RED_SLICES) s0 += partial[(size_t)c * total + e];
+    }
+    red[sl][o] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (sl == 0 && e < total) {
+      float s = red[0][o];
+#pragma unroll
+      for (int j = 1; j < RED_SLICES; ++j) s += red[j][o];
+      const int n = (int)(e % N);
+      const int row = (int)(e / N);
+      const int q = row / BLK, i = row % BLK;
+      const int seg = q / q_per_seg;
+      const int64_t kc = (int64_t)(q % q_per_seg) * BLK + i;
+      if (kc < Kc) C[kc * s_kc + seg * s_seg + n * s_n] = s;
+    }
+    __syncthreads();
   }
 }
 
@@ -398,7 +422,7 @@ int launch_umma_gemm_tn(int64_t R, int64_t N, int64_t Kc, int nseg, const float*
   umma_gemm_tn_kernel<<<g.n_cta, three ? 320 : 192, g.smem_bytes, st>>>(m0, m1, md, p);
   DS_LAUNCHED();
   const int64_t total = (int64_t)g.n_q * BLK * N;
-  umma_tn_reduce_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 2048), 256, 0, st>>>(
+  umma_tn_reduce_kernel<<<(unsigned)std::min<int64_t>((total + RED_OUT - 1) / RED_OUT, 4096), RED_SLICES * RED_OUT, 0, st>>>(
       g.n_cta, g.n_q, g.q_per_seg, (int)N, Kc, partial, C, s_kc, s_seg, s_n);
   DS_LAUNCHED();
   return 0;

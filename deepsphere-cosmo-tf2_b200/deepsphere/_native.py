@@ -37,6 +37,7 @@ SIGNATURES = {
     "ds_plan_attach_lattice": (
         ctypes.c_int, [_ptr, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _ptr]
     ),
+    "ds_plan_attach_patches": (ctypes.c_int, [_ptr, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "ds_spmm": (ctypes.c_int, [_ptr, _i32, _i64, _i64, _ptr, _f32, _ptr, _f32, _ptr, _f32, _ptr, _ptr]),
     "ds_graph_conv_basis_elems": (_i64, [_i64, _i64, _i64, _i32]),
     "ds_graph_conv_forward_writes_basis": (_i32, [_ptr, _i32, _i64, _i64, _i64, _i32]),
@@ -230,6 +231,15 @@ class GraphPlan:
                 ),
                 "ds_plan_attach_lattice",
             )
+            pt = p.get("patches")
+            if pt is not None and os.environ.get("DEEPSPHERE_PATCH", "1") != "0":
+                check(
+                    lib().ds_plan_attach_patches(
+                        h, pt["n_patches"], cptr(pt["row_ptr"]), cptr(pt["rows"]), cptr(pt["ell_col"]),
+                        cptr(pt["ell_val"]), cptr(pt["own_ptr"]), cptr(pt["own_local"]),
+                    ),
+                    "ds_plan_attach_patches",
+                )
 
     def info(self, device_index=0):
         names = ["M", "nnz", "ell_width", "tail_rows", "tail_nnz", "ell_width_T", "tail_rows_T", "device_bytes",

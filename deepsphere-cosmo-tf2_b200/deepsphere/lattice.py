@@ -248,6 +248,47 @@ def check_plan(plan, Lt, rng=None, n_tiles=None):
     return worst
 
 
+def make_patches(csr, closure, rows_irr, max_rows=1024):
+    """The irregular sub-problem as connected patches (ds_plan_attach_patches): the closure of the irregular rows falls
+    apart into one neighbourhood per valence-3 vertex (8 x 189 rows for H = 4 on the full sphere); each patch carries
+    its rows, L~ restricted to them as a 9-wide ELL with patch-local columns, and the patch-local rows that are wanted.
+    None when a row has more than 9 entries or a patch is too large for one thread block."""
+    from scipy.sparse.csgraph import connected_components
+
+    sub = sparse.csr_matrix(csr[closure][:, closure])
+    sub.sort_indices()
+    n = sub.shape[0]
+    width = np.diff(sub.indptr)
+    if n == 0 or width.max() > 9:
+        return None
+    n_comp, label = connected_components(sub, directed=False)
+    order = np.argsort(label, kind="stable")  # closure-local rows grouped by patch
+    counts = np.bincount(label, minlength=n_comp)
+    if counts.max() > max_rows:
+        return None
+    row_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    local = np.empty(n, dtype=np.int64)  # patch-local index of every closure-local row
+    local[order] = np.arange(n) - np.repeat(row_ptr[:-1], counts)
+    ell_col = np.full((n, 9), -1, dtype=np.int32)
+    ell_val = np.zeros((n, 9), dtype=np.float32)
+    r_of = np.repeat(np.arange(n), width)
+    slot = np.arange(sub.nnz) - np.repeat(sub.indptr[:-1], width)
+    ell_col[r_of, slot] = local[sub.indices]
+    ell_val[r_of, slot] = sub.data
+    own_cl = np.searchsorted(closure, rows_irr)  # closure-local ids of the wanted rows
+    own_cl = own_cl[np.argsort(label[own_cl], kind="stable")]
+    own_counts = np.bincount(label[own_cl], minlength=n_comp)
+    return {
+        "n_patches": int(n_comp),
+        "row_ptr": np.ascontiguousarray(row_ptr),
+        "rows": np.ascontiguousarray(closure[order], dtype=np.int32),
+        "ell_col": np.ascontiguousarray(ell_col[order]),
+        "ell_val": np.ascontiguousarray(ell_val[order]),
+        "own_ptr": np.ascontiguousarray(np.concatenate([[0], np.cumsum(own_counts)]).astype(np.int32)),
+        "own_local": np.ascontiguousarray(local[own_cl], dtype=np.int32),
+    }
+
+
 def make_payload(Lt, nside, indices, H, tile_order=4):
     """Everything ds_plan_attach_lattice needs, as contiguous numpy arrays (or None if the fused path does
     not apply): tables of every tile the lattice serves + the compact generic sub-problem that recomputes the rows it
@@ -273,7 +314,9 @@ def make_payload(Lt, nside, indices, H, tile_order=4):
         sub_idx = np.ascontiguousarray(np.column_stack((sub.row, sub.col)).astype(np.int64))
         sub_val = np.ascontiguousarray(sub.data.astype(np.float32))
         own_sub = np.searchsorted(closure, rows_irr).astype(np.int32)
+        patches = make_patches(csr, closure, rows_irr)
     else:
+        patches = None
         closure = np.zeros(0, dtype=np.int64)
         sub_idx, sub_val = np.zeros((0, 2), np.int64), np.zeros(0, np.float32)
         own_sub = np.zeros(0, dtype=np.int32)
@@ -287,4 +330,5 @@ def make_payload(Lt, nside, indices, H, tile_order=4):
         "own_sub": np.ascontiguousarray(own_sub, dtype=np.int32),
         "n_irregular_tiles": int((~plan.regular).sum()),
         "lattice_rows": plan.lattice_rows(),
+        "patches": patches,
     }

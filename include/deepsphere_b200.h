@@ -85,13 +85,25 @@ int ds_plan_info(const ds_plan_t* plan, int32_t what, int64_t* value_out);
 /* Optional: attach the HEALPix tile plan that enables the fused K-hop recursion kernel (all K-1 hops of
  * gnn_layers.py:135-143 in shared memory) for layers with K = H + 1 on a symmetric 8-neighbour graph.
  * HOST arrays: pix [n_tiles, LW*LW] row of L~ at each lattice position (-1 = hole), w [n_tiles, LW*LW, 9]
- * stencil weights (8 directions + centre), LW = T + 2H.  Rows owned by tiles that are not regular lattices
- * (the vertex tiles) are served by the generic kernels on a compact sub-problem: `sub_plan` is L~ restricted
- * to `closure_rows` (ownership passes to `plan`), `own_sub` lists the closure rows to scatter back.
+ * stencil weights (8 directions + centre), LW = T + 2H.  The rows whose H-hop neighbourhood is not a lattice
+ * (the own pixels within reach of the 8 valence-3 vertices of the tessellation: the fused kernels write them too,
+ * wrongly) are recomputed by the generic kernels on a compact sub-problem and overwritten: `sub_plan` is L~
+ * restricted to `closure_rows` (ownership passes to `plan`), `own_sub` lists the closure rows to scatter back.
  * Without an attachment (or when it does not apply) the generic per-hop kernels run. */
 int ds_plan_attach_lattice(ds_plan_t* plan, int32_t n_tiles, int32_t LW, int32_t H, int32_t T, const int32_t* pix,
                            const float* w, ds_plan_t* sub_plan, int64_t n_closure, const int32_t* closure_rows,
                            int64_t n_own, const int32_t* own_sub);
+
+/* Optional, after ds_plan_attach_lattice: the same sub-problem grouped into its connected patches, which lets the
+ * tf32-mode graph convolution serve the irregular rows in ONE launch (ds_patch.cu: hops in shared memory, fp32
+ * contraction, epilogue) instead of gather + K-1 hops + GEMM + scatters.  HOST arrays: row_ptr [n_patches + 1] ranges
+ * of rows; rows [n_closure] row of L~ of every patch row (a permutation of closure_rows); ell_col / ell_val
+ * [n_closure, 9] L~ restricted to the patch, columns patch-local, -1 = unused slot; own_ptr [n_patches + 1] ranges of
+ * own_local; own_local [n_own] patch-local rows whose result is wanted.  Replaces nothing in the reference (it
+ * multiplies by one tf.SparseTensor, utils.py:76); without it the generic sub-problem path runs. */
+int ds_plan_attach_patches(ds_plan_t* plan, int32_t n_patches, const int32_t* row_ptr, const int32_t* rows,
+                           const int32_t* ell_col, const float* ell_val, const int32_t* own_ptr,
+                           const int32_t* own_local);
 
 /* ---- utils.split_sparse_dense_matmul (utils.py:49-78) ---------------------------------
  * out[b,m,f] = alpha * sum_j L~[m,j] in[b,j,f] + beta * prev[b,m,f] + gamma * add[b,m,f]

@@ -197,3 +197,99 @@ def test_fused_lattice_kernel_protocol_under_thread_sanitizer(tmp_path, conv2_pr
     if "FATAL: ThreadSanitizer" in res.stderr and "unexpected memory mapping" in res.stderr:
         pytest.skip("ThreadSanitizer cannot run in this container (ASLR settings)")
     assert res.returncode == 0 and "WARNING: ThreadSanitizer" not in res.stderr, res.stderr[-3000:]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# patch_conv_kernel (csrc/ds_patch.cu): the irregular rows of a lattice plan - the own pixels within reach of the valence-3
+# vertices - in one launch, on the host emulator against the oracle; with the ThreadSanitizer build the rotation of the
+# three shared-memory buffers and the per-hop weight image are checked for missing barriers.
+def _run_patch_cases(tmp_path, exe, conv2_problem, cases):
+    import numpy as np
+    from scipy import sparse
+
+    from helpers import orc
+
+    g, layers = conv2_problem
+    rng = np.random.default_rng(3)
+    for ci, (name, K, B, F, N, act, has_bias, want_basis) in enumerate(cases):
+        bwd = name.endswith("-bwd")
+        name = name.split("-")[0]
+        layer, pay = layers[name]
+        pt = pay["patches"]
+        assert pt is not None and pt["n_patches"] == 8
+        M = int(layer._L_shape[0])
+        recursion = "monomial" if name == "Monomial" else "chebyshev"
+        d = os.path.join(str(tmp_path), f"patch_{ci}")
+        os.makedirs(d)
+        x = rng.standard_normal((B, M, F)).astype(np.float32)
+        # forward: kernel [(F*K), N], B_k(f, n) = W[(f*K + k)*N + n]; backward-data: kernel [(N*K), F], x plays dz,
+        # B_k(f, n) = W[(n*K + k)*F + f] (the transposed read of the same layer kernel)
+        W = (rng.standard_normal((N * K, F) if bwd else (F * K, N)) * 0.2).astype(np.float32)
+        s_f, s_k, s_n = (1, F, K * F) if bwd else (K * N, N, 1)
+        bias = rng.standard_normal(N).astype(np.float32)
+        for key in ("row_ptr", "rows", "ell_col", "ell_val", "own_ptr", "own_local"):
+            pt[key].tofile(os.path.join(d, key + ".bin"))
+        for arr, fn in ((x, "x"), (W, "W"), (bias, "bias")):
+            arr.tofile(os.path.join(d, fn + ".bin"))
+        max_rows = int(np.diff(pt["row_ptr"]).max())
+        with open(os.path.join(d, "meta.txt"), "w") as f:
+            f.write(f"{pt['n_patches']} {B} {M} {F} {N} {K - 1} {int(recursion == 'chebyshev')} {act} {int(has_bias)} "
+                    f"{int(want_basis)} {s_f} {s_k} {s_n} {max_rows}\n")
+        res = subprocess.run([exe, d], capture_output=True, text=True, timeout=900)
+        assert res.returncode == 0 and "WARNING: ThreadSanitizer" not in res.stderr, res.stdout + res.stderr[-3000:]
+        y = np.fromfile(os.path.join(d, "y.bin"), dtype=np.float32).reshape(B, M, N)
+        Lt = sparse.csr_matrix((layer._L_values.astype(np.float64), (layer._L_indices[:, 0], layer._L_indices[:, 1])),
+                               shape=(M, M))
+        if bwd:
+            ref, _, _ = orc.graph_conv_backward(np.zeros((B, M, N)), Lt, W.astype(np.float64), K, x.astype(np.float64),
+                                                recursion)
+        else:
+            ref = orc.graph_conv_forward(x.astype(np.float64), Lt, W.astype(np.float64), K, recursion,
+                                         bias=bias.reshape(1, 1, -1).astype(np.float64) if has_bias else None,
+                                         activation="relu" if act == 1 else None, dtype=np.float64)
+        want = pay["closure_rows"][pay["own_sub"]]
+        assert len(want) == 360
+        other = np.setdiff1d(np.arange(M), want)
+        assert np.isnan(y[:, other]).all() and np.isfinite(y[:, want]).all()  # exactly the irregular rows are written
+        err = np.abs(y[:, want] - ref[:, want]).max() / np.abs(ref).max()
+        assert err <= 2e-6, (name, K, F, N, err)  # fp32 FMA throughout
+        if want_basis:
+            t_prev, t_cur = x.astype(np.float64), np.stack([Lt @ x[b].astype(np.float64) for b in range(B)])
+            for s in range(1, K):
+                u = np.fromfile(os.path.join(d, f"u{s}.bin"), dtype=np.float32).reshape(B, M, F)
+                assert np.isnan(u[:, other]).all()
+                assert np.abs(u[:, want] - t_cur[:, want]).max() <= 2e-6 * np.abs(t_cur).max(), s
+                nxt = np.stack([Lt @ t_cur[b] for b in range(B)])
+                t_prev, t_cur = t_cur, (2 * nxt - t_prev if recursion == "chebyshev" else nxt)
+
+
+def _build_patch(tmp_path, extra):
+    exe = os.path.join(tmp_path, "emul_patch")
+    cmd = ["g++", "-std=c++20", "-O1", "-pthread", "-DDS_EMULATE", *extra, "-I", os.path.join(HERE, "emul"),
+           os.path.join(HERE, "emul", "emul_patch.cpp"), "-o", exe]
+    subprocess.run(cmd, check=True, cwd=ROOT, capture_output=True, text=True)
+    return exe
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_patch_kernel_on_the_host_emulator(tmp_path, conv2_problem):
+    exe = _build_patch(str(tmp_path), [])
+    _run_patch_cases(tmp_path, exe, conv2_problem, [
+        # (layer, K, B, F, N, activation id, bias, basis wanted)
+        ("Chebyshev", 5, 2, 8, 16, 0, True, True),
+        ("Monomial", 4, 1, 16, 32, 1, False, True),
+        ("Chebyshev", 2, 1, 8, 64, 1, True, False),       # one hop
+        ("Chebyshev-bwd", 5, 1, 32, 16, 0, False, True),  # backward-data launch: transposed weight strides
+        ("Chebyshev", 5, 1, 64, 80, 1, True, False),      # widest: 3 row groups x 16 accumulators >= 45 wanted rows
+        ("Chebyshev", 3, 1, 4, 5, 0, True, False),        # odd N: 51 row groups
+    ])
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_patch_kernel_has_no_shared_memory_race(tmp_path, conv2_problem):
+    exe = _build_patch(str(tmp_path), ["-g", "-fsanitize=thread"])
+    probe = subprocess.run([exe], capture_output=True, text=True)
+    if "FATAL: ThreadSanitizer" in probe.stderr and "unexpected memory mapping" in probe.stderr:
+        pytest.skip("ThreadSanitizer cannot run in this container (ASLR settings)")
+    _run_patch_cases(tmp_path, exe, conv2_problem, [("Chebyshev", 5, 1, 8, 16, 1, True, True),
+                                                    ("Chebyshev-bwd", 4, 1, 16, 8, 0, False, True)])

@@ -100,6 +100,8 @@ def test_fused_lattice_conv_matches_oracle(mode, tol, cls, nside, B, Fin, Fout, 
     assert layer._plan.info(0)["lattice"] == 1
     # fused forward = weight-image prep + fused kernel + the irregular-tile sub-problem; no per-hop launches
     assert fwd_launches <= 4 + 2 * K, fwd_launches
+    if mode == "tf32":  # weight image + fused kernel + ONE launch for the irregular rows (ds_patch.cu)
+        assert fwd_launches == 3, fwd_launches
     rec = cls.lower()
     Lt, _ = orc.prepare_laplacian(g.L, 0.75 if rec == "chebyshev" else 1.0)
     xr = torch.tensor(x, requires_grad=True)
@@ -111,6 +113,11 @@ def test_fused_lattice_conv_matches_oracle(mode, tol, cls, nside, B, Fin, Fout, 
     assert rel_err(xt.grad.cpu().numpy(), xr.grad.numpy()) <= tol
     assert rel_err(layer.kernel.grad.cpu().numpy(), wr.grad.numpy()) <= tol
     assert rel_err(layer.bias.grad.cpu().numpy(), br.grad.numpy()) <= tol
+    if mode == "tf32":  # the rows around the valence-3 vertices come from the fp32 patch kernel (forward: exact inputs)
+        pay = layer._plan._lattice_payload
+        irr = pay["closure_rows"][pay["own_sub"]]
+        assert len(irr) == 360 and pay["patches"]["n_patches"] == 8
+        assert rel_err(y.detach().cpu().numpy()[:, irr], yr.detach().numpy()[:, irr]) <= 2e-5
     # the scale-aware metric as well (errors relative to the tensor's norm, not to its largest element)
     assert rel_l2(y.detach().cpu().numpy(), yr.detach().numpy()) <= tol
     assert rel_l2(xt.grad.cpu().numpy(), xr.grad.numpy()) <= tol
