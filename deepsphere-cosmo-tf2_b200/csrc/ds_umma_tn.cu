@@ -55,6 +55,89 @@ struct TnCtl {
   uint32_t tmem_base;
 };
 
+// ---- cp.async operand producers of umma_gemm_tn_kernel (warps 2-5) ---------------------------------------------------
+// The TMA box in 32-byte-atom swizzle mode sustains only ~10 B/clk/SM (ncu: 2.6 TB/s chip-wide, nothing saturated); 128
+// threads issuing 16-byte cp.async straight into the same layout (row r of a 16 x 32 block at r*128 B, 32-byte chunk index
+// XOR r % 4) reach the HBM rate.  One 16-byte chunk per thread per block; out-of-range rows / channels are zero-filled.
+//
+// One producer warp walks EVERY stage, so its instruction chain per stage is the pace of the kernel: with the block count
+// a run-time value the 16 block slots were predicated, not skipped - 317 issue slots per 16-row stage (three integer
+// divisions for the stage / phase indices, 64-bit selects and size arithmetic per slot), ~1 300 cycles per stage whatever
+// the stage carried: 5.9 TB/s with 64-channel operands but 1.8 TB/s with 16 (profiles/r2ac_umma_gemm_tn_narrow_summary.txt).
+// NB is now a template parameter (exactly NB copies, no predicates), everything that does not change from stage to stage
+// lives in registers (the running source address of this thread's chunk in every block, its advance per stage, whether
+// it is zero-filled), the stage / phase indices are counters, and the zero-fill uses cp.async's ignore-src predicate.
+template <int NB>
+__device__ __forceinline__ void tn_produce(const TnParams& p, TnCtl* ctl, uint8_t* stage_base, int64_t rb0, int64_t n_it) {
+  const int t = threadIdx.x - 64;
+  const int r = t >> 3, j = t & 7;
+  const uint32_t dst_off = (uint32_t)(r * 128 + (((j >> 1) ^ (r & 3)) * 32) + (j & 1) * 16);
+  constexpr int LAG = 3;  // stages whose copies may still be in flight per thread
+  const char* src[NB];
+  uint32_t step[NB], ign[NB];
+  const int64_t row0 = rb0 * BKR + r;  // this thread's row in the first stage
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    src[k] = reinterpret_cast<const char*>(p.A0);
+    step[k] = 0;
+    ign[k] = 1;
+    if (k < p.n_q) {
+      const int seg = k / p.q_per_seg, cb = k % p.q_per_seg;
+      const int col = cb * BLK + 4 * j;
+      const float* base = seg == 0 ? p.A0 : p.Arest + (int64_t)(seg - 1) * p.R * p.Kc;
+      if (col < p.Kc && row0 < p.R) {
+        src[k] = reinterpret_cast<const char*>(base + row0 * p.Kc + col);
+        step[k] = (uint32_t)(BKR * p.Kc * 4);
+        ign[k] = 0;
+      }
+    } else {
+      const int col = (k - p.n_q) * BLK + 4 * j;
+      if (col < p.N && row0 < p.R) {
+        src[k] = reinterpret_cast<const char*>(p.D + row0 * (int64_t)p.N + col);
+        step[k] = (uint32_t)(BKR * p.N * 4);
+        ign[k] = 0;
+      }
+    }
+  }
+  // stages in which this thread's row exists (only the last stage of the whole problem can be ragged)
+  const int64_t live = row0 < p.R ? (p.R - row0 + BKR - 1) / BKR : 0;
+  const uint32_t stage0 = ptx::smem_u32(stage_base) + dst_off;
+  int s = 0, s_done = 0;  // stage of iteration `it` / of iteration it - LAG
+  uint32_t ph = 0, st = stage0;
+  for (int64_t it = 0; it < n_it + LAG; ++it) {
+    if (it < n_it) {
+      if (it == live) {  // the row ran past the end: zero-fill from a valid address from here on
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          src[k] = reinterpret_cast<const char*>(p.A0);
+          step[k] = 0;
+          ign[k] = 1;
+        }
+      }
+      ptx::mbar_wait(&ctl->empty[s], ph ^ 1);
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        // the D blocks follow the A blocks in the stage (off_d = n_q * BLK_BYTES)
+        asm volatile(
+            "{\n\t.reg .pred pz;\n\tsetp.ne.u32 pz, %2, 0;\n\t"
+            "cp.async.cg.shared.global [%0], [%1], 16, pz;\n\t}" ::"r"(st + (uint32_t)k * BLK_BYTES),
+            "l"(src[k]), "r"(ign[k])
+            : "memory");
+        src[k] += step[k];
+      }
+      st += p.stage_bytes;
+      if (++s == p.stages) { s = 0; ph ^= 1; st = stage0; }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (it >= LAG) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(LAG) : "memory");
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&ctl->full[s_done]);
+      if (++s_done == p.stages) s_done = 0;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(320, 1)
 umma_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_arest,
                     const __grid_constant__ CUtensorMap map_d, const TnParams p) {
@@ -147,58 +230,13 @@ umma_gemm_tn_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_con
     }
   } else if (warp < 6) {
     if (p.use_cp_async) {
-      // Operand producers (the epilogue warps are idle during the main loop).  The TMA box in 32-byte-atom swizzle
-      // mode sustains only ~10 B/clk/SM (ncu: 2.6 TB/s chip-wide, nothing saturated); 128 threads issuing 16-byte
-      // cp.async straight into the same layout (row r of a 16 x 32 block at r*128 B, 32-byte chunk index XOR r % 4)
-      // reach the HBM rate.  One 16-byte chunk per thread per block; out-of-range rows / channels are zero-filled.
-      const int t = threadIdx.x - 64;
-      const int r = t >> 3, j = t & 7;
-      const uint32_t dst_off = (uint32_t)(r * 128 + (((j >> 1) ^ (r & 3)) * 32) + (j & 1) * 16);
-      constexpr int LAG = 3;      // stages whose copies may still be in flight per thread
-      constexpr int MAXB = 16;    // blocks per stage handled by this path (launcher checks n_q + nb <= MAXB)
-      // per-block source column pointer / row pitch / validity do not depend on the stage: hoist them
-      const float* bptr[MAXB];
-      uint32_t bok = 0;
-      const int nblk = p.n_q + p.nb_blocks;
-#pragma unroll
-      for (int k = 0; k < MAXB; ++k) {
-        bptr[k] = p.A0;
-        if (k < p.n_q) {
-          const int seg = k / p.q_per_seg, cb = k % p.q_per_seg;
-          const int col = cb * BLK + 4 * j;
-          const float* base = seg == 0 ? p.A0 : p.Arest + (int64_t)(seg - 1) * p.R * p.Kc;
-          if (col < p.Kc) { bptr[k] = base + col; bok |= 1u << k; }
-        } else if (k < nblk) {
-          const int col = (k - p.n_q) * BLK + 4 * j;
-          if (col < p.N) { bptr[k] = p.D + col; bok |= 1u << k; }
-        }
-      }
-      for (int64_t it = 0; it < n_it + LAG; ++it) {
-        if (it < n_it) {
-          const int s = (int)(it % p.stages);
-          const uint32_t ph = (uint32_t)(it / p.stages) & 1;
-          ptx::mbar_wait(&ctl->empty[s], ph ^ 1);
-          const uint32_t st = ptx::smem_u32(stage_base + (size_t)s * p.stage_bytes) + dst_off;
-          const int64_t row = (rb0 + it) * BKR + r;
-          const bool row_ok = row < p.R;
-          const int64_t offA = row_ok ? row * p.Kc : 0, offD = row_ok ? row * (int64_t)p.N : 0;
-#pragma unroll
-          for (int k = 0; k < MAXB; ++k) {
-            if (k < nblk) {
-              const bool ok = row_ok && ((bok >> k) & 1u);
-              const float* src = bptr[k] + (k < p.n_q ? offA : offD);
-              // the D blocks follow the A blocks in the stage (off_d = n_q * BLK_BYTES)
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(st + (uint32_t)k * BLK_BYTES), "l"(src),
-                           "r"(ok ? 16u : 0u) : "memory");
-            }
-          }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        if (it >= LAG) {
-          asm volatile("cp.async.wait_group %0;" ::"n"(LAG) : "memory");
-          ptx::fence_proxy_async_smem();
-          ptx::mbar_arrive(&ctl->full[(int)((it - LAG) % p.stages)]);
-        }
+      // operand producers (the epilogue warps are idle during the main loop): tn_produce above
+      switch (p.n_q + p.nb_blocks) {
+#define DS_TN_CASE(nb) case nb: tn_produce<nb>(p, ctl, stage_base, rb0, n_it); break;
+        DS_TN_CASE(2) DS_TN_CASE(3) DS_TN_CASE(4) DS_TN_CASE(5) DS_TN_CASE(6) DS_TN_CASE(7) DS_TN_CASE(8) DS_TN_CASE(9)
+        DS_TN_CASE(10) DS_TN_CASE(11) DS_TN_CASE(12) DS_TN_CASE(13) DS_TN_CASE(14) DS_TN_CASE(15) DS_TN_CASE(16)
+#undef DS_TN_CASE
+        default: __trap();  // the launcher only takes this path for 2..16 blocks
       }
     }
     // epilogue: once, after the whole row range has been reduced
