@@ -17,7 +17,8 @@ from .keras_compat import Sequential
 class HealpyGCNN(Sequential):
     """A graph convolutional network using the Keras-style model API and the layers of this package."""
 
-    def __init__(self, nside, indices, layers, n_neighbors=8, max_batch_size=None, initial_Fin=None):
+    def __init__(self, nside, indices, layers, n_neighbors=8, max_batch_size=None, initial_Fin=None,
+                 graph_builder=None):
         """
         :param nside: integer, the nside of the input
         :param indices: 1d array of pixel ids (NESTED) of the input of the network
@@ -27,6 +28,15 @@ class HealpyGCNN(Sequential):
                                splits of tf.sparse.sparse_dense_matmul (healpy_networks.py:125-134);
                                the splits are computed the same way and ignored by the kernels
         :param initial_Fin: initial number of input features (same remark)
+        :param graph_builder: optional callable ``(nside, indices, n_neighbors) -> graph`` whose result has a sparse
+                              Laplacian ``.L`` over ``indices`` (NESTED, same order).  NOT in the reference: it builds
+                              every graph with the PyGSP fork's ``SphereHealpix`` (healpy_networks.py:110-118), which is
+                              not a dependency here; ``deepsphere.graph.SphereHealpix`` is an independent builder whose
+                              edge set and weights are not pinned against PyGSP, so weights trained with the
+                              reference see a different ``L`` unless the original graphs are supplied, e.g.
+                              ``graph_builder=lambda n, idx, k: pygsp.graphs.SphereHealpix(subdivisions=n, indexes=idx,
+                              nest=True, k=k, lap_type="normalized")``.  The kernels are chosen from the matrix itself
+                              (8-neighbour HEALPix pattern: fused lattice kernels; anything else: generic SpMM).
         """
         super().__init__(name="")
         logger.info("WARNING: This network assumes that everything concerning healpy is in NEST ordering...")
@@ -97,10 +107,19 @@ class HealpyGCNN(Sequential):
                 key = (current_nside, len(current_indices), int(current_indices[0]), int(current_indices[-1]),
                        int(np.sum(current_indices, dtype=np.int64)))
                 if key not in graph_cache:
-                    graph_cache[key] = SphereHealpix(
-                        subdivisions=current_nside, indexes=current_indices, nest=True, k=self.n_neighbors,
-                        lap_type="normalized",
-                    )
+                    if graph_builder is not None:
+                        graph_cache[key] = graph_builder(current_nside, current_indices, self.n_neighbors)
+                        L_user = getattr(graph_cache[key], "L", None)
+                        if L_user is None or tuple(L_user.shape) != (len(current_indices),) * 2:
+                            raise ValueError(
+                                f"graph_builder must return an object with a Laplacian .L of shape "
+                                f"({len(current_indices)}, {len(current_indices)}) for nside {current_nside}"
+                            )
+                    else:
+                        graph_cache[key] = SphereHealpix(
+                            subdivisions=current_nside, indexes=current_indices, nest=True, k=self.n_neighbors,
+                            lap_type="normalized",
+                        )
                 sphere = graph_cache[key]
                 current_L = sphere.L
                 if (max_batch_size is not None) and (current_Fin is not None):

@@ -245,3 +245,36 @@ def test_partitioned_model_rejects_incomplete_sibling_groups():
     assert len(idx) % 4 == 0
     with pytest.raises(ValueError):
         partition.PartitionedHealpyGCNN(8, idx, [hl.HealpyPool(p=1)], rank=0, world=1)
+
+
+def test_healpy_gcnn_takes_the_graphs_of_a_user_supplied_builder():
+    """the built-in graph builder is not pinned against the PyGSP fork the reference calls
+    (healpy_networks.py:110-118), so a checkpoint trained there needs its own Laplacians: `graph_builder` is called
+    once per (nside, index set) with the reference's arguments and its `.L` is what the layers get."""
+    import deepsphere
+    from deepsphere import healpy_layers as hl
+    from deepsphere.graph import SphereHealpix
+    from helpers import orc
+
+    calls = []
+
+    class Scaled:  # a builder whose L is recognisably not the built-in one
+        def __init__(self, nside, idx, k):
+            calls.append((nside, len(idx), k))
+            self.L = SphereHealpix(nside, indexes=idx, k=k).L * 0.5
+
+    nside = 8
+    idx = np.arange(12 * nside**2)
+    layers = [hl.HealpyChebyshev(K=3, Fout=4), hl.HealpyChebyshev(K=3, Fout=4), hl.HealpyPool(p=1),
+              hl.HealpyMonomial(K=2, Fout=2)]
+    model = deepsphere.HealpyGCNN(nside=nside, indices=idx, layers=layers, n_neighbors=20, graph_builder=Scaled)
+    assert calls == [(8, 768, 20), (4, 192, 20)]  # one graph per resolution, k passed through
+    ref = SphereHealpix(nside, k=20).L.tocoo()
+    got = model.layers_use[0]
+    dense = np.zeros((768, 768))
+    dense[got._L_indices[:, 0], got._L_indices[:, 1]] = got._L_values
+    expect, _ = orc.prepare_laplacian(ref.tocsr() * 0.5, 0.75)
+    assert np.abs(dense - expect.toarray()).max() <= 1e-6
+    with pytest.raises(ValueError, match="graph_builder must return"):
+        deepsphere.HealpyGCNN(nside=nside, indices=idx, layers=[hl.HealpyChebyshev(K=2, Fout=2)],
+                              graph_builder=lambda n, i, k: object())
