@@ -249,3 +249,49 @@ def test_native_halo_lists_reproduce_the_exchange_and_its_transpose():
             for s in p.reduce_slots[p.reduce_ptr[row]: p.reduce_ptr[row + 1]]:
                 g_own[:, row] += got[s]
         assert np.allclose(g_own, g_global[:, b0:e0], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_lattice_payload_of_every_rank_of_a_partition(world):
+    """The fused-kernel tables of a rank's EXTENDED row set (own rows + 4-hop halo): every tile is launched, the rows the
+    lattice cannot reproduce (within reach of a valence-3 vertex; their neighbourhoods are cut by the partition into patches
+    of different sizes) are listed exactly once in the patch tables ds_plan_attach_patches checks, and lattice rows +
+    irregular rows cover the local graph."""
+    from scipy import sparse
+
+    from deepsphere import lattice, partition, utils
+    from deepsphere.graph import SphereHealpix
+
+    nside = 32
+    M = 12 * nside**2
+    L = sparse.csr_matrix(SphereHealpix(nside, k=8).L)
+    Lt = sparse.csr_matrix(utils.rescale_L(L, lmax=1.9, scale=0.75).astype(np.float32))
+    sizes = set()
+    for rank in range(world):
+        rows = np.asarray(partition.HaloPlan(L, 4, rank, world, align=M // 48).ext)
+        pay = lattice.make_payload(sparse.csr_matrix(Lt[rows][:, rows]), nside, np.arange(M)[rows], 4)
+        assert pay is not None and pay["H"] == 4
+        wanted = pay["closure_rows"][pay["own_sub"]]
+        assert np.array_equal(np.sort(np.concatenate([pay["lattice_rows"], wanted])), np.arange(len(rows)))
+        pt = pay["patches"]
+        if pt is None:
+            assert len(wanted) == 0
+            continue
+        nr, no = np.diff(pt["row_ptr"]), np.diff(pt["own_ptr"])
+        sizes.update(nr.tolist())
+        assert pt["row_ptr"][-1] == len(pay["closure_rows"]) and pt["own_ptr"][-1] == len(wanted)
+        assert np.array_equal(np.sort(pt["rows"]), pay["closure_rows"]) and nr.max() <= 1024 and no.max() <= 45
+        got = np.concatenate([pt["rows"][pt["row_ptr"][p] + pt["own_local"][pt["own_ptr"][p]:pt["own_ptr"][p + 1]]]
+                              for p in range(pt["n_patches"])])
+        assert np.array_equal(np.sort(got), wanted)
+        for p in range(pt["n_patches"]):  # columns stay inside their patch; the ELL is L~ restricted to it
+            sl = slice(pt["row_ptr"][p], pt["row_ptr"][p + 1])
+            assert pt["ell_col"][sl].max() < nr[p] and pt["ell_col"][sl].min() >= -1
+            r = pt["rows"][sl]
+            dense = np.zeros((nr[p], nr[p]), np.float32)
+            rr, jj = np.nonzero(pt["ell_col"][sl] >= 0)
+            dense[rr, pt["ell_col"][sl][rr, jj]] = pt["ell_val"][sl][rr, jj]
+            assert np.array_equal(dense, Lt[rows[r]][:, rows[r]].toarray())
+    assert sizes and max(sizes) <= 189
+    if world == 2:
+        assert len(sizes) > 1  # whole (189 rows) and cut neighbourhoods both occur
